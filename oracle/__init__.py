@@ -1,0 +1,183 @@
+"""ctypes front end of the CPU oracle — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Only tests/, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline /
+``--impl reference`` leg may import this package (see oracle/oracle.cpp header).
+``liboracle.so`` is the restatement; ``_ref/libnaive_ref.so`` is the UNMODIFIED
+reference naive path (/root/reference/src/naive_simulation.cpp) compiled by
+oracle/Makefile.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+_REF = None
+
+u8p = np.ctypeslib.ndpointer(np.uint8, flags="C")
+u32p = np.ctypeslib.ndpointer(np.uint32, flags="C")
+i32p = np.ctypeslib.ndpointer(np.int32, flags="C")
+u64p = np.ctypeslib.ndpointer(np.uint64, flags="C")
+f32p = np.ctypeslib.ndpointer(np.float32, flags="C")
+f64p = np.ctypeslib.ndpointer(np.float64, flags="C")
+
+
+def build():
+    """Compile liboracle.so (and _ref/ when /root/reference is present)."""
+    subprocess.check_call(["make", "-s", "-C", _HERE, "all"])
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(path):
+            build()
+        L = C.CDLL(path)
+        L.orc_morton_keys.argtypes = [C.c_uint64, f32p, C.c_uint32, f32p, u64p]
+        L.orc_sort_keys.argtypes = [C.c_uint64, u64p, u64p, u32p]
+        L.orc_tree_build.argtypes = [C.c_uint64, u64p, f32p, C.c_uint32, C.c_uint32]
+        L.orc_tree_build.restype = C.c_void_p
+        L.orc_tree_free.argtypes = [C.c_void_p]
+        L.orc_tree_num_nodes.argtypes = [C.c_void_p]
+        L.orc_tree_num_nodes.restype = C.c_uint32
+        L.orc_tree_get.argtypes = [C.c_void_p] + [C.c_void_p] * 9
+        L.orc_traverse.argtypes = [C.c_void_p, C.c_float, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.orc_get_lists.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_traverse_rounds.argtypes = [C.c_void_p]
+        L.orc_traverse_rounds.restype = C.c_uint64
+        L.orc_direct_field.argtypes = [C.c_uint64, f32p, C.c_uint64, C.c_void_p, C.c_double, f64p, C.c_void_p, C.c_int]
+        L.orc_ncoef.argtypes = [C.c_uint32]
+        L.orc_ncoef.restype = C.c_uint32
+        L.orc_fmm_field.argtypes = [C.c_void_p, C.c_uint64, f32p, C.c_uint32, C.c_double, f64p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_naive_step_as_written.argtypes = [C.c_uint64, f32p, C.c_float, C.c_float, C.c_uint32]
+        L.orc_naive_step_as_written.restype = C.c_float
+        L.orc_direct_step.argtypes = [C.c_uint64, f32p, C.c_float, C.c_float, C.c_float, C.c_uint32, C.c_int, C.c_int]
+        L.orc_direct_step.restype = C.c_float
+        _LIB = L
+    return _LIB
+
+
+def ref_lib():
+    """The unmodified reference naive path, or None when it was never built."""
+    global _REF
+    if _REF is None:
+        path = os.path.join(_HERE, "_ref", "libnaive_ref.so")
+        if not os.path.exists(path):
+            if os.path.isdir("/root/reference/src"):
+                build()
+            else:
+                return None
+        R = C.CDLL(path)
+        R.ref_naive_run.argtypes = [C.c_uint64, f32p, C.c_float, C.c_float, C.c_uint32]
+        R.ref_naive_run.restype = C.c_float
+        R.ref_particle_size.restype = C.c_uint32
+        _REF = R
+    return _REF
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def morton_keys(pos, bounds):
+    pos = np.ascontiguousarray(pos, np.float32)
+    keys = np.empty(pos.shape[0], np.uint64)
+    lib().orc_morton_keys(pos.shape[0], pos, pos.shape[1], np.asarray(bounds, np.float32)[:3].copy(), keys)
+    return keys
+
+
+def sort_keys(keys):
+    keys = np.ascontiguousarray(keys, np.uint64)
+    out = np.empty_like(keys)
+    perm = np.empty(keys.shape[0], np.uint32)
+    lib().orc_sort_keys(keys.shape[0], keys, out, perm)
+    return out, perm
+
+
+class Tree:
+    """Reference-contract octree in DFS pre-order."""
+
+    def __init__(self, sorted_keys, bounds, capacity=8, max_depth=21):
+        sorted_keys = np.ascontiguousarray(sorted_keys, np.uint64)
+        self._h = lib().orc_tree_build(sorted_keys.shape[0], sorted_keys, np.asarray(bounds, np.float32)[:3].copy(),
+                                       capacity, max_depth)
+        m = self.num_nodes = lib().orc_tree_num_nodes(self._h)
+        self.depth = np.empty(m, np.uint32)
+        self.prefix = np.empty(m, np.uint64)
+        self.leaf_index = np.empty(m, np.uint32)
+        self.leaf_count = np.empty(m, np.uint32)
+        self.has_children = np.empty(m, np.uint8)
+        self.child_off = np.empty((m, 9), np.uint32)
+        self.parent_off = np.empty(m, np.int32)
+        self.sibling = np.empty(m, np.uint32)
+        self.geom = np.empty((m, 4), np.float32)
+        lib().orc_tree_get(self._h, *[_ptr(a) for a in (self.depth, self.prefix, self.leaf_index, self.leaf_count,
+                                                         self.has_children, self.child_off, self.parent_off,
+                                                         self.sibling, self.geom)])
+        self.m2l = self.p2p = None
+
+    def traverse(self, mac_ratio=0.5):
+        a, b = C.c_uint64(), C.c_uint64()
+        lib().orc_traverse(self._h, mac_ratio, C.byref(a), C.byref(b))
+        self.m2l = np.empty((a.value, 2), np.uint32)
+        self.p2p = np.empty((b.value, 2), np.uint32)
+        lib().orc_get_lists(self._h, _ptr(self.m2l), _ptr(self.p2p))
+        self.rounds = lib().orc_traverse_rounds(self._h)
+        return self.m2l, self.p2p
+
+    def fmm_field(self, posq_sorted, order, eps, want_phi=False, want_expansions=False):
+        posq = np.ascontiguousarray(posq_sorted, np.float32)
+        n = posq.shape[0]
+        g = np.empty((n, 3), np.float64)
+        phi = np.empty(n, np.float64) if want_phi else None
+        nc = lib().orc_ncoef(order)
+        M = np.empty((self.num_nodes, nc), np.float64) if want_expansions else None
+        L = np.empty((self.num_nodes, nc), np.float64) if want_expansions else None
+        lib().orc_fmm_field(self._h, n, posq, order, eps, g, _ptr(phi), _ptr(M), _ptr(L), 1)
+        out = [g]
+        if want_phi:
+            out.append(phi)
+        if want_expansions:
+            out += [M, L]
+        return out[0] if len(out) == 1 else tuple(out)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_tree_free(self._h)
+            self._h = None
+
+
+def direct_field(posq, targets=None, eps=0.01, want_phi=False, threads=None):
+    posq = np.ascontiguousarray(posq, np.float32)
+    if targets is not None:
+        targets = np.ascontiguousarray(targets, np.uint32)
+    nt = posq.shape[0] if targets is None else targets.shape[0]
+    g = np.empty((nt, 3), np.float64)
+    phi = np.empty(nt, np.float64) if want_phi else None
+    lib().orc_direct_field(posq.shape[0], posq, nt, _ptr(targets), eps, g, _ptr(phi), threads or os.cpu_count() or 1)
+    return (g, phi) if want_phi else g
+
+
+def naive_step_as_written(particles12, force_constant, dt, steps=1):
+    P = np.ascontiguousarray(particles12, np.float32).copy()
+    t = lib().orc_naive_step_as_written(P.shape[0], P, force_constant, dt, steps)
+    return P, t
+
+
+def direct_step(particles12, G=1.0, eps=0.01, dt=1e-3, steps=1, integrator=0, threads=None):
+    P = np.ascontiguousarray(particles12, np.float32).copy()
+    t = lib().orc_direct_step(P.shape[0], P, G, eps, dt, steps, integrator, threads or os.cpu_count() or 1)
+    return P, t
+
+
+def ref_naive_run(particles12, force_constant, dt, steps=1):
+    R = ref_lib()
+    if R is None:
+        raise RuntimeError("oracle/_ref/libnaive_ref.so is not built")
+    P = np.ascontiguousarray(particles12, np.float32).copy()
+    t = R.ref_naive_run(P.shape[0], P, force_constant, dt, steps)
+    return P, t
