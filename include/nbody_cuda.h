@@ -1,0 +1,170 @@
+/*
+ * nbody_cuda.h — C ABI of the B200-native FMM gravity solver.
+ *
+ * This is the drop-in boundary for the reference's simulation interface
+ * (duanebyer/nbody; citations relative to the reference tree):
+ *   - nbody::Simulation<TScalar,TVector>::step() / ::particles()
+ *         include/nbody/simulation.h:6-37
+ *   - OpenClSimulation(bounds, particles, timeStep, log)
+ *         include/nbody/open_cl_simulation.h:194-198, src/open_cl_simulation.cpp:15-51
+ *   - NaiveSimulation(particles, forceConstant, timeStep)
+ *         include/nbody/naive_simulation.h:25-33
+ * The reference defines no FFI; a maintainer binds these entry points from the
+ * C++ class in include/nbody/cuda_simulation.h.
+ *
+ * Plain C: pointers, sizes and POD structs only. No exception crosses this
+ * boundary: every call returns NBODY_OK (0) or an error code, and
+ * nbody_cuda_last_error() returns the message of the last failure on the
+ * calling thread. There is no CPU fallback: without a CUDA device (sm_100)
+ * nbody_cuda_create fails with NBODY_ERR_CUDA.
+ */
+#ifndef NBODY_CUDA_H_
+#define NBODY_CUDA_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NBODY_CUDA_ABI_VERSION 1
+
+/* Particle record at the boundary: layout of Simulation::Particle instantiated
+ * with the reference's 16-byte vector (include/nbody/simulation.h:16-35,
+ * include/nbody/device/types.h:53-74): 48 bytes, 16-byte aligned. */
+typedef struct nbody_particle {
+	float position[4];
+	float velocity[4];
+	float mass;
+	float charge;
+	float _pad[2];
+} nbody_particle;
+
+enum {
+	NBODY_OK = 0,
+	NBODY_ERR_INVALID = 1,   /* bad argument */
+	NBODY_ERR_CUDA = 2,      /* CUDA runtime failure / no device */
+	NBODY_ERR_CAPACITY = 3,  /* a device pool could not be grown */
+	NBODY_ERR_STATE = 4,     /* call not valid in the current state */
+	NBODY_ERR_COMM = 5       /* NCCL failure */
+};
+
+/* integrators */
+enum {
+	NBODY_KICK_DRIFT = 0,     /* v += a dt; x += v_new dt  (src/naive_simulation.cpp:28-42) */
+	NBODY_EXPLICIT_EULER = 1  /* v += a dt; x += v_old dt  (src/open_cl_simulation.cpp:602-607) */
+};
+
+/* flags */
+enum {
+	NBODY_FLAG_KEEP_LISTS = 1u,   /* keep interaction lists after step() for nbody_cuda_get_lists */
+	NBODY_FLAG_NO_INTEGRATE = 2u, /* step() computes accelerations only (state is re-ordered, not advanced) */
+	NBODY_FLAG_DIRECT = 4u        /* all-pairs direct sum instead of the FMM (validation / P2P microbenchmark) */
+};
+
+typedef struct nbody_cuda_config {
+	uint32_t abi_version;   /* NBODY_CUDA_ABI_VERSION */
+	float bounds[4];        /* root box [0,bounds) (src/open_cl_simulation.cpp:20,44; src/main.cpp:24) */
+	float time_step;        /* src/main.cpp:69 */
+	float force_constant;   /* naive convention: > 0 attracts like charges; default +1 */
+	float softening;        /* PARTICLE_RADIUS, src/field.cl:3-5; default 0.01 */
+	float mac_ratio;        /* NODE_APPROX_RATIO, src/interaction.cl:3-5; default 0.5 */
+	uint32_t leaf_capacity; /* octree node capacity, src/open_cl_simulation.cpp:41-47; default 8 */
+	uint32_t max_depth;     /* <= 21 */
+	uint32_t order;         /* expansion order P in {2,3,4}; default 4 */
+	uint32_t integrator;    /* NBODY_KICK_DRIFT (default) | NBODY_EXPLICIT_EULER */
+	uint32_t flags;
+	int32_t device;         /* CUDA device ordinal; -1 = current */
+	float pool_scale;       /* multiplies the initial sizes of the list pools; default 1 */
+	uint32_t _reserved[7];
+} nbody_cuda_config;
+
+/* per-step statistics (tracing/metrics hook) */
+typedef struct nbody_cuda_stats {
+	uint64_t n_particles;
+	uint64_t n_nodes, n_leaves, n_levels;
+	uint64_t m2l_entries;      /* (source, target-mask) entries in the grouped M2L lists */
+	uint64_t m2l_interactions; /* directed target<-source M2L evaluations */
+	uint64_t p2p_entries;      /* directed target-leaf <- source-leaf pairs */
+	uint64_t p2p_interactions; /* directed target-particle <- source-particle evaluations */
+	uint64_t near_entries;     /* total near-list entries written by the traversal */
+	uint64_t retries;          /* times a step was re-run after growing a pool */
+	uint64_t device_bytes;     /* bytes currently allocated on the device */
+	/* device time of the last step, milliseconds (CUDA events on the compute stream) */
+	float ms_total, ms_sort, ms_tree, ms_upsweep, ms_traverse, ms_m2l, ms_l2l, ms_leaf, ms_comm;
+	float _pad;
+} nbody_cuda_stats;
+
+typedef struct nbody_cuda_sim nbody_cuda_sim; /* opaque; single-threaded use */
+
+/* Fill cfg with the reference's constants (bounds 1,1,1; dt 0.001; G +1; eps 0.01;
+ * MAC 0.5; capacity 8; depth 21; order 4; kick-drift). */
+void nbody_cuda_default_config(nbody_cuda_config* cfg);
+
+/* Construct from host particles (copied; caller keeps ownership of `particles`).
+ * Replaces the OpenClSimulation ctor, src/open_cl_simulation.cpp:15-51. */
+int nbody_cuda_create(const nbody_cuda_config* cfg, const nbody_particle* particles, uint64_t n, nbody_cuda_sim** out);
+void nbody_cuda_destroy(nbody_cuda_sim* sim);
+
+/* Replace the whole particle state from host memory (same n). */
+int nbody_cuda_set_particles(nbody_cuda_sim* sim, const nbody_particle* particles, uint64_t n);
+
+/* Advance one time step; blocking; *time_out = new simulation time (FP32
+ * accumulation, src/open_cl_simulation.cpp:103-105). Replaces Simulation::step(). */
+int nbody_cuda_step(nbody_cuda_sim* sim, float* time_out);
+
+uint64_t nbody_cuda_num_particles(const nbody_cuda_sim* sim);
+
+/* Copy the particle state to host, in tree (Morton/DFS leaf) order like
+ * OpenClSimulation::particles(), src/open_cl_simulation.cpp:53-68 (input order
+ * before the first step). Replaces Simulation::particles(). */
+int nbody_cuda_get_particles(nbody_cuda_sim* sim, nbody_particle* out, uint64_t capacity);
+
+/* orig_index[i] = index in the constructor's array of the particle now at i. */
+int nbody_cuda_get_permutation(nbody_cuda_sim* sim, uint32_t* orig_index, uint64_t capacity);
+
+/* Accelerations of the last step, xyz per particle, same order as get_particles. */
+int nbody_cuda_get_accelerations(nbody_cuda_sim* sim, float* xyz, uint64_t capacity);
+
+/* ---- parity exports (tests only) ---------------------------------------- */
+/* Sorted Morton keys of the last step. */
+int nbody_cuda_get_keys(nbody_cuda_sim* sim, uint64_t* keys, uint64_t capacity);
+/* Octree of the last step in the reference's DFS pre-order node_t contract
+ * (include/nbody/device/types.h:124-141). Any pointer may be NULL.
+ * Call with all NULL to obtain *n_nodes. child_off9: 9 per node. geom4: centre xyz + dimensions.x */
+int nbody_cuda_get_tree(nbody_cuda_sim* sim, uint32_t* n_nodes, uint32_t capacity, uint32_t* depth, uint64_t* prefix,
+                        uint32_t* leaf_index, uint32_t* leaf_count, uint8_t* has_children, uint32_t* child_off9,
+                        int32_t* parent_off, uint32_t* sibling, float* geom4);
+/* Directed interaction lists of the last step (needs NBODY_FLAG_KEEP_LISTS), as
+ * (target, source) pairs of DFS node ids. Call with NULL to obtain the counts. */
+int nbody_cuda_get_lists(nbody_cuda_sim* sim, uint64_t* n_m2l, uint32_t* m2l_pairs, uint64_t* n_p2p, uint32_t* p2p_pairs);
+/* Multipole (M) and local (L) coefficients per DFS node, ncoef(order) floats each.
+ * M_m = sum q (y-c)^m/m!;  L_n = d^n Phi / dx^n at the cell centre (far field only). */
+int nbody_cuda_get_expansions(nbody_cuda_sim* sim, float* multipoles, float* locals, uint64_t capacity_floats);
+
+int nbody_cuda_get_stats(nbody_cuda_sim* sim, nbody_cuda_stats* stats);
+
+/* All-pairs softened field of `n_src` sources (x,y,z,q) on `n_tgt` targets (x,y,z,*)
+ * with the tiled P2P kernel; host buffers in, field (not yet scaled by G q/m) out.
+ * Used to validate large runs against direct summation on a target subsample and as
+ * the P2P FP32 microbenchmark; *ms = kernel time. */
+int nbody_cuda_direct_field(int device, const float* src_posq, uint64_t n_src, const float* tgt_pos4, uint64_t n_tgt,
+                            float softening, float* field_xyz, float* ms, uint32_t repeats);
+
+/* ---- multi-GPU (one process per GPU; Morton-range partition, NCCL) ------- */
+/* 128-byte NCCL unique id created on rank 0 and sent to the other ranks by the caller. */
+int nbody_cuda_comm_unique_id(uint8_t id[128]);
+/* Same as nbody_cuda_create, but this rank passes only ITS slice of the global
+ * particle set; `global_offset` is the index of its first particle. */
+int nbody_cuda_create_distributed(const nbody_cuda_config* cfg, const nbody_particle* local_particles, uint64_t n_local,
+                                  uint64_t n_global, uint64_t global_offset, int rank, int world, const uint8_t id[128],
+                                  nbody_cuda_sim** out);
+/* Range [first, first+count) of the tree-ordered particle array owned by this rank after the last step. */
+int nbody_cuda_owned_range(nbody_cuda_sim* sim, uint64_t* first, uint64_t* count);
+
+const char* nbody_cuda_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NBODY_CUDA_H_ */

@@ -1,0 +1,259 @@
+"""nbody_b200 — host-side mirror (Python) of the reference's simulation interface
+over the C ABI of the B200 FMM solver (include/nbody_cuda.h).
+
+``CudaSimulation`` has the reference's shape: construct from bounds, particles and
+a time step (OpenClSimulation ctor, include/nbody/open_cl_simulation.h:194-198),
+``step()`` returns the new time and ``particles()`` returns the state in tree order
+(include/nbody/simulation.h:33-34, src/open_cl_simulation.cpp:53-68). The C++ twin
+is include/nbody/cuda_simulation.h. There is no CPU path here: importing works
+anywhere, but constructing a simulation needs libnbody_cuda.so AND a B200.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnbody_cuda.so")
+PARTICLE_FLOATS = 12  # 48-byte AoS record: position[4], velocity[4], mass, charge, pad[2]
+
+KICK_DRIFT, EXPLICIT_EULER = 0, 1
+FLAG_KEEP_LISTS, FLAG_NO_INTEGRATE, FLAG_DIRECT = 1, 2, 4
+
+EXPORTED_SYMBOLS = [
+    "nbody_cuda_default_config", "nbody_cuda_create", "nbody_cuda_destroy", "nbody_cuda_set_particles", "nbody_cuda_step",
+    "nbody_cuda_num_particles", "nbody_cuda_get_particles", "nbody_cuda_get_permutation", "nbody_cuda_get_accelerations",
+    "nbody_cuda_get_keys", "nbody_cuda_get_tree", "nbody_cuda_get_lists", "nbody_cuda_get_expansions", "nbody_cuda_get_stats",
+    "nbody_cuda_direct_field", "nbody_cuda_comm_unique_id", "nbody_cuda_create_distributed", "nbody_cuda_owned_range",
+    "nbody_cuda_last_error",
+]
+
+
+class Config(C.Structure):
+    _fields_ = [("abi_version", C.c_uint32), ("bounds", C.c_float * 4), ("time_step", C.c_float), ("force_constant", C.c_float),
+                ("softening", C.c_float), ("mac_ratio", C.c_float), ("leaf_capacity", C.c_uint32), ("max_depth", C.c_uint32),
+                ("order", C.c_uint32), ("integrator", C.c_uint32), ("flags", C.c_uint32), ("device", C.c_int32),
+                ("pool_scale", C.c_float), ("_reserved", C.c_uint32 * 7)]
+
+
+class Stats(C.Structure):
+    _fields_ = [(k, C.c_uint64) for k in ("n_particles", "n_nodes", "n_leaves", "n_levels", "m2l_entries", "m2l_interactions",
+                                          "p2p_entries", "p2p_interactions", "near_entries", "retries", "device_bytes")] + \
+               [(k, C.c_float) for k in ("ms_total", "ms_sort", "ms_tree", "ms_upsweep", "ms_traverse", "ms_m2l", "ms_l2l",
+                                         "ms_leaf", "ms_comm", "_pad")]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if not k.startswith("_")}
+
+
+class NbodyCudaError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def build(force=False, verbose=False):
+    from . import build as _b
+    return _b.build(force=force, verbose=verbose)
+
+
+def load_library():
+    """Load libnbody_cuda.so; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NbodyCudaError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                             "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, u64, u32 = C.c_void_p, C.c_uint64, C.c_uint32
+    L.nbody_cuda_default_config.argtypes = [C.POINTER(Config)]
+    L.nbody_cuda_default_config.restype = None
+    L.nbody_cuda_create.argtypes = [C.POINTER(Config), vp, u64, C.POINTER(vp)]
+    L.nbody_cuda_destroy.argtypes = [vp]
+    L.nbody_cuda_destroy.restype = None
+    L.nbody_cuda_set_particles.argtypes = [vp, vp, u64]
+    L.nbody_cuda_step.argtypes = [vp, C.POINTER(C.c_float)]
+    L.nbody_cuda_num_particles.argtypes = [vp]
+    L.nbody_cuda_num_particles.restype = u64
+    L.nbody_cuda_get_particles.argtypes = [vp, vp, u64]
+    L.nbody_cuda_get_permutation.argtypes = [vp, vp, u64]
+    L.nbody_cuda_get_accelerations.argtypes = [vp, vp, u64]
+    L.nbody_cuda_get_keys.argtypes = [vp, vp, u64]
+    L.nbody_cuda_get_tree.argtypes = [vp, C.POINTER(u32), u32] + [vp] * 9
+    L.nbody_cuda_get_lists.argtypes = [vp, C.POINTER(u64), vp, C.POINTER(u64), vp]
+    L.nbody_cuda_get_expansions.argtypes = [vp, vp, vp, u64]
+    L.nbody_cuda_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.nbody_cuda_direct_field.argtypes = [C.c_int, vp, u64, vp, u64, C.c_float, vp, C.POINTER(C.c_float), u32]
+    L.nbody_cuda_comm_unique_id.argtypes = [vp]
+    L.nbody_cuda_create_distributed.argtypes = [C.POINTER(Config), vp, u64, u64, u64, C.c_int, C.c_int, vp, C.POINTER(vp)]
+    L.nbody_cuda_owned_range.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
+    L.nbody_cuda_last_error.restype = C.c_char_p
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise NbodyCudaError(f"nbody_cuda error {rc}: {load_library().nbody_cuda_last_error().decode()}")
+
+
+def default_config(**overrides):
+    cfg = Config()
+    load_library().nbody_cuda_default_config(C.byref(cfg))
+    for k, v in overrides.items():
+        if k == "bounds":
+            for i, b in enumerate(list(v)[:4]):
+                cfg.bounds[i] = b
+        elif not hasattr(cfg, k):
+            raise TypeError(f"unknown config field {k}")
+        else:
+            setattr(cfg, k, v)
+    return cfg
+
+
+def _ptr(a):
+    return C.c_void_p(a.ctypes.data) if a is not None else None
+
+
+def ncoef(order):
+    return (order + 1) * (order + 2) * (order + 3) // 6
+
+
+class CudaSimulation:
+    """``Simulation<float, float4>`` on one B200 (or one rank of a multi-GPU run).
+
+    particles: float32 [N, 12] boundary records (see nbody_b200.workloads)."""
+
+    def __init__(self, bounds, particles, time_step, log=None, *, _distributed=None, **config):
+        self._h = C.c_void_p()
+        self._lib = load_library()
+        particles = np.ascontiguousarray(particles, np.float32)
+        if particles.ndim != 2 or particles.shape[1] != PARTICLE_FLOATS:
+            raise ValueError("particles must be float32 [N, 12]")
+        self.config = default_config(bounds=list(bounds) + [0.0] * (4 - len(bounds)), time_step=time_step, **config)
+        self._log = log
+        if _distributed is None:
+            _check(self._lib.nbody_cuda_create(C.byref(self.config), _ptr(particles), particles.shape[0], C.byref(self._h)))
+        else:
+            d = _distributed
+            uid = np.frombuffer(d["unique_id"], np.uint8).copy()
+            _check(self._lib.nbody_cuda_create_distributed(C.byref(self.config), _ptr(particles), particles.shape[0],
+                                                           d["n_global"], d["global_offset"], d["rank"], d["world"], _ptr(uid),
+                                                           C.byref(self._h)))
+        self.n = int(self._lib.nbody_cuda_num_particles(self._h))
+        self.time = 0.0
+
+    # --- the reference interface -------------------------------------------------
+    def step(self):
+        if self._log is not None:
+            self._log.write(f"Starting a new step (t={self.time}).\n")
+        t = C.c_float()
+        _check(self._lib.nbody_cuda_step(self._h, C.byref(t)))
+        self.time = t.value
+        if self._log is not None:
+            self._log.write("Step finished.\n")
+        return t.value
+
+    def particles(self, out=None):
+        if out is None:
+            out = np.empty((self.n, PARTICLE_FLOATS), np.float32)
+        _check(self._lib.nbody_cuda_get_particles(self._h, _ptr(out), out.shape[0]))
+        return out
+
+    # --- extras --------------------------------------------------------------------
+    def set_particles(self, particles):
+        particles = np.ascontiguousarray(particles, np.float32)
+        _check(self._lib.nbody_cuda_set_particles(self._h, _ptr(particles), particles.shape[0]))
+
+    def set_particles_ptr(self, ptr, n):
+        _check(self._lib.nbody_cuda_set_particles(self._h, C.c_void_p(ptr), n))
+
+    def particles_into_ptr(self, ptr, n):
+        _check(self._lib.nbody_cuda_get_particles(self._h, C.c_void_p(ptr), n))
+
+    def permutation(self):
+        out = np.empty(self.n, np.uint32)
+        _check(self._lib.nbody_cuda_get_permutation(self._h, _ptr(out), self.n))
+        return out
+
+    def accelerations(self):
+        out = np.empty((self.n, 3), np.float32)
+        _check(self._lib.nbody_cuda_get_accelerations(self._h, _ptr(out), self.n))
+        return out
+
+    def keys(self):
+        out = np.empty(self.n, np.uint64)
+        _check(self._lib.nbody_cuda_get_keys(self._h, _ptr(out), self.n))
+        return out
+
+    def tree(self):
+        m = C.c_uint32()
+        _check(self._lib.nbody_cuda_get_tree(self._h, C.byref(m), 0, *([None] * 9)))
+        m = m.value
+        t = {"depth": np.empty(m, np.uint32), "prefix": np.empty(m, np.uint64), "leaf_index": np.empty(m, np.uint32),
+             "leaf_count": np.empty(m, np.uint32), "has_children": np.empty(m, np.uint8), "child_off": np.empty((m, 9), np.uint32),
+             "parent_off": np.empty(m, np.int32), "sibling": np.empty(m, np.uint32), "geom": np.empty((m, 4), np.float32)}
+        mm = C.c_uint32()
+        _check(self._lib.nbody_cuda_get_tree(self._h, C.byref(mm), m, *[_ptr(t[k]) for k in
+                                             ("depth", "prefix", "leaf_index", "leaf_count", "has_children", "child_off",
+                                              "parent_off", "sibling", "geom")]))
+        return t
+
+    def lists(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        _check(self._lib.nbody_cuda_get_lists(self._h, C.byref(a), None, C.byref(b), None))
+        m2l = np.empty((a.value, 2), np.uint32)
+        p2p = np.empty((b.value, 2), np.uint32)
+        _check(self._lib.nbody_cuda_get_lists(self._h, C.byref(a), _ptr(m2l), C.byref(b), _ptr(p2p)))
+        return m2l, p2p
+
+    def expansions(self):
+        m = C.c_uint32()
+        _check(self._lib.nbody_cuda_get_tree(self._h, C.byref(m), 0, *([None] * 9)))
+        nc = ncoef(self.config.order)
+        M = np.empty((m.value, nc), np.float32)
+        L = np.empty((m.value, nc), np.float32)
+        _check(self._lib.nbody_cuda_get_expansions(self._h, _ptr(M), _ptr(L), M.size))
+        return M, L
+
+    def stats(self):
+        st = Stats()
+        _check(self._lib.nbody_cuda_get_stats(self._h, C.byref(st)))
+        return st.as_dict()
+
+    def owned_range(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        _check(self._lib.nbody_cuda_owned_range(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.nbody_cuda_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def direct_field(src_posq, tgt_pos4, softening=0.01, device=-1, repeats=1):
+    """All-pairs field of sources (x,y,z,q) on targets (x,y,z,*) with the tiled P2P kernel.
+    Returns (field [n_tgt,3] float32, kernel milliseconds)."""
+    L = load_library()
+    src = np.ascontiguousarray(src_posq, np.float32)
+    tgt = np.ascontiguousarray(tgt_pos4, np.float32)
+    out = np.empty((tgt.shape[0], 3), np.float32)
+    ms = C.c_float()
+    _check(L.nbody_cuda_direct_field(device, _ptr(src), src.shape[0], _ptr(tgt), tgt.shape[0], softening, _ptr(out), C.byref(ms),
+                                     repeats))
+    return out, ms.value
+
+
+def comm_unique_id():
+    uid = np.zeros(128, np.uint8)
+    _check(load_library().nbody_cuda_comm_unique_id(_ptr(uid)))
+    return uid.tobytes()

@@ -1,0 +1,148 @@
+// Shared declarations of the B200 FMM gravity solver (sm_100a only).
+// HBM layout, control block and the launch functions of each stage.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include "../../include/nbody_cuda.h"
+#include "expansion.cuh"
+
+namespace nbody {
+
+constexpr int kMaxDepth = 21;           // 21 bits per dimension, 63-bit keys
+constexpr int kNumLevels = kMaxDepth + 1;
+constexpr int kNumSM = 148;             // B200: grids are sized in multiples of this
+constexpr int kScanBlocks = 592;        // 4 * 148 tiles per level scan (<= 1024)
+
+// status bits raised by kernels when a pool is too small; the host grows the pool and re-runs the step
+enum : uint32_t {
+	kOvfNodes = 1u, kOvfNear = 2u, kOvfP2P = 4u, kOvfM2L = 8u, kOvfSeg = 16u, kOvfGroups = 32u, kOvfItems = 64u
+};
+
+// One work item of the traversal / of the M2L kernel: `nt` sibling targets
+// (8 = the children of one parent, 1 = a carried childless node) that share one
+// candidate list.
+struct Group {
+	uint32_t first;      // first target node id (level-major)
+	uint32_t nt;         // 8 or 1
+	uint32_t list_off;   // traversal: offset of the shared near list (in the previous level's pool);  M2L: offset into the m2l pool
+	uint32_t list_cnt;   // entries in that list
+	uint32_t n_cand;     // traversal: number of candidate slots the near list expands to (8 per split entry, 1 per childless)
+	uint32_t _pad[3];
+};
+
+struct Segment { uint32_t off, cnt, next; };  // one piece of a target leaf's P2P source list (chained)
+
+// Device-resident control block: everything the host would otherwise have to read back between launches.
+struct Ctrl {
+	uint32_t level_off[kNumLevels + 2];  // nodes of level l are [level_off[l], level_off[l+1])
+	uint32_t n_nodes;
+	uint32_t status;
+	uint32_t scan_ticket;
+	uint32_t n_levels;
+	uint32_t gq_count[2];                // traversal group queues, ping-pong by round
+	uint32_t items_count[2];             // M2L work items: [0] = 8-target groups, [1] = single targets
+	uint32_t seg_cursor;
+	uint32_t _pad0;
+	unsigned long long near_cursor[2];   // near-list pools, ping-pong by round
+	unsigned long long p2p_cursor;
+	unsigned long long m2l_cursor;
+	unsigned long long stat_m2l_inter, stat_p2p_entries, stat_p2p_inter, stat_near, stat_leaves;
+	uint32_t work_ticket[4];             // dynamic work distribution of the persistent kernels
+};
+
+struct Pools {
+	uint32_t* near[2] = {nullptr, nullptr};
+	uint64_t near_cap = 0;
+	uint32_t* p2p = nullptr;
+	uint64_t p2p_cap = 0;
+	uint32_t* m2l_id = nullptr;
+	uint8_t* m2l_mask = nullptr;
+	uint64_t m2l_cap = 0;
+	Segment* seg = nullptr;
+	uint32_t seg_cap = 0;
+	Group* gq[2] = {nullptr, nullptr};
+	uint32_t gq_cap = 0;
+	Group* items[2] = {nullptr, nullptr};
+	uint32_t items_cap = 0;
+};
+
+struct Comm;  // NCCL state (comm.cu)
+
+struct Sim {
+	nbody_cuda_config cfg;
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	uint64_t n = 0;
+	float time = 0.0f;
+	uint64_t steps_done = 0;
+	int nc_stride = 0;  // floats per multipole/local record
+
+	// particle state, SoA of two float4 planes; [0] = state (order of the last step), [1] = sorted scratch of the current step
+	float4* posq[2] = {nullptr, nullptr};  // x y z charge
+	float4* velm[2] = {nullptr, nullptr};  // vx vy vz mass
+	uint32_t* orig[2] = {nullptr, nullptr};
+	float4* acc = nullptr;                 // ax ay az (w unused), order of the last step
+	uint64_t* keys[2] = {nullptr, nullptr};
+	uint32_t* idx[2] = {nullptr, nullptr};
+	void* sort_tmp = nullptr;
+	size_t sort_tmp_bytes = 0;
+	nbody_particle* aos_dev = nullptr;     // staging for AoS48 <-> SoA conversion
+	nbody_particle* aos_host = nullptr;    // pinned
+
+	// octree, level-major; the 8 children of a split node are contiguous
+	uint32_t max_nodes = 0;
+	float4* geom = nullptr;      // centre xyz, dimensions.x
+	uint2* info = nullptr;       // {first child (0 = childless), particle count}
+	uint32_t* nbegin = nullptr;  // first particle
+	uint32_t* nparent = nullptr;
+	uint64_t* nkey = nullptr;    // key prefix
+	float* M = nullptr;          // multipoles, nc_stride floats per node
+	float* L = nullptr;          // locals (pure derivatives), nc_stride floats per node
+	uint2* near_ref = nullptr;   // per target node: {offset, count} of its near list in the current round's pool
+	uint32_t* p2p_head = nullptr;  // per node: head of its P2P segment chain (0xffffffff = none)
+	uint32_t* scan_sums = nullptr; // kScanBlocks + 1
+
+	Pools pools;
+	Ctrl* ctrl = nullptr;        // device
+	Ctrl* ctrl_host = nullptr;   // pinned copy read after each step
+	Comm* comm = nullptr;
+	// distributed: this rank's slice of the tree-ordered particle array
+	uint64_t own_first = 0, own_count = 0;
+
+	nbody_cuda_stats stats{};
+	cudaEvent_t ev[12] = {};
+	uint64_t device_bytes = 0;
+	bool lists_valid = false;
+};
+
+// ---- error plumbing ---------------------------------------------------------
+void set_error(const std::string& msg);
+#define NB_CUDA_CHECK(expr)                                                                         \
+	do {                                                                                               \
+		cudaError_t _e = (expr);                                                                         \
+		if (_e != cudaSuccess) {                                                                         \
+			::nbody::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"); \
+			return NBODY_ERR_CUDA;                                                                         \
+		}                                                                                                \
+	} while (0)
+
+// ---- stage launchers (each enqueues on sim.stream; no host synchronisation) --
+void launch_import(Sim& s, const nbody_particle* aos_dev, uint64_t n);                 // AoS48 -> SoA state
+void launch_export(Sim& s, nbody_particle* aos_dev, uint64_t n);                       // SoA state -> AoS48
+int launch_keys_sort_permute(Sim& s);                                                 // stage 1a: keys, radix sort, gather
+void launch_tree_build(Sim& s);                                                        // stage 1b: linear octree, level-major
+void launch_upsweep(Sim& s);                                                           // stage 2: P2M + M2M
+void launch_traversal(Sim& s);                                                         // stage 3: dual-tree traversal -> lists
+void launch_m2l(Sim& s);                                                               // stage 4a: M2L over grouped lists
+void launch_l2l(Sim& s);                                                               // stage 4b: L2L downsweep
+void launch_leaf(Sim& s);                                                              // stage 5: P2P + L2P + integrator
+void launch_direct(Sim& s);                                                            // all-pairs P2P + integrator (validation)
+int direct_field_device(const float4* src, uint64_t n_src, const float4* tgt, uint64_t n_tgt, float eps2, float4* out, cudaStream_t st);
+
+// device helpers shared by several translation units
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+
+}  // namespace nbody

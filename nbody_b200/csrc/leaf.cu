@@ -1,0 +1,285 @@
+// Stage 5: near field. One warp per target leaf: the leaf's P2P source list is
+// expanded into a per-warp shared-memory tile of source particles (x,y,z,q) and the
+// warp evaluates T targets x S source slices (T*S = 32, T = leaf population rounded
+// up to a power of two) so that small leaves still fill the warp. The epilogue adds
+// the far field (L2P) and applies the integrator, so accelerations never make a
+// round trip through a per-interaction buffer.
+//
+// Replaces src/field.cl:49-148 (8x8 work-group per leaf interaction writing one
+// 16-byte slot per (leaf, partner leaf, interaction)), src/force.cl:21-81 (slot
+// reductions), the CPU prefix sums at src/open_cl_simulation.cpp:371-417 and the
+// serial host integration loop at :572-616.
+// Field of source j on target i: q_j (x_j - x_i) / (|x_j - x_i|^2 + eps^2)^(3/2)
+// (src/field.cl:17-32 with FORCE_CONSTANT folded into force_constant).
+// 20 flop per evaluation by the SURVEY 8d convention: 3 FADD, 3 FFMA, MUFU.RSQ (2), 3 FMUL, 3 FFMA.
+#include "common.cuh"
+
+namespace nbody {
+
+constexpr int kLeafWarps = 8;
+constexpr int kLeafBuf = 256;  // source particles per warp tile (4 KB)
+
+template <bool SOFT>
+__device__ __forceinline__ void p2p_interact(const float4& s, float tx, float ty, float tz, float eps2, float& ax, float& ay, float& az) {
+	const float dx = s.x - tx, dy = s.y - ty, dz = s.z - tz;
+	const float r2 = fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, eps2)));
+	float inv = rsqrtf(r2);
+	if (!SOFT) inv = r2 > 0.0f ? inv : 0.0f;  // eps = 0: coincident points (and i == j) exert no force
+	const float inv2 = inv * inv;
+	const float w = (s.w * inv) * inv2;
+	ax = fmaf(w, dx, ax);
+	ay = fmaf(w, dy, ay);
+	az = fmaf(w, dz, az);
+}
+
+struct LeafArgs {
+	const Ctrl* c;
+	const float4* posq;      // sorted positions of this step (sources and targets)
+	const float4* velm_in;   // sorted velocities
+	float4* posq_out;        // new state
+	float4* velm_out;
+	float4* acc;
+	const float4* geom;
+	const uint2* info;
+	const uint32_t* nbegin;
+	const uint32_t* p2p_head;
+	const Segment* seg;
+	const uint32_t* p2p;
+	const float* L;
+	float eps2, G, dt;
+	int integrator, no_integrate;
+	uint32_t own_first, own_end;  // this rank's slice of the tree-ordered particle array
+	unsigned long long* stat_inter;
+	unsigned long long* stat_leaves;
+};
+
+template <bool SOFT>
+__device__ __forceinline__ void tile_compute(const float4* buf, uint32_t fill, unsigned sl, unsigned S, float tx, float ty, float tz,
+                                             float eps2, float& ax, float& ay, float& az) {
+	__syncwarp();
+	uint32_t j = sl;
+	for (; j + 3 * S < fill; j += 4 * S) {
+		const float4 s0 = buf[j], s1 = buf[j + S], s2 = buf[j + 2 * S], s3 = buf[j + 3 * S];
+		p2p_interact<SOFT>(s0, tx, ty, tz, eps2, ax, ay, az);
+		p2p_interact<SOFT>(s1, tx, ty, tz, eps2, ax, ay, az);
+		p2p_interact<SOFT>(s2, tx, ty, tz, eps2, ax, ay, az);
+		p2p_interact<SOFT>(s3, tx, ty, tz, eps2, ax, ay, az);
+	}
+	for (; j < fill; j += S) p2p_interact<SOFT>(buf[j], tx, ty, tz, eps2, ax, ay, az);
+	__syncwarp();
+}
+
+template <int P, bool SOFT>
+__global__ void __launch_bounds__(kLeafWarps * 32) k_leaf(const LeafArgs a) {
+	using E = Expansion<P>;
+	constexpr int STRIDE = coef_stride(P);
+	__shared__ float4 sbuf[kLeafWarps][kLeafBuf];
+	const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+	float4* buf = sbuf[w];
+	if (a.c->status) return;  // a pool overflowed: the host grows it and re-runs the step; leave the state untouched
+	const uint32_t n_nodes = a.c->n_nodes;
+	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+	unsigned long long inter = 0, leaves = 0;
+	for (uint32_t node = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; node < n_nodes; node += warps) {
+		const uint2 nf = a.info[node];
+		if (nf.x != 0u || nf.y == 0u) continue;  // internal or empty
+		const uint32_t b = a.nbegin[node];
+		if (b < a.own_first || b >= a.own_end) continue;  // another rank's leaf
+		++leaves;
+		const uint32_t nt = nf.y;
+		const float4 g = a.geom[node];
+		for (uint32_t t0 = 0; t0 < nt; t0 += 32) {
+			const uint32_t ntc = min(32u, nt - t0);
+			const unsigned T = ntc <= 1 ? 1u : 1u << (32 - __clz(ntc - 1));  // power of two >= ntc
+			const unsigned S = 32u / T;
+			const unsigned t = lane & (T - 1u), sl = lane / T;
+			const bool has_t = t < ntc;
+			float4 tp = make_float4(0.f, 0.f, 0.f, 0.f);
+			if (has_t) tp = a.posq[b + t0 + t];
+			float ax = 0.f, ay = 0.f, az = 0.f;
+			uint32_t fill = 0;
+			unsigned long long nsrc = 0;
+			for (uint32_t si = a.p2p_head[node]; si != 0xffffffffu;) {
+				const Segment sg = a.seg[si];
+				si = sg.next;
+				for (uint32_t e0 = 0; e0 < sg.cnt; e0 += 32) {
+					uint32_t sb = 0, sc = 0;
+					if (e0 + lane < sg.cnt) {
+						const uint32_t src = a.p2p[sg.off + e0 + lane];
+						sb = a.nbegin[src];
+						sc = a.info[src].y;
+					}
+					unsigned pending = __ballot_sync(0xffffffffu, sc > 0);
+					while (pending) {
+						const uint32_t v = (pending >> lane & 1u) ? sc : 0u;
+						uint32_t inc = v;
+#pragma unroll
+						for (int d = 1; d < 32; d <<= 1) {
+							const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d);
+							if (lane >= (unsigned) d) inc += u;
+						}
+						const bool fits = v > 0 && fill + inc <= (uint32_t) kLeafBuf;
+						const unsigned fm = __ballot_sync(0xffffffffu, fits);
+						if (fm == 0) {
+							if (fill > 0) {  // tile full: consume it and retry
+								tile_compute<SOFT>(buf, fill, sl, S, tp.x, tp.y, tp.z, a.eps2, ax, ay, az);
+								nsrc += fill; fill = 0;
+								continue;
+							}
+							// a single source leaf larger than the tile (only possible at max depth): stream it
+							const int first = __ffs(pending) - 1;
+							const uint32_t fb = __shfl_sync(0xffffffffu, sb, first), fc = __shfl_sync(0xffffffffu, sc, first);
+							for (uint32_t q0 = 0; q0 < fc; q0 += kLeafBuf) {
+								const uint32_t m = min((uint32_t) kLeafBuf, fc - q0);
+								for (uint32_t q = lane; q < m; q += 32) buf[q] = a.posq[fb + q0 + q];
+								tile_compute<SOFT>(buf, m, sl, S, tp.x, tp.y, tp.z, a.eps2, ax, ay, az);
+							}
+							nsrc += fc;
+							pending &= ~(1u << first);
+							continue;
+						}
+						const uint32_t maxc = __reduce_max_sync(0xffffffffu, fits ? v : 0u);
+						const uint32_t dst = fill + inc - v;
+						for (uint32_t k = 0; k < maxc; ++k)
+							if (fits && k < v) buf[dst + k] = a.posq[sb + k];
+						const int last = 31 - __clz(fm);
+						fill += __shfl_sync(0xffffffffu, inc, last);
+						pending &= ~fm;
+					}
+				}
+			}
+			if (fill) { tile_compute<SOFT>(buf, fill, sl, S, tp.x, tp.y, tp.z, a.eps2, ax, ay, az); nsrc += fill; }
+			for (unsigned d = T; d < 32u; d <<= 1) {
+				ax += __shfl_xor_sync(0xffffffffu, ax, d);
+				ay += __shfl_xor_sync(0xffffffffu, ay, d);
+				az += __shfl_xor_sync(0xffffffffu, az, d);
+			}
+			if (lane == 0) inter += nsrc * ntc;
+			if (sl == 0 && has_t) {
+				// far field: L2P of this leaf's local expansion
+				float l[E::NC];
+				const float4* L4 = reinterpret_cast<const float4*>(a.L + (size_t) node * STRIDE);
+#pragma unroll
+				for (int q = 0; q < (E::NC + 3) / 4; ++q) {
+					const float4 v = L4[q];
+					l[4 * q] = v.x;
+					if (4 * q + 1 < E::NC) l[4 * q + 1] = v.y;
+					if (4 * q + 2 < E::NC) l[4 * q + 2] = v.z;
+					if (4 * q + 3 < E::NC) l[4 * q + 3] = v.w;
+				}
+				float fx, fy, fz;
+				E::l2p(l, tp.x - g.x, tp.y - g.y, tp.z - g.z, fx, fy, fz);
+				const uint32_t i = b + t0 + t;
+				const float4 vm = a.velm_in[i];
+				const float sc = a.G * tp.w / vm.w;  // a = G q/m * field (src/force.cl:4-10, src/open_cl_simulation.cpp:602-604)
+				const float axx = sc * (ax + fx), ayy = sc * (ay + fy), azz = sc * (az + fz);
+				a.acc[i] = make_float4(axx, ayy, azz, 0.f);
+				if (!a.no_integrate) {
+					const float vx = fmaf(axx, a.dt, vm.x), vy = fmaf(ayy, a.dt, vm.y), vz = fmaf(azz, a.dt, vm.z);
+					const float ux = a.integrator == NBODY_KICK_DRIFT ? vx : vm.x, uy = a.integrator == NBODY_KICK_DRIFT ? vy : vm.y,
+					            uz = a.integrator == NBODY_KICK_DRIFT ? vz : vm.z;
+					a.posq_out[i] = make_float4(fmaf(ux, a.dt, tp.x), fmaf(uy, a.dt, tp.y), fmaf(uz, a.dt, tp.z), tp.w);
+					a.velm_out[i] = make_float4(vx, vy, vz, vm.w);
+				} else {
+					a.posq_out[i] = tp;
+					a.velm_out[i] = vm;
+				}
+			}
+		}
+	}
+	if (lane == 0 && leaves) { atomicAdd(a.stat_inter, inter); atomicAdd(a.stat_leaves, leaves); }
+}
+
+template <int P>
+static void leaf_t(Sim& s, const LeafArgs& a) {
+	if (s.cfg.softening > 0.0f) k_leaf<P, true><<<kNumSM * 6, kLeafWarps * 32, 0, s.stream>>>(a);
+	else k_leaf<P, false><<<kNumSM * 6, kLeafWarps * 32, 0, s.stream>>>(a);
+}
+
+void launch_leaf(Sim& s) {
+	LeafArgs a{};
+	a.c = s.ctrl; a.posq = s.posq[1]; a.velm_in = s.velm[1]; a.posq_out = s.posq[0]; a.velm_out = s.velm[0]; a.acc = s.acc;
+	a.geom = s.geom; a.info = s.info; a.nbegin = s.nbegin; a.p2p_head = s.p2p_head; a.seg = s.pools.seg; a.p2p = s.pools.p2p; a.L = s.L;
+	a.eps2 = s.cfg.softening * s.cfg.softening; a.G = s.cfg.force_constant; a.dt = s.cfg.time_step;
+	a.integrator = (int) s.cfg.integrator; a.no_integrate = (s.cfg.flags & NBODY_FLAG_NO_INTEGRATE) ? 1 : 0;
+	a.own_first = (uint32_t) s.own_first; a.own_end = (uint32_t) (s.own_first + s.own_count);
+	a.stat_inter = &s.ctrl->stat_p2p_inter; a.stat_leaves = &s.ctrl->stat_leaves;
+	switch (s.cfg.order) {
+		case 2: leaf_t<2>(s, a); break;
+		case 3: leaf_t<3>(s, a); break;
+		default: leaf_t<4>(s, a); break;
+	}
+}
+
+// ---------------------------------------------------------------------------
+// All-pairs tiled P2P (no tree): validation against direct summation on large N
+// and the P2P FP32 microbenchmark. Each thread owns 2 targets; sources stream
+// through a double-buffered shared-memory tile.
+// ---------------------------------------------------------------------------
+constexpr int kDirThreads = 256;
+constexpr int kDirTile = 512;
+
+template <bool SOFT>
+__global__ void __launch_bounds__(kDirThreads) k_direct(const float4* __restrict__ src, uint64_t n_src, const float4* __restrict__ tgt,
+                                                        uint64_t n_tgt, float eps2, float4* __restrict__ out) {
+	__shared__ float4 tile[kDirTile];
+	const uint64_t i0 = (uint64_t) blockIdx.x * (2 * kDirThreads) + threadIdx.x, i1 = i0 + kDirThreads;
+	float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0;
+	if (i0 < n_tgt) p0 = tgt[i0];
+	if (i1 < n_tgt) p1 = tgt[i1];
+	float ax0 = 0.f, ay0 = 0.f, az0 = 0.f, ax1 = 0.f, ay1 = 0.f, az1 = 0.f;
+	for (uint64_t base = 0; base < n_src; base += kDirTile) {
+		__syncthreads();
+		for (int q = threadIdx.x; q < kDirTile; q += kDirThreads) {
+			const uint64_t j = base + q;
+			tile[q] = j < n_src ? src[j] : make_float4(0.f, 0.f, 0.f, 0.f);  // q = 0 padding exerts no force
+		}
+		__syncthreads();
+#pragma unroll 8
+		for (int q = 0; q < kDirTile; ++q) {
+			const float4 s = tile[q];
+			p2p_interact<SOFT>(s, p0.x, p0.y, p0.z, eps2, ax0, ay0, az0);
+			p2p_interact<SOFT>(s, p1.x, p1.y, p1.z, eps2, ax1, ay1, az1);
+		}
+	}
+	if (i0 < n_tgt) out[i0] = make_float4(ax0, ay0, az0, 0.f);
+	if (i1 < n_tgt) out[i1] = make_float4(ax1, ay1, az1, 0.f);
+}
+
+int direct_field_device(const float4* src, uint64_t n_src, const float4* tgt, uint64_t n_tgt, float eps2, float4* out, cudaStream_t st) {
+	const unsigned grid = (unsigned) ((n_tgt + 2 * kDirThreads - 1) / (2 * kDirThreads));
+	if (grid == 0) return NBODY_OK;
+	if (eps2 > 0.0f) k_direct<true><<<grid, kDirThreads, 0, st>>>(src, n_src, tgt, n_tgt, eps2, out);
+	else k_direct<false><<<grid, kDirThreads, 0, st>>>(src, n_src, tgt, n_tgt, eps2, out);
+	return NBODY_OK;
+}
+
+__global__ void k_direct_finish(uint64_t n, const float4* __restrict__ field, const float4* __restrict__ posq, const float4* __restrict__ velm,
+                                float4* __restrict__ posq_out, float4* __restrict__ velm_out, float4* __restrict__ acc, float G, float dt,
+                                int integrator, int no_integrate) {
+	for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
+		const float4 f = field[i], p = posq[i], vm = velm[i];
+		const float sc = G * p.w / vm.w;
+		const float ax = sc * f.x, ay = sc * f.y, az = sc * f.z;
+		acc[i] = make_float4(ax, ay, az, 0.f);
+		if (no_integrate) { posq_out[i] = p; velm_out[i] = vm; continue; }
+		const float vx = fmaf(ax, dt, vm.x), vy = fmaf(ay, dt, vm.y), vz = fmaf(az, dt, vm.z);
+		const bool kd = integrator == NBODY_KICK_DRIFT;
+		posq_out[i] = make_float4(fmaf(kd ? vx : vm.x, dt, p.x), fmaf(kd ? vy : vm.y, dt, p.y), fmaf(kd ? vz : vm.z, dt, p.z), p.w);
+		velm_out[i] = make_float4(vx, vy, vz, vm.w);
+	}
+}
+
+// NBODY_FLAG_DIRECT: the whole step by direct summation (state is still Morton-sorted first,
+// so particles() keeps the same order contract). Field staged in `acc`, then finished in place.
+void launch_direct(Sim& s) {
+	const float eps2 = s.cfg.softening * s.cfg.softening;
+	float4* field = s.acc;  // staged in place: k_direct_finish reads field[i] before it writes acc[i]
+	direct_field_device(s.posq[1], s.n, s.posq[1], s.n, eps2, field, s.stream);
+	const uint64_t want = (s.n + 255) / 256;
+	k_direct_finish<<<(unsigned) (want > kNumSM * 16 ? kNumSM * 16 : (want ? want : 1)), 256, 0, s.stream>>>(
+	    s.n, field, s.posq[1], s.velm[1], s.posq[0], s.velm[0], s.acc, s.cfg.force_constant, s.cfg.time_step, (int) s.cfg.integrator,
+	    (s.cfg.flags & NBODY_FLAG_NO_INTEGRATE) ? 1 : 0);
+}
+
+}  // namespace nbody

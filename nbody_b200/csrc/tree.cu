@@ -1,0 +1,269 @@
+// Stage 1: Morton keys, device radix sort, state permutation and the linear
+// octree, all on the device with no host round trip.
+//
+// Replaces the reference's host-side glade::Orthtree build and per-step
+// re-bucketing (src/open_cl_simulation.cpp:15-51,108-124) and the per-step
+// upload of the whole leaf/node arrays (:128-135). The octree obeys the contract
+// the reference consumes (split above `capacity`, all 8 children
+// exist, contiguous particle range per node) but is stored LEVEL-MAJOR with the
+// 8 children of a node contiguous, which is what the traversal / M2L kernels
+// want; nbody_cuda_get_tree() re-emits it in the reference's DFS pre-order.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "common.cuh"
+
+namespace nbody {
+
+// ---------------------------------------------------------------------------
+// AoS48 boundary records <-> SoA float4 planes
+// ---------------------------------------------------------------------------
+__global__ void k_import(uint64_t n, const float4* __restrict__ aos, float4* __restrict__ posq, float4* __restrict__ velm,
+                         uint32_t* __restrict__ orig) {
+	for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
+		const float4 p = aos[3 * i], v = aos[3 * i + 1], mq = aos[3 * i + 2];
+		posq[i] = make_float4(p.x, p.y, p.z, mq.y);
+		velm[i] = make_float4(v.x, v.y, v.z, mq.x);
+		orig[i] = (uint32_t) i;
+	}
+}
+__global__ void k_export(uint64_t n, float4* __restrict__ aos, const float4* __restrict__ posq, const float4* __restrict__ velm) {
+	for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
+		const float4 p = posq[i], v = velm[i];
+		aos[3 * i] = make_float4(p.x, p.y, p.z, 0.0f);
+		aos[3 * i + 1] = make_float4(v.x, v.y, v.z, 0.0f);
+		aos[3 * i + 2] = make_float4(v.w, p.w, 0.0f, 0.0f);
+	}
+}
+static inline int grid_for(uint64_t n, int block) {
+	const uint64_t want = (n + block - 1) / block;
+	const uint64_t cap = (uint64_t) kNumSM * 16;
+	return (int) (want < 1 ? 1 : (want > cap ? cap : want));
+}
+void launch_import(Sim& s, const nbody_particle* aos_dev, uint64_t n) {
+	k_import<<<grid_for(n, 256), 256, 0, s.stream>>>(n, (const float4*) aos_dev, s.posq[0], s.velm[0], s.orig[0]);
+}
+void launch_export(Sim& s, nbody_particle* aos_dev, uint64_t n) {
+	k_export<<<grid_for(n, 256), 256, 0, s.stream>>>(n, (float4*) aos_dev, s.posq[0], s.velm[0]);
+}
+
+// ---------------------------------------------------------------------------
+// Morton keys. 21 bits per dimension, digit = x | y<<1 | z<<2, one FP32 multiply
+// per coordinate (no FMA contraction) so the host oracle classifies identically.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t spread3(uint32_t v) {
+	uint64_t x = v & 0x1fffffu;
+	x = (x | x << 32) & 0x1f00000000ffffull;
+	x = (x | x << 16) & 0x1f0000ff0000ffull;
+	x = (x | x << 8) & 0x100f00f00f00f00full;
+	x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+	x = (x | x << 2) & 0x1249249249249249ull;
+	return x;
+}
+__device__ __forceinline__ uint32_t compact3(uint64_t x) {
+	x &= 0x1249249249249249ull;
+	x = (x | x >> 2) & 0x10c30c30c30c30c3ull;
+	x = (x | x >> 4) & 0x100f00f00f00f00full;
+	x = (x | x >> 8) & 0x1f0000ff0000ffull;
+	x = (x | x >> 16) & 0x1f00000000ffffull;
+	x = (x | x >> 32) & 0x1fffffull;
+	return (uint32_t) x;
+}
+__device__ __forceinline__ uint32_t quantise(float x, float scale) {
+	const float v = fminf(fmaxf(__fmul_rn(x, scale), 0.0f), 2097151.0f);
+	return __float2uint_rz(v);
+}
+__global__ void k_keys(uint64_t n, const float4* __restrict__ posq, float sx, float sy, float sz, uint64_t* __restrict__ keys,
+                       uint32_t* __restrict__ idx) {
+	for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
+		const float4 p = posq[i];
+		keys[i] = spread3(quantise(p.x, sx)) | spread3(quantise(p.y, sy)) << 1 | spread3(quantise(p.z, sz)) << 2;
+		idx[i] = (uint32_t) i;
+	}
+}
+__global__ void k_gather(uint64_t n, const uint32_t* __restrict__ idx, const float4* __restrict__ posq_in,
+                         const float4* __restrict__ velm_in, const uint32_t* __restrict__ orig_in, float4* __restrict__ posq_out,
+                         float4* __restrict__ velm_out, uint32_t* __restrict__ orig_out) {
+	for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
+		const uint32_t j = idx[i];
+		posq_out[i] = posq_in[j];
+		velm_out[i] = velm_in[j];
+		orig_out[i] = orig_in[j];
+	}
+}
+
+size_t sort_temp_bytes(uint64_t n) {
+	size_t bytes = 0;
+	cub::DoubleBuffer<uint64_t> k(nullptr, nullptr);
+	cub::DoubleBuffer<uint32_t> v(nullptr, nullptr);
+	cub::DeviceRadixSort::SortPairs(nullptr, bytes, k, v, (int64_t) n, 0, 63);
+	return bytes;
+}
+
+// keys of state order -> stable radix sort -> gather the state into sorted order (posq[1], velm[1], orig[1]).
+// After this call keys[0] holds the sorted keys.
+int launch_keys_sort_permute(Sim& s) {
+	const uint64_t n = s.n;
+	const float sx = 2097152.0f / s.cfg.bounds[0], sy = 2097152.0f / s.cfg.bounds[1], sz = 2097152.0f / s.cfg.bounds[2];
+	k_keys<<<grid_for(n, 256), 256, 0, s.stream>>>(n, s.posq[0], sx, sy, sz, s.keys[0], s.idx[0]);
+	cub::DoubleBuffer<uint64_t> k(s.keys[0], s.keys[1]);
+	cub::DoubleBuffer<uint32_t> v(s.idx[0], s.idx[1]);
+	size_t bytes = s.sort_tmp_bytes;
+	NB_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(s.sort_tmp, bytes, k, v, (int64_t) n, 0, 63, s.stream));
+	if (k.Current() != s.keys[0]) { std::swap(s.keys[0], s.keys[1]); }
+	if (v.Current() != s.idx[0]) { std::swap(s.idx[0], s.idx[1]); }
+	k_gather<<<grid_for(n, 256), 256, 0, s.stream>>>(n, s.idx[0], s.posq[0], s.velm[0], s.orig[0], s.posq[1], s.velm[1], s.orig[1]);
+	return NBODY_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Linear octree, one level per pair of launches, sizes read from the device
+// control block (the host never learns the node count during a step).
+// ---------------------------------------------------------------------------
+__global__ void k_tree_init(Ctrl* c, uint32_t n, float bx, float by, float bz, float4* geom, uint2* info, uint32_t* nbegin,
+                            uint32_t* nparent, uint64_t* nkey, uint32_t* p2p_head) {
+	if (threadIdx.x == 0 && blockIdx.x == 0) {
+		for (int l = 0; l < kNumLevels + 2; ++l) c->level_off[l] = l == 0 ? 0u : 1u;
+		c->n_nodes = 1; c->status = 0; c->scan_ticket = 0; c->n_levels = 1;
+		c->gq_count[0] = c->gq_count[1] = 0; c->items_count[0] = c->items_count[1] = 0;
+		c->seg_cursor = 0; c->near_cursor[0] = c->near_cursor[1] = 0; c->p2p_cursor = 0; c->m2l_cursor = 0;
+		c->stat_m2l_inter = c->stat_p2p_entries = c->stat_p2p_inter = c->stat_near = c->stat_leaves = 0;
+		for (int k = 0; k < 4; ++k) c->work_ticket[k] = 0;
+		geom[0] = make_float4(__fadd_rn(__fmul_rn(0.0f, bx), __fmul_rn(bx, 0.5f)), __fadd_rn(__fmul_rn(0.0f, by), __fmul_rn(by, 0.5f)),
+		                      __fadd_rn(__fmul_rn(0.0f, bz), __fmul_rn(bz, 0.5f)), bx);
+		info[0] = make_uint2(0u, n);
+		nbegin[0] = 0; nparent[0] = 0; nkey[0] = 0; p2p_head[0] = 0xffffffffu;
+	}
+}
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* warp_sums, uint32_t& total) {
+	const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+	uint32_t inc = v;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+		if (lane >= (unsigned) d) inc += t;
+	}
+	if (lane == 31) warp_sums[w] = inc;
+	__syncthreads();
+	if (w == 0) {
+		uint32_t ws = lane < (blockDim.x >> 5) ? warp_sums[lane] : 0u;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const uint32_t t = __shfl_up_sync(0xffffffffu, ws, d);
+			if (lane >= (unsigned) d) ws += t;
+		}
+		warp_sums[lane] = ws;  // inclusive over warps
+	}
+	__syncthreads();
+	total = warp_sums[(blockDim.x >> 5) - 1];
+	const uint32_t base = w == 0 ? 0u : warp_sums[w - 1];
+	__syncthreads();
+	return base + inc - v;
+}
+
+// Pass A of level `l`: count the nodes that split in each tile; the last block to finish
+// turns the tile counts into exclusive offsets and publishes the size of level l+1.
+__global__ void __launch_bounds__(256) k_level_count(Ctrl* c, int l, uint32_t cap, uint32_t max_depth, uint32_t max_nodes,
+                                                      const uint2* __restrict__ info, uint32_t* scan_sums) {
+	__shared__ uint32_t warp_sums[32];
+	__shared__ bool last;
+	const uint32_t lo = c->level_off[l], hi = c->level_off[l + 1];
+	const uint32_t nl = hi - lo;
+	const uint32_t tile = (nl + gridDim.x - 1) / gridDim.x;
+	const uint32_t t0 = lo + blockIdx.x * tile, t1 = min(hi, t0 + tile);
+	uint32_t cnt = 0;
+	if ((uint32_t) l < max_depth)
+		for (uint32_t i = t0 + threadIdx.x; i < t1; i += blockDim.x) cnt += info[i].y > cap ? 1u : 0u;
+	uint32_t total;
+	block_exclusive_scan(cnt, warp_sums, total);
+	if (threadIdx.x == 0) {
+		scan_sums[blockIdx.x] = total;
+		__threadfence();
+		last = atomicAdd(&c->scan_ticket, 1u) == gridDim.x - 1;
+	}
+	__syncthreads();
+	if (last && threadIdx.x == 0) {
+		__threadfence();
+		uint32_t run = 0;
+		for (uint32_t b = 0; b < gridDim.x; ++b) { const uint32_t v = ((volatile uint32_t*) scan_sums)[b]; scan_sums[b] = run; run += v; }
+		uint32_t next = hi + 8u * run;
+		if (next > max_nodes || next < hi) { atomicOr(&c->status, kOvfNodes); run = 0; next = hi; }
+		scan_sums[gridDim.x] = run;
+		for (int k = l + 2; k < kNumLevels + 2; ++k) c->level_off[k] = next;
+		c->n_nodes = next;
+		if (run) c->n_levels = l + 2;
+		c->scan_ticket = 0;
+	}
+}
+
+// Pass B of level `l`: every splitting node gets its 8 children at level_off[l+1] + 8*rank,
+// rank = its position among the splitting nodes of the level (deterministic, Morton order).
+__global__ void __launch_bounds__(256) k_level_split(Ctrl* c, int l, uint32_t cap, uint32_t max_depth, float bx, float by, float bz,
+                                                      const uint64_t* __restrict__ keys, float4* geom, uint2* info, uint32_t* nbegin,
+                                                      uint32_t* nparent, uint64_t* nkey, uint32_t* p2p_head,
+                                                      const uint32_t* __restrict__ scan_sums) {
+	__shared__ uint32_t warp_sums[32];
+	if ((uint32_t) l >= max_depth || scan_sums[gridDim.x] == 0) return;
+	const uint32_t lo = c->level_off[l], hi = c->level_off[l + 1];
+	const uint32_t nl = hi - lo;
+	const uint32_t tile = (nl + gridDim.x - 1) / gridDim.x;
+	const uint32_t t0 = lo + blockIdx.x * tile, t1 = min(hi, t0 + tile);
+	uint32_t running = scan_sums[blockIdx.x];
+	const int shift = 3 * (kMaxDepth - 1 - l);
+	const float sc = __int_as_float((127 - (l + 1)) << 23);  // 2^-(l+1), exact
+	const float dx = __fmul_rn(bx, sc), dy = __fmul_rn(by, sc), dz = __fmul_rn(bz, sc);
+	for (uint32_t base = t0; base < t1; base += blockDim.x) {  // uniform trip count inside the block
+		const uint32_t i = base + threadIdx.x;
+		uint2 nf = make_uint2(0u, 0u);
+		if (i < t1) nf = info[i];
+		const bool split = i < t1 && nf.y > cap;
+		uint32_t total;
+		const uint32_t rank = block_exclusive_scan(split ? 1u : 0u, warp_sums, total);
+		if (split) {
+			const uint32_t cb = hi + 8u * (running + rank);
+			const uint32_t b = nbegin[i], e = b + nf.y;
+			const uint64_t pk = nkey[i];
+			info[i] = make_uint2(cb, nf.y);
+			uint32_t prev = b;
+			const uint64_t pp = l == 0 ? 0ull : pk >> (shift + 3);  // parent's digits, last one in bits 0..2
+			const uint32_t pix = compact3(pp), piy = compact3(pp >> 1), piz = compact3(pp >> 2);
+#pragma unroll 1
+			for (uint32_t k = 0; k < 8; ++k) {
+				// first particle whose digit at this level exceeds k
+				uint32_t end_k = e;
+				if (k < 7) {
+					const uint64_t bound = pk | (uint64_t) (k + 1) << shift;
+					uint32_t a = prev, z = e;
+					while (a < z) { const uint32_t m = a + ((z - a) >> 1); if (keys[m] < bound) a = m + 1; else z = m; }
+					end_k = a;
+				}
+				const uint32_t cid = cb + k;
+				const uint32_t ix = pix << 1 | (k & 1u), iy = piy << 1 | (k >> 1 & 1u), iz = piz << 1 | (k >> 2 & 1u);
+				geom[cid] = make_float4(__fadd_rn(__fmul_rn((float) ix, dx), __fmul_rn(dx, 0.5f)),
+				                        __fadd_rn(__fmul_rn((float) iy, dy), __fmul_rn(dy, 0.5f)),
+				                        __fadd_rn(__fmul_rn((float) iz, dz), __fmul_rn(dz, 0.5f)), dx);
+				info[cid] = make_uint2(0u, end_k - prev);
+				nbegin[cid] = prev;
+				nparent[cid] = i;
+				nkey[cid] = pk | (uint64_t) k << shift;
+				p2p_head[cid] = 0xffffffffu;
+				prev = end_k;
+			}
+		}
+		running += total;
+	}
+}
+
+void launch_tree_build(Sim& s) {
+	const nbody_cuda_config& cf = s.cfg;
+	k_tree_init<<<1, 32, 0, s.stream>>>(s.ctrl, (uint32_t) s.n, cf.bounds[0], cf.bounds[1], cf.bounds[2], s.geom, s.info, s.nbegin,
+	                                     s.nparent, s.nkey, s.p2p_head);
+	for (int l = 0; l < (int) cf.max_depth; ++l) {
+		k_level_count<<<kScanBlocks, 256, 0, s.stream>>>(s.ctrl, l, cf.leaf_capacity, cf.max_depth, s.max_nodes, s.info, s.scan_sums);
+		k_level_split<<<kScanBlocks, 256, 0, s.stream>>>(s.ctrl, l, cf.leaf_capacity, cf.max_depth, cf.bounds[0], cf.bounds[1],
+		                                                  cf.bounds[2], s.keys[0], s.geom, s.info, s.nbegin, s.nparent, s.nkey,
+		                                                  s.p2p_head, s.scan_sums);
+	}
+}
+
+}  // namespace nbody

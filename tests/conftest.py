@@ -1,0 +1,36 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
+
+
+def sorted_system(P, bounds=(1.0, 1.0, 1.0), capacity=8, max_depth=21):
+    """Oracle view of one particle set: keys, stable order, tree, sorted (x,y,z,q)."""
+    import oracle
+    keys = oracle.morton_keys(P[:, 0:3], bounds)
+    sk, perm = oracle.sort_keys(keys)
+    Ps = P[perm]
+    posq = np.ascontiguousarray(np.concatenate([Ps[:, 0:3], Ps[:, 9:10]], axis=1))
+    tree = oracle.Tree(sk, bounds, capacity, max_depth)
+    return {"keys": sk, "perm": perm, "P": Ps, "posq": posq, "tree": tree}
+
+
+def rms_rel(a, ref):
+    a = np.asarray(a, np.float64)
+    ref = np.asarray(ref, np.float64)
+    return float(np.sqrt(((a - ref) ** 2).sum() / (ref ** 2).sum()))
+
+
+@pytest.fixture(scope="session")
+def gpu_lib():
+    import nbody_b200
+    return nbody_b200.load_library()
