@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py — particle-steps/s of one full FMM gravity step (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  (N > 1: launched by torchrun, one rank per GPU)
+
+A "step" is one Simulation::step() on the metric's configuration: a Plummer sphere
+of N = 16M particles (BASELINE.json configs[2]), at the reference's constants (MAC
+0.5, softening 0.01, leaf capacity 8). One JSON line on stdout (rank 0).
+  value     whole-job particle-steps/s, state resident in HBM
+  e2e       the same through the C ABI with HOST buffers: set_particles (H2D) +
+            step + get_particles (D2H) inside the timed region
+  roofline  dominant kernel vs the FP32 FMA peak (this path is FP32-pipe bound by
+            design, not HBM/tensor: BASELINE.md section 3), live CUDA-event times
+  cpu_baseline  the UNMODIFIED reference naive_simulation.cpp (oracle/_ref) timed on
+            this box's host cores on a bounded sample of the same workload
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "particle-steps/sec at N=16M Plummer (1/2/4/8 B200); P2P FP32 TFLOP/s"
+UNIT = "particle-steps/s"
+N_SM = 148
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d.get("hbm_gbs", 6650.0), "sm_max_mhz": d.get("sm_max_mhz", 1965.0), "source": "MEASURED_PEAKS.json"}
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def fp32_peak_tflops(sm_mhz):
+    return N_SM * 128 * 2 * sm_mhz * 1e6 / 1e12
+
+
+def m2l_flops_per_interaction(P):
+    """Exact operation count of one directed M2L as implemented (expansion.cuh):
+    derivative tensor (monomials, radial scalars, Hermite-form sums) + the field-only contraction."""
+    mi = [(i, j, o - i - j) for o in range(P + 1) for i in range(o, -1, -1) for j in range(o - i, -1, -1)]
+    nc = len(mi)
+    flops = (nc - 1)            # monomials: one multiply each
+    flops += 3 + 2 * 3 + 2      # displacement (3 sub), R2 (3 FMA), rsqrt (counted 2)
+    flops += 1 + 2 * P          # inv2, g_k recurrences (2 mul each)
+    for (i, j, k) in mi:        # D_n = sum_j c g x^(n-2j): one FMA per term (+ a constant*g product shared; ignored)
+        terms = (i // 2 + 1) * (j // 2 + 1) * (k // 2 + 1)
+        flops += 2 * terms
+    contraction = sum(1 for n in mi if sum(n) >= 1 for m in mi if sum(n) + sum(m) <= P)
+    return flops + 2 * contraction, contraction
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for k, nm in enumerate(names):
+                    if r[3 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def reference_arm(args, rank):
+    """--impl reference: the unmodified reference CPU path (naive_simulation.cpp via oracle/_ref;
+    the oracle port if the reference was never compiled) on a bounded sample of the same workload."""
+    if rank != 0:
+        return
+    import oracle
+    from nbody_b200 import workloads
+    ns = args.cpu_sample
+    P = workloads.GENERATORS[args.workload](ns, n_total=args.n) if args.workload == "plummer" else workloads.GENERATORS[args.workload](ns)
+    have_ref = oracle.ref_lib() is not None
+    run = (lambda steps: oracle.ref_naive_run(P, 1.0, args.dt, steps)) if have_ref else \
+          (lambda steps: oracle.naive_step_as_written(P, 1.0, args.dt, steps))
+    for _ in range(min(args.warmup, 1)):
+        run(1)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        run(1)
+    dt = time.perf_counter() - t0
+    value = ns * args.steps / dt
+    pairs_per_s = ns * (ns - 1) / 2 * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload} N={args.n} (reference arm: first {ns} particles of it)", "sample_n": ns},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "reference" if have_ref else "port",
+                         "sample": f"NaiveSimulation::step() x{args.steps} on the first {ns} particles of the workload "
+                                   f"(O(N^2), single-threaded by construction; {pairs_per_s:.3e} pair-interactions/s; "
+                                   f"at the full N={args.n} the same code would deliver {2 * pairs_per_s / max(args.n - 1, 1):.3e} particle-steps/s)",
+                         "host_cores_visible": os.cpu_count()},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="plummer", choices=["plummer", "uniform", "two_galaxies"])
+    ap.add_argument("--n", type=int, default=1 << 24)
+    ap.add_argument("--order", type=int, default=4)
+    ap.add_argument("--leaf-capacity", type=int, default=8)
+    ap.add_argument("--dt", type=float, default=1e-3)
+    ap.add_argument("--cpu-sample", type=int, default=16384)
+    ap.add_argument("--cpu-steps", type=int, default=8)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pool-scale", type=float, default=1.0)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        reference_arm(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import nbody_b200
+    from nbody_b200 import workloads
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    n = args.n
+    # this rank's slice of the global particle set (weak in memory, strong in work: N is fixed)
+    lo = n * rank // world
+    hi = n * (rank + 1) // world
+    gen = workloads.GENERATORS[args.workload]
+    P = gen(hi - lo, start=lo, n_total=n) if args.workload == "plummer" else gen(hi - lo, start=lo) if args.workload == "uniform" else gen(n)
+    host = torch.from_numpy(P).pin_memory()
+    Pn = host.numpy()
+
+    cfgkw = dict(order=args.order, leaf_capacity=args.leaf_capacity, device=local_rank, pool_scale=args.pool_scale,
+                 force_constant=workloads.force_constant(args.workload, n))
+    if world == 1:
+        sim = nbody_b200.CudaSimulation([1.0, 1.0, 1.0], Pn, args.dt, **cfgkw)
+    else:
+        uid = [nbody_b200.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        sim = nbody_b200.CudaSimulation([1.0, 1.0, 1.0], Pn, args.dt, _distributed={
+            "unique_id": uid[0], "n_global": n, "global_offset": lo, "rank": rank, "world": world}, **cfgkw)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        sim.step()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    stage_ms = {}
+    counts = {}
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        sim.step()
+        st = sim.stats()
+        for k, v in st.items():
+            if k.startswith("ms_"):
+                stage_ms[k] = stage_ms.get(k, 0.0) + v
+            else:
+                counts[k] = v
+    barrier()
+    elapsed = time.perf_counter() - t0
+    clocks = sampler.stop()
+    if world > 1:
+        tt = torch.tensor([elapsed], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        elapsed = float(tt.item())
+    value = n * args.steps / elapsed
+    K = args.steps
+    stage_ms = {k: v / K for k, v in stage_ms.items()}
+
+    # ---- end to end through the C ABI with host buffers --------------------------------
+    e2e = None
+    if world == 1:
+        out = torch.empty_like(host).pin_memory()
+        sim.particles_into_ptr(out.data_ptr(), n)  # warm the export path
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            sim.set_particles_ptr(out.data_ptr(), n)   # H2D: this step's input state from pinned host memory
+            sim.step()
+            sim.particles_into_ptr(out.data_ptr(), n)  # D2H: the step's result
+        barrier()
+        e2e_t = time.perf_counter() - t0
+        e2e = {"value": n * args.e2e_steps / e2e_t, "unit": UNIT, "h2d_bytes_per_step": 48 * n, "d2h_bytes_per_step": 48 * n,
+               "ms_per_step": 1e3 * e2e_t / args.e2e_steps, "steps": args.e2e_steps}
+
+    if rank == 0:
+        peaks = measured_peaks()
+        peak = fp32_peak_tflops(peaks["sm_max_mhz"])
+        m2l_flops, m2l_fma = m2l_flops_per_interaction(args.order)
+        m2l_tf = counts["m2l_interactions"] * m2l_flops / (stage_ms["ms_m2l"] * 1e-3) / 1e12 if stage_ms.get("ms_m2l", 0) > 0 else 0.0
+        p2p_tf = counts["p2p_interactions"] * 20 / (stage_ms["ms_leaf"] * 1e-3) / 1e12 if stage_ms.get("ms_leaf", 0) > 0 else 0.0
+        dominant = "m2l" if stage_ms.get("ms_m2l", 0) >= stage_ms.get("ms_leaf", 0) else "p2p"
+        roof = {
+            "bound": "fp32", "kernel": "k_m2l (M2L, both launches)" if dominant == "m2l" else "k_leaf (P2P+L2P+integrate)",
+            "achieved": m2l_tf if dominant == "m2l" else p2p_tf, "peak": peak, "unit": "TFLOP/s",
+            "frac": (m2l_tf if dominant == "m2l" else p2p_tf) / peak, "traffic": None,
+            "peak_source": f"148 SM x 128 lanes x 2 x {peaks['sm_max_mhz']} MHz ({peaks['source']}; FP32 FMA peak, derived)",
+            "algorithmic_flops_per_unit": m2l_flops if dominant == "m2l" else 20,
+            "units_per_step": counts["m2l_interactions"] if dominant == "m2l" else counts["p2p_interactions"],
+            "kernel_ms": stage_ms["ms_m2l"] if dominant == "m2l" else stage_ms["ms_leaf"],
+            "share_of_step": (stage_ms["ms_m2l"] if dominant == "m2l" else stage_ms["ms_leaf"]) / stage_ms["ms_total"],
+        }
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
+            "ms_per_step": 1e3 * elapsed / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"{args.workload} sphere N={n}" if args.workload == "plummer" else f"{args.workload} N={n}",
+                       "order": args.order, "leaf_capacity": args.leaf_capacity, "mac_ratio": 0.5, "softening": 0.01,
+                       "integrator": "kick-drift", "l2_policy": "working set (>1 GB of lists and particle state per step) exceeds the 126 MB L2",
+                       "partition": "morton-range" if world > 1 else "single"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": K * launches_per_step(sim, world),
+            "roofline": roof,
+            "p2p_fp32_tflops": p2p_tf, "p2p_frac_of_fp32_peak": p2p_tf / peak, "m2l_fp32_tflops": m2l_tf,
+            "stage_ms": stage_ms, "counts": counts,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args)
+        print(json.dumps(line), flush=True)
+    sim.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def launches_per_step(sim, world):
+    d = int(sim.config.max_depth)
+    # keys, gather, tree init, per level (count, split), P2M, per level M2M, traversal init, per round (prep, traverse),
+    # two M2L launches, per level L2L, leaf kernel  (+ the radix sort's own launches, not counted)
+    return 1 + 1 + 1 + 2 * d + 1 + d + 1 + 2 * d + 2 + d + 1
+
+
+def cpu_baseline(args):
+    import oracle
+    from nbody_b200 import workloads
+    ns = args.cpu_sample
+    P = workloads.plummer(ns, n_total=args.n) if args.workload == "plummer" else workloads.GENERATORS[args.workload](ns)
+    have_ref = oracle.ref_lib() is not None
+    t0 = time.perf_counter()
+    if have_ref:
+        oracle.ref_naive_run(P, 1.0, args.dt, args.cpu_steps)
+    else:
+        oracle.naive_step_as_written(P, 1.0, args.dt, args.cpu_steps)
+    dt = time.perf_counter() - t0
+    pairs = ns * (ns - 1) / 2 * args.cpu_steps / dt
+    return {"value": ns * args.cpu_steps / dt, "unit": UNIT, "cores": 1, "kind": "reference" if have_ref else "port",
+            "sample": f"unmodified NaiveSimulation::step() x{args.cpu_steps} on the first {ns} particles of the workload "
+                      f"({pairs:.3e} pair-interactions/s; O(N^2): at N={args.n} this is {2 * pairs / max(args.n - 1, 1):.3e} particle-steps/s)",
+            "host_cores_visible": os.cpu_count()}
+
+
+if __name__ == "__main__":
+    main()

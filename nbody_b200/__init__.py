@@ -53,9 +53,9 @@ class NbodyCudaError(RuntimeError):
 _lib = None
 
 
-def build(force=False, verbose=False):
-    from . import build as _b
-    return _b.build(force=force, verbose=verbose)
+def build_library(force=False, verbose=False):
+    import importlib
+    return importlib.import_module("nbody_b200.build").build(force=force, verbose=verbose)
 
 
 def load_library():

@@ -108,3 +108,18 @@ def two_galaxies(n, seed=42):
 
 
 GENERATORS = {"uniform": uniform_cube, "plummer": plummer, "two_galaxies": two_galaxies}
+
+
+def force_constant(kind, n):
+    """Force constant that keeps each workload dynamically tame at dt = 1e-3.
+
+    The reference demo (src/main.cpp:23-69: masses 1..10, unit force constant, dt = 0.001)
+    is violently unstable for any sizeable N — the free-fall time of the cube is far
+    below dt, so after one step every particle has left the box (and the reference has
+    no boundary handling). Multi-step runs of the uniform cube therefore use
+    G = 1 / (total mass) (free-fall time of order 1); single force evaluations are
+    unaffected because G only scales the accelerations. The Plummer models are built in
+    virial equilibrium for G = 1 and total mass 1."""
+    if kind == "uniform":
+        return 1.0 / (5.5 * n)
+    return 1.0
