@@ -330,7 +330,7 @@ int nbody_cuda_step(nbody_cuda_sim* sim, float* time_out) {
 		if (rc) return rc;
 		const uint32_t status = s->ctrl_host->status;
 		if (status == 0) break;
-		if (attempt >= 12) { set_error("step: pools still overflow after 12 growth attempts"); return NBODY_ERR_CAPACITY; }
+		if (attempt >= 24) { set_error("step: pools still overflow after 24 growth attempts"); return NBODY_ERR_CAPACITY; }
 		if ((rc = grow_after_overflow(*s, status))) return rc;
 		++s->stats.retries;
 	}

@@ -19,60 +19,97 @@ namespace nbody {
 
 constexpr int kM2LChunk = 128;
 
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+	const unsigned sa = (unsigned) __cvta_generic_to_shared(smem);
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// Multipole record in shared memory, read with LDS.128 (records are 16-byte aligned and the
+// record stride of 36/20/12 floats keeps a quarter warp on distinct banks).
+struct SmemCoefs {
+	const float4* p;
+	__device__ __forceinline__ float operator[](int i) const {
+		const float4 v = p[i >> 2];
+		return (i & 3) == 0 ? v.x : (i & 3) == 1 ? v.y : (i & 3) == 2 ? v.z : v.w;
+	}
+};
+
 template <int P>
 __device__ __forceinline__ void m2l_one(float (&Lacc)[Expansion<P>::NC], const float4& tg, const float4& sg, const float* sM, float eps2) {
 	using E = Expansion<P>;
 	float D[E::NC];
 	E::derivatives(tg.x - sg.x, tg.y - sg.y, tg.z - sg.z, eps2, D);
-	E::template m2l<1>(Lacc, sM, D);
+	const SmemCoefs M{reinterpret_cast<const float4*>(sM)};
+	E::template m2l<1>(Lacc, M, D);
 }
 
+// One CTA per work item, items handed out by an atomic ticket. Candidate chunks are double
+// buffered with cp.async: while the warps evaluate chunk c, chunk c+1 (geometry + multipole
+// records, fetched by the 1-2 threads that own each slot) is in flight; one barrier per chunk.
 template <int P, int NT>
 __global__ void __launch_bounds__(NT == 8 ? 256 : 128, NT == 8 ? 2 : 4)
-k_m2l(const Ctrl* __restrict__ c, const Group* __restrict__ items, uint32_t items_cap, const float4* __restrict__ geom,
+k_m2l(Ctrl* __restrict__ c, const Group* __restrict__ items, uint32_t items_cap, const float4* __restrict__ geom,
       const float* __restrict__ M, float* __restrict__ L, const uint32_t* __restrict__ m2l_id, const uint8_t* __restrict__ m2l_mask,
       float eps2) {
 	using E = Expansion<P>;
 	constexpr int STRIDE = coef_stride(P);
 	constexpr int S4 = STRIDE / 4;
-	constexpr int NWARP = NT == 8 ? 8 : 4;
-	__shared__ __align__(16) float sM[kM2LChunk * STRIDE];
-	__shared__ float4 sgeom[kM2LChunk];
-	__shared__ uint32_t sid[kM2LChunk];
-	__shared__ uint8_t smask[kM2LChunk];
+	constexpr int NTHREADS = NT == 8 ? 256 : 128;
+	constexpr int TPS = NTHREADS / kM2LChunk;      // threads per candidate slot (2 or 1)
+	constexpr int PER = (S4 + TPS - 1) / TPS;      // float4 copies per thread
+	__shared__ __align__(16) float sM[2][kM2LChunk * STRIDE];
+	__shared__ float4 sgeom[2][kM2LChunk];
+	__shared__ uint8_t smask[2][kM2LChunk];
+	__shared__ uint32_t s_item;
 	const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+	const unsigned my_slot = threadIdx.x / TPS, part = threadIdx.x % TPS;
 	const uint32_t n_items = min(c->items_count[NT == 8 ? 0 : 1], items_cap);
-	for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x) {
+	const float4* M4 = reinterpret_cast<const float4*>(M);
+	for (;;) {
+		__syncthreads();  // everyone is done with the previous item (and with s_item)
+		if (threadIdx.x == 0) s_item = atomicAdd(&c->work_ticket[NT == 8 ? 0 : 1], 1u);
+		__syncthreads();
+		const uint32_t it = s_item;
+		if (it >= n_items) break;
 		const Group G = items[it];
 		const uint32_t target = NT == 8 ? G.first + w : G.first;
 		const float4 tg = geom[target];
 		float Lacc[E::NC];
 #pragma unroll
 		for (int a = 0; a < E::NC; ++a) Lacc[a] = 0.0f;
-		for (uint32_t c0 = 0; c0 < G.list_cnt; c0 += kM2LChunk) {
-			const uint32_t ns = min((uint32_t) kM2LChunk, G.list_cnt - c0);
-			__syncthreads();  // previous chunk fully consumed
-			if (threadIdx.x < ns) {
-				const uint32_t id = m2l_id[G.list_off + c0 + threadIdx.x];
-				sid[threadIdx.x] = id;
-				smask[threadIdx.x] = m2l_mask[G.list_off + c0 + threadIdx.x];
-				sgeom[threadIdx.x] = geom[id];
+		bool any = false;
+		const uint32_t nchunks = (G.list_cnt + kM2LChunk - 1) / kM2LChunk;
+		auto issue = [&](uint32_t chunk, int buf) {
+			const uint32_t e = chunk * kM2LChunk + my_slot;
+			if (e < G.list_cnt) {
+				const uint32_t id = m2l_id[G.list_off + e];
+				float4* dst = reinterpret_cast<float4*>(sM[buf]) + my_slot * S4;
+				const float4* src = M4 + (size_t) id * S4;
+#pragma unroll
+				for (int j = 0; j < PER; ++j)
+					if (part * PER + j < S4) cp_async16(dst + part * PER + j, src + part * PER + j);
+				if (part == 0) cp_async16(&sgeom[buf][my_slot], geom + id);
+				if (part == TPS - 1) smask[buf][my_slot] = m2l_mask[G.list_off + e];
 			}
-			__syncthreads();
-			const float4* M4 = reinterpret_cast<const float4*>(M);
-			float4* sM4 = reinterpret_cast<float4*>(sM);
-			for (uint32_t t = threadIdx.x; t < ns * S4; t += blockDim.x) {
-				const uint32_t slot = t / S4, j = t - slot * S4;
-				sM4[slot * S4 + j] = M4[(size_t) sid[slot] * S4 + j];
-			}
-			__syncthreads();
+			cp_async_commit();
+		};
+		issue(0, 0);
+		for (uint32_t ch = 0; ch < nchunks; ++ch) {
+			const int cur = ch & 1;
+			cp_async_wait_all();
+			__syncthreads();  // chunk ch has landed for everyone; everyone has finished chunk ch-1
+			if (ch + 1 < nchunks) issue(ch + 1, cur ^ 1);
+			const uint32_t ns = min((uint32_t) kM2LChunk, G.list_cnt - ch * kM2LChunk);
 			if (NT == 8) {
 				for (uint32_t s = lane; s < ns; s += 32)
-					if (smask[s] >> w & 1u) m2l_one<P>(Lacc, tg, sgeom[s], sM + s * STRIDE, eps2);
+					if (smask[cur][s] >> w & 1u) { m2l_one<P>(Lacc, tg, sgeom[cur][s], sM[cur] + s * STRIDE, eps2); any = true; }
 			} else {
-				for (uint32_t s = threadIdx.x; s < ns; s += 32 * NWARP) m2l_one<P>(Lacc, tg, sgeom[s], sM + s * STRIDE, eps2);
+				for (uint32_t s = threadIdx.x; s < ns; s += NTHREADS) { m2l_one<P>(Lacc, tg, sgeom[cur][s], sM[cur] + s * STRIDE, eps2); any = true; }
 			}
 		}
+		if (!__any_sync(0xffffffffu, any)) continue;
 		// warp reduction, then lane a adds coefficient a (L[0], the potential term, is not carried)
 #pragma unroll
 		for (int a = 1; a < E::NC; ++a) {

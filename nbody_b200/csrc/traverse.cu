@@ -18,21 +18,37 @@
 // A childless target whose near list is not empty is carried to the next round as a
 // single-target group (the reference splits only the side that has children).
 // Every directed (target, source) pair produced is exactly one direction of one
-// unordered pair the reference's recursion produces (tests/test_gpu_lists.py).
+// unordered pair the reference's recursion produces (tests/test_gpu_parity.py).
 //
-// One warp per group; lanes = 4 near entries x 8 children. Two passes over the
-// candidates: count, allocate exact space with one atomic per list, then write in
-// deterministic (list) order.
+// Kernel shape: one CTA (8 warps) per group, groups handed out by an atomic ticket.
+//   A. the near list is expanded into a candidate table in shared memory (ids, cell
+//      geometry, flags) with coalesced loads — once per CTA, shared by the 8 targets;
+//   B. warp w classifies (target w, 32 candidates) per step; the outcome is kept as three
+//      ballots per (target, batch) in shared memory, so nothing is classified twice;
+//   C. warp scans over the ballot popcounts give exact list sizes and write positions;
+//   D. one atomic per list reserves space; E. the lists are written in candidate order
+//      (deterministic content; only their placement in the pools depends on timing).
 #include "common.cuh"
 
 namespace nbody {
 
-__device__ __forceinline__ bool mac_accept(float ax, float ay, float az, float ad, const float4& b, float ratio_sq) {
-	// FP32, round-to-nearest, no FMA contraction: bit-identical to oracle mac_accept()
+constexpr int kTravThreads = 256;
+constexpr int kTravEntries = 256;                 // near entries expanded per chunk
+constexpr int kTravCand = kTravEntries * 8;       // candidate slots per chunk
+constexpr int kTravBatches = kTravCand / 32;      // 64
+
+// MAC, src/interaction.cl:64-82, FP32 round-to-nearest without FMA contraction: bit-identical
+// to oracle mac_accept(). For the reference's ratio 0.5 (ratio^2 = 0.25) the IEEE division is
+// replaced by an exactly equivalent test: fl(ext2/d2) < 0.25  <=>  ext2/d2 < 0.25 - 2^-27
+// (the rounding boundary below 0.25, ties go to the even 0.25)  <=>  d2/4 - ext2 > d2 * 2^-27,
+// where d2/4 and d2*2^-27 are exact and the subtraction is exact whenever the outcome is in
+// doubt (Sterbenz: ext2 in [d2/8, d2/2]); outside that range the sign is unambiguous.
+__device__ __forceinline__ bool mac_accept(float ax, float ay, float az, float ad, const float4& b, float ratio_sq, bool quarter) {
 	const float dx = __fsub_rn(b.x, ax), dy = __fsub_rn(b.y, ay), dz = __fsub_rn(b.z, az);
 	const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 	const float ext = __fadd_rn(ad, b.w);
 	const float ext2 = __fmul_rn(__fmul_rn(0.75f, ext), ext);
+	if (quarter) return __fsub_rn(__fmul_rn(0.25f, d2), ext2) > __fmul_rn(d2, 7.450580596923828125e-9f);  // 2^-27
 	return __fdiv_rn(ext2, d2) < ratio_sq;
 }
 
@@ -56,6 +72,7 @@ __global__ void k_round_prep(Ctrl* c, int r) {
 	if (threadIdx.x == 0 && blockIdx.x == 0) {
 		c->near_cursor[r & 1] = 0;
 		c->gq_count[(r + 1) & 1] = 0;
+		c->work_ticket[2] = 0;
 	}
 }
 
@@ -85,172 +102,235 @@ struct TraverseArgs {
 	int round;
 };
 
-__global__ void __launch_bounds__(128) k_traverse(const TraverseArgs a) {
+struct TravSmem {
+	float4 cgeom[kTravCand];
+	uint32_t cid[kTravCand];
+	uint8_t cflag[kTravCand];               // bit0: non-empty, bit1: has children
+	uint32_t bal[3][8][kTravBatches];       // ballots per (list, target, batch): 0 = M2L, 1 = near, 2 = P2P
+	uint32_t pre[3][8][kTravBatches];       // exclusive prefix of their popcounts over the batches
+	uint32_t uni[kTravBatches], upre[kTravBatches];  // union of the M2L ballots over the targets, and its prefix
+	uint32_t chunk_cnt[4][8];               // per-chunk totals: 0 = M2L (per target), 1 = near, 2 = P2P, 3 = next-round candidate slots
+	uint32_t total[4][8];                   // per-group totals
+	uint32_t off[3][8];                     // reserved offsets: [0][0] = M2L group list, [1][t] near, [2][t] P2P
+	uint32_t running[3][8];
+	uint32_t warp_sums[32];
+	uint32_t ncand, u_total, m2l_total, item, ok;
+};
+
+__device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, unsigned lane, uint32_t& total) {
+	uint32_t inc = v;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+		if (lane >= (unsigned) d) inc += t;
+	}
+	total = __shfl_sync(0xffffffffu, inc, 31);
+	return inc - v;
+}
+
+__global__ void __launch_bounds__(kTravThreads) k_traverse(const TraverseArgs a) {
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	TravSmem& S = *reinterpret_cast<TravSmem*>(smem_raw);
 	Ctrl* c = a.c;
-	const unsigned lane = threadIdx.x & 31u;
+	const unsigned tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
 	const unsigned lt_mask = (1u << lane) - 1u;
 	const uint32_t n_groups = min(c->gq_count[a.round & 1], a.gq_cap);
-	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
 	const int out = a.round & 1;
-	for (uint32_t gi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; gi < n_groups; gi += warps) {
+	const bool quarter = a.ratio_sq == 0.25f;
+	for (;;) {
+		__syncthreads();
+		if (tid == 0) S.item = atomicAdd(&c->work_ticket[2], 1u);
+		__syncthreads();
+		const uint32_t gi = S.item;
+		if (gi >= n_groups) break;
 		const Group G = a.q_in[gi];
-		// ---- targets: up to 8 siblings, data replicated in every lane's registers ----
-		float4 tg0 = make_float4(0.f, 0.f, 0.f, 0.f);
-		uint2 ti0 = make_uint2(0u, 0u);
-		if (lane < G.nt) { tg0 = a.geom[G.first + lane]; ti0 = a.info[G.first + lane]; }
-		float tx[8], ty[8], tz[8], td[8];
-		unsigned act = 0, tch = 0;  // bit t: target t is non-empty / has children
-#pragma unroll
-		for (int t = 0; t < 8; ++t) {
-			tx[t] = __shfl_sync(0xffffffffu, tg0.x, t);
-			ty[t] = __shfl_sync(0xffffffffu, tg0.y, t);
-			tz[t] = __shfl_sync(0xffffffffu, tg0.z, t);
-			td[t] = __shfl_sync(0xffffffffu, tg0.w, t);
-			const uint32_t cx = __shfl_sync(0xffffffffu, ti0.x, t), cy = __shfl_sync(0xffffffffu, ti0.y, t);
-			if (cy) act |= 1u << t;
-			if (cx) tch |= 1u << t;
-		}
-		uint32_t cnt_near[8], cnt_p2p[8], cnt_nc[8];
-#pragma unroll
-		for (int t = 0; t < 8; ++t) cnt_near[t] = cnt_p2p[t] = cnt_nc[t] = 0;
-		uint32_t cnt_m2l = 0;
-		uint32_t off_near = 0, off_p2p = 0, off_m2l = 0;  // lane t holds the offsets of target t; m2l in every lane
-		bool ok = true;
-		unsigned long long m2l_inter = 0;
-
-#pragma unroll 1
+		const uint32_t nt = G.nt;
+		// target data: for nt == 8 warp w owns target w; for nt == 1 every warp works for target 0
+		const uint32_t my_t = nt == 8 ? w : 0u;
+		const float4 tg = a.geom[G.first + my_t];
+		const uint2 ti = a.info[G.first + my_t];
+		const bool t_act = ti.y > 0, t_ch = ti.x != 0;
+		if (tid < 32) { S.total[tid >> 3][tid & 7] = 0; }
+		const uint32_t nchunks = (G.list_cnt + kTravEntries - 1) / kTravEntries;
 		for (int pass = 0; pass < 2; ++pass) {
-			uint32_t run_near[8], run_p2p[8];
-#pragma unroll
-			for (int t = 0; t < 8; ++t) run_near[t] = run_p2p[t] = 0;
-			uint32_t run_m2l = 0;
-			if (pass == 1 && !ok) break;
-#pragma unroll 1
-			for (uint32_t base = 0; base < G.list_cnt; base += 4) {
-				const uint32_t e = base + (lane >> 3);
-				const unsigned k = lane & 7u;
-				bool valid = e < G.list_cnt;
-				uint32_t B = 0;
-				uint2 bi = make_uint2(0u, 0u);
-				if (valid) { B = a.near_in[G.list_off + e]; bi = a.info[B]; }
-				uint32_t cand = B;
-				uint2 ci = bi;
-				if (bi.x) { cand = bi.x + k; ci = a.info[cand]; }
-				else valid = valid && k == 0;
-				valid = valid && ci.y > 0;
-				float4 cg = make_float4(0.f, 0.f, 0.f, 1.f);
-				if (valid) cg = a.geom[cand];
-				const bool cch = ci.x != 0;
-				unsigned amask = 0;
-#pragma unroll
-				for (int t = 0; t < 8; ++t) {
-					if (!(act >> t & 1u)) continue;  // warp-uniform
-					const bool same = cand == G.first + t;
-					const bool accept = valid && !same && mac_accept(tx[t], ty[t], tz[t], td[t], cg, a.ratio_sq);
-					const bool nearb = valid && !accept && ((tch >> t & 1u) || cch);
-					const bool p2pb = valid && !accept && !nearb;
-					if (accept) amask |= 1u << t;
-					const unsigned mn = __ballot_sync(0xffffffffu, nearb), mp = __ballot_sync(0xffffffffu, p2pb);
+			if (pass == 1) {
+				// ---- D. reserve exact space: thread t for target t's lists, thread 8 for the group's M2L list ----
+				__syncthreads();
+				if (tid == 0) S.ok = 1;
+				__syncthreads();
+				if (tid < nt) {
+					const uint32_t nn = S.total[1][tid], np = S.total[2][tid];
+					S.off[1][tid] = 0; S.off[2][tid] = 0;
+					if (nn) {
+						const unsigned long long o = atomicAdd(&c->near_cursor[out], (unsigned long long) nn);
+						if (o + nn > a.near_cap) { S.ok = 0; atomicOr(&c->status, kOvfNear); } else S.off[1][tid] = (uint32_t) o;
+					}
+					if (np) {
+						const unsigned long long o = atomicAdd(&c->p2p_cursor, (unsigned long long) np);
+						if (o + np > a.p2p_cap) { S.ok = 0; atomicOr(&c->status, kOvfP2P); } else S.off[2][tid] = (uint32_t) o;
+					}
+					S.running[1][tid] = 0; S.running[2][tid] = 0;
+				} else if (tid == 8) {
+					const uint32_t nm = S.m2l_total;
+					S.off[0][0] = 0; S.running[0][0] = 0;
+					if (nm) {
+						const unsigned long long o = atomicAdd(&c->m2l_cursor, (unsigned long long) nm);
+						if (o + nm > a.m2l_cap) { S.ok = 0; atomicOr(&c->status, kOvfM2L); } else S.off[0][0] = (uint32_t) o;
+					}
+				}
+				__syncthreads();
+				if (!S.ok) break;
+			} else if (tid == 0) S.m2l_total = 0;
+			for (uint32_t ch = 0; ch < nchunks; ++ch) {
+				const uint32_t e0 = ch * kTravEntries;
+				const uint32_t ne = min((uint32_t) kTravEntries, G.list_cnt - e0);
+				if (pass == 0 || nchunks > 1) {
+					// ---- A. expand near entries into the candidate table ----
+					__syncthreads();
+					uint32_t B = 0, nslots = 0;
+					uint2 bi = make_uint2(0u, 0u);
+					if (tid < ne) { B = a.near_in[G.list_off + e0 + tid]; bi = a.info[B]; nslots = bi.x ? 8u : 1u; }
+					uint32_t wtot;
+					const uint32_t wex = warp_excl_scan(nslots, lane, wtot);
+					if (lane == 31) S.warp_sums[w] = wtot;
+					__syncthreads();
+					uint32_t base = wex;
+					for (unsigned k = 0; k < w; ++k) base += S.warp_sums[k];
+					if (tid == 0) { uint32_t t = 0; for (int k = 0; k < kTravThreads / 32; ++k) t += S.warp_sums[k]; S.ncand = t; }
+					for (uint32_t k = 0; k < nslots; ++k) S.cid[base + k] = bi.x ? bi.x + k : B;
+					__syncthreads();
+					const uint32_t ncand = S.ncand;
+					for (uint32_t s = tid; s < ncand; s += kTravThreads) {
+						const uint32_t id = S.cid[s];
+						const uint2 ci = a.info[id];
+						S.cgeom[s] = a.geom[id];
+						S.cflag[s] = (uint8_t) ((ci.y > 0 ? 1u : 0u) | (ci.x ? 2u : 0u));
+					}
+					if (tid < 32) S.chunk_cnt[tid >> 3][tid & 7] = 0;
+					__syncthreads();
+					// ---- B. classify: (target, batch) pairs round-robin over the warps ----
+					const uint32_t nb = (ncand + 31) / 32;
+					for (uint32_t q = w; q < nt * nb; q += 8) {
+						const uint32_t t = nt == 8 ? w : 0u, b = nt == 8 ? q >> 3 : q;
+						const uint32_t s = 32 * b + lane;
+						unsigned code = 0;
+						if (s < ncand && t_act) {
+							const unsigned fl = S.cflag[s];
+							if (fl & 1u) {
+								const bool same = S.cid[s] == G.first + t;
+								const bool accept = !same && mac_accept(tg.x, tg.y, tg.z, tg.w, S.cgeom[s], a.ratio_sq, quarter);
+								code = accept ? 1u : ((t_ch || (fl & 2u)) ? 2u : 3u);
+							}
+						}
+						const unsigned m_acc = __ballot_sync(0xffffffffu, code == 1u), m_near = __ballot_sync(0xffffffffu, code == 2u),
+						               m_p2p = __ballot_sync(0xffffffffu, code == 3u);
+						const unsigned m_ch = __ballot_sync(0xffffffffu, code == 2u && (S.cflag[s < ncand ? s : 0] & 2u));
+						if (lane == 0) {
+							S.bal[0][t][b] = m_acc; S.bal[1][t][b] = m_near; S.bal[2][t][b] = m_p2p;
+							if (m_near) atomicAdd(&S.chunk_cnt[3][t], 8u * __popc(m_ch) + __popc(m_near & ~m_ch));
+						}
+					}
+					__syncthreads();
+					// ---- C. prefix sums over the batches: 3 lists x nt targets + the M2L union, one warp each ----
+					for (uint32_t job = w; job < 3 * nt + 1; job += 8) {
+						const bool is_union = job == 3 * nt;
+						const uint32_t li = is_union ? 0u : job / nt, t = is_union ? 0u : job - li * nt;
+						uint32_t carry = 0;
+						for (uint32_t b0 = 0; b0 < nb; b0 += 32) {
+							const uint32_t b = b0 + lane;
+							uint32_t m = 0;
+							if (b < nb) {
+								if (is_union) { for (uint32_t tt = 0; tt < nt; ++tt) m |= S.bal[0][tt][b]; S.uni[b] = m; }
+								else m = S.bal[li][t][b];
+							}
+							uint32_t tot;
+							const uint32_t ex = warp_excl_scan(__popc(m), lane, tot);
+							if (b < nb) { if (is_union) S.upre[b] = carry + ex; else S.pre[li][t][b] = carry + ex; }
+							carry += tot;
+						}
+						if (lane == 0) { if (is_union) S.u_total = carry; else S.chunk_cnt[li][t] = carry; }
+					}
+					__syncthreads();
 					if (pass == 0) {
-						cnt_near[t] += __popc(mn);
-						cnt_p2p[t] += __popc(mp);
-						const unsigned mc = __ballot_sync(0xffffffffu, nearb && cch);
-						cnt_nc[t] += 8u * __popc(mc) + __popc(mn & ~mc);
-					} else {
-						const uint32_t on = __shfl_sync(0xffffffffu, off_near, t), op = __shfl_sync(0xffffffffu, off_p2p, t);
-						if (nearb) a.near_out[on + run_near[t] + __popc(mn & lt_mask)] = cand;
-						if (p2pb) a.p2p[op + run_p2p[t] + __popc(mp & lt_mask)] = cand;
-						run_near[t] += __popc(mn);
-						run_p2p[t] += __popc(mp);
+						if (tid < 32) S.total[tid >> 3][tid & 7] += S.chunk_cnt[tid >> 3][tid & 7];
+						if (tid == 32) S.m2l_total += S.u_total;
 					}
 				}
-				const unsigned mm = __ballot_sync(0xffffffffu, amask != 0);
-				if (pass == 0) cnt_m2l += __popc(mm);
-				else {
-					if (amask) {
-						const uint32_t pos = off_m2l + run_m2l + __popc(mm & lt_mask);
-						a.m2l_id[pos] = cand;
-						a.m2l_mask[pos] = (uint8_t) amask;
+				if (pass == 1) {
+					// ---- E. write the lists of this chunk in candidate order ----
+					const uint32_t ncand = S.ncand, nb = (ncand + 31) / 32;
+					for (uint32_t q = w; q < nt * nb; q += 8) {
+						const uint32_t t = nt == 8 ? w : 0u, b = nt == 8 ? q >> 3 : q;
+						const uint32_t s = 32 * b + lane;
+						const uint32_t mn = S.bal[1][t][b], mp = S.bal[2][t][b];
+						if (mn >> lane & 1u) a.near_out[S.off[1][t] + S.running[1][t] + S.pre[1][t][b] + __popc(mn & lt_mask)] = S.cid[s];
+						if (mp >> lane & 1u) a.p2p[S.off[2][t] + S.running[2][t] + S.pre[2][t][b] + __popc(mp & lt_mask)] = S.cid[s];
 					}
-					run_m2l += __popc(mm);
-					m2l_inter += __popc(amask);
+					for (uint32_t b = w; b < nb; b += 8) {
+						const uint32_t u = S.uni[b];
+						if (u >> lane & 1u) {
+							unsigned am = 0;
+							for (uint32_t tt = 0; tt < nt; ++tt) am |= (S.bal[0][tt][b] >> lane & 1u) << tt;
+							const uint32_t pos = S.off[0][0] + S.running[0][0] + S.upre[b] + __popc(u & lt_mask);
+							a.m2l_id[pos] = S.cid[32 * b + lane];
+							a.m2l_mask[pos] = (uint8_t) am;
+						}
+					}
+					__syncthreads();
+					if (tid < nt) { S.running[1][tid] += S.chunk_cnt[1][tid]; S.running[2][tid] += S.chunk_cnt[2][tid]; }
+					if (tid == 8) S.running[0][0] += S.u_total;
 				}
-			}
-			if (pass == 0) {
-				// ---- exact allocation: lane t allocates for target t, lane 0 for the group's M2L list ----
-				uint32_t my_near = 0, my_p2p = 0;
-#pragma unroll
-				for (int t = 0; t < 8; ++t) if (lane == (unsigned) t) { my_near = cnt_near[t]; my_p2p = cnt_p2p[t]; }
-				bool fail = false;
-				if (lane < 8 && my_near) {
-					const unsigned long long o = atomicAdd(&c->near_cursor[out], (unsigned long long) my_near);
-					if (o + my_near > a.near_cap) { fail = true; atomicOr(&c->status, kOvfNear); } else off_near = (uint32_t) o;
-				}
-				if (lane < 8 && my_p2p) {
-					const unsigned long long o = atomicAdd(&c->p2p_cursor, (unsigned long long) my_p2p);
-					if (o + my_p2p > a.p2p_cap) { fail = true; atomicOr(&c->status, kOvfP2P); } else off_p2p = (uint32_t) o;
-				}
-				if (lane == 0 && cnt_m2l) {
-					const unsigned long long o = atomicAdd(&c->m2l_cursor, (unsigned long long) cnt_m2l);
-					if (o + cnt_m2l > a.m2l_cap) { fail = true; atomicOr(&c->status, kOvfM2L); } else off_m2l = (uint32_t) o;
-				}
-				off_m2l = __shfl_sync(0xffffffffu, off_m2l, 0);
-				ok = !__any_sync(0xffffffffu, fail);
 			}
 		}
-		if (!ok) continue;
-		// ---- publish: near lists -> next round's groups, P2P segments, M2L work item ----
-		uint32_t my_near = 0, my_p2p = 0, my_nc = 0;
-#pragma unroll
-		for (int t = 0; t < 8; ++t) if (lane == (unsigned) t) { my_near = cnt_near[t]; my_p2p = cnt_p2p[t]; my_nc = cnt_nc[t]; }
-		if (lane < G.nt && (act >> lane & 1u)) {
-			const uint32_t target = G.first + lane;
-			a.near_ref[target] = make_uint2(off_near, my_near);
-			if (my_near) {
-				const uint32_t qi = atomicAdd(&c->gq_count[(a.round + 1) & 1], 1u);
-				if (qi < a.gq_cap) {
-					Group g{};
-					if (ti0.x) { g.first = ti0.x; g.nt = 8; } else { g.first = target; g.nt = 1; }
-					g.list_off = off_near; g.list_cnt = my_near; g.n_cand = my_nc;
-					a.q_out[qi] = g;
-				} else atomicOr(&c->status, kOvfGroups);
+		__syncthreads();
+		if (!S.ok) continue;
+		// ---- F. publish: near lists -> next round's groups, P2P segments, the M2L work item, statistics ----
+		if (tid < nt) {
+			const uint32_t target = G.first + tid;
+			const uint2 tin = a.info[target];
+			const uint32_t nn = S.total[1][tid], np = S.total[2][tid];
+			if (tin.y) {
+				a.near_ref[target] = make_uint2(S.off[1][tid], nn);
+				if (nn) {
+					const uint32_t qi = atomicAdd(&c->gq_count[(a.round + 1) & 1], 1u);
+					if (qi < a.gq_cap) {
+						Group g{};
+						if (tin.x) { g.first = tin.x; g.nt = 8; } else { g.first = target; g.nt = 1; }
+						g.list_off = S.off[1][tid]; g.list_cnt = nn; g.n_cand = S.total[3][tid];
+						a.q_out[qi] = g;
+					} else atomicOr(&c->status, kOvfGroups);
+				}
+				if (np) {
+					const uint32_t si = atomicAdd(&c->seg_cursor, 1u);
+					if (si < a.seg_cap) {
+						Segment sg; sg.off = S.off[2][tid]; sg.cnt = np; sg.next = a.p2p_head[target];
+						a.seg[si] = sg;
+						a.p2p_head[target] = si;
+					} else atomicOr(&c->status, kOvfSeg);
+				}
 			}
-			if (my_p2p) {
-				const uint32_t si = atomicAdd(&c->seg_cursor, 1u);
-				if (si < a.seg_cap) {
-					Segment sg; sg.off = off_p2p; sg.cnt = my_p2p; sg.next = a.p2p_head[target];
-					a.seg[si] = sg;
-					a.p2p_head[target] = si;
-				} else atomicOr(&c->status, kOvfSeg);
-			}
-		}
-		unsigned long long p2p_total = my_p2p, near_total = my_near;
-#pragma unroll
-		for (int d = 4; d >= 1; d >>= 1) {
-			p2p_total += __shfl_xor_sync(0xffffffffu, p2p_total, d);
-			near_total += __shfl_xor_sync(0xffffffffu, near_total, d);
-		}
-#pragma unroll
-		for (int d = 16; d >= 1; d >>= 1) m2l_inter += __shfl_xor_sync(0xffffffffu, m2l_inter, d);
-		if (lane == 0) {
-			if (cnt_m2l) {
-				const int which = G.nt == 8 ? 0 : 1;
+		} else if (tid == 32) {
+			uint32_t inter = 0, p2pn = 0, nearn = 0;
+			for (uint32_t t = 0; t < nt; ++t) { inter += S.total[0][t]; p2pn += S.total[2][t]; nearn += S.total[1][t]; }
+			if (S.m2l_total) {
+				const int which = nt == 8 ? 0 : 1;
 				const uint32_t ii = atomicAdd(&c->items_count[which], 1u);
 				if (ii < a.items_cap) {
 					Group it{};
-					it.first = G.first; it.nt = G.nt; it.list_off = off_m2l; it.list_cnt = cnt_m2l;
+					it.first = G.first; it.nt = nt; it.list_off = S.off[0][0]; it.list_cnt = S.m2l_total;
 					(which == 0 ? a.items8 : a.items1)[ii] = it;
 				} else atomicOr(&c->status, kOvfItems);
 			}
-			atomicAdd(&c->stat_m2l_inter, m2l_inter);
-			atomicAdd(&c->stat_p2p_entries, p2p_total);
-			atomicAdd(&c->stat_near, near_total);
+			atomicAdd(&c->stat_m2l_inter, (unsigned long long) inter);
+			atomicAdd(&c->stat_p2p_entries, (unsigned long long) p2pn);
+			atomicAdd(&c->stat_near, (unsigned long long) nearn);
 		}
 	}
 }
 
 void launch_traversal(Sim& s) {
 	Pools& p = s.pools;
+	cudaFuncSetAttribute(k_traverse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(TravSmem));
 	k_traverse_init<<<1, 32, 0, s.stream>>>(s.ctrl, s.info, p.near[0], p.gq[1]);
 	TraverseArgs a{};
 	a.c = s.ctrl; a.geom = s.geom; a.info = s.info; a.near_ref = s.near_ref; a.p2p_head = s.p2p_head;
@@ -264,7 +344,7 @@ void launch_traversal(Sim& s) {
 		a.near_out = p.near[r & 1];
 		a.q_in = p.gq[r & 1];
 		a.q_out = p.gq[(r + 1) & 1];
-		k_traverse<<<kNumSM * 8, 128, 0, s.stream>>>(a);
+		k_traverse<<<kNumSM * 4, kTravThreads, sizeof(TravSmem), s.stream>>>(a);
 	}
 }
 

@@ -1,0 +1,80 @@
+"""CPU tests of the boundary: the C-ABI library loads and exports every symbol that
+include/nbody_cuda.h declares; no compute call is made without a GPU, and the product
+refuses to run (never falls back to a CPU path) when there is no CUDA device."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import nbody_b200
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "nbody_cuda.h")).read()
+    return sorted(set(re.findall(r"\b(nbody_cuda_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_header_and_python_mirror_agree():
+    assert declared_symbols() == sorted(nbody_b200.EXPORTED_SYMBOLS)
+
+
+def test_library_exports_every_declared_symbol():
+    if not os.path.exists(nbody_b200.LIB_PATH):
+        nbody_b200.build_library()
+    lib = C.CDLL(nbody_b200.LIB_PATH)
+    for s in declared_symbols():
+        assert hasattr(lib, s), s
+
+
+def test_struct_layouts():
+    assert C.sizeof(nbody_b200.Config) == 4 + 16 + 4 * 4 + 4 * 6 + 4 + 7 * 4   # 92 bytes, mirrors nbody_cuda_config
+    assert C.sizeof(nbody_b200.Stats) == 11 * 8 + 10 * 4
+    cfg = nbody_b200.default_config()
+    assert cfg.abi_version == 1 and cfg.leaf_capacity == 8 and cfg.order == 4 and cfg.max_depth == 21
+    assert abs(cfg.softening - 0.01) < 1e-9 and abs(cfg.mac_ratio - 0.5) < 1e-9 and cfg.force_constant == 1.0
+    assert list(cfg.bounds)[:3] == [1.0, 1.0, 1.0]
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    P = np.zeros((4, 12), np.float32)
+    P[:, 8] = 1; P[:, 9] = 1
+    with pytest.raises(nbody_b200.NbodyCudaError) as e:
+        nbody_b200.CudaSimulation([1, 1, 1], P, 1e-3)
+    assert "no CPU fallback" in str(e.value) or "CUDA" in str(e.value)
+    with pytest.raises(nbody_b200.NbodyCudaError):
+        nbody_b200.direct_field(np.zeros((4, 4), np.float32), np.zeros((4, 4), np.float32))
+
+
+def test_argument_validation_without_gpu():
+    lib = nbody_b200.load_library()
+    h = C.c_void_p()
+    cfg = nbody_b200.default_config()
+    P = np.zeros((4, 12), np.float32)
+    assert lib.nbody_cuda_create(C.byref(cfg), None, 4, C.byref(h)) == 1          # NULL particles
+    cfg.order = 7
+    assert lib.nbody_cuda_create(C.byref(cfg), P.ctypes.data_as(C.c_void_p), 4, C.byref(h)) == 1
+    assert b"order" in lib.nbody_cuda_last_error()
+    cfg = nbody_b200.default_config(leaf_capacity=0)
+    assert lib.nbody_cuda_create(C.byref(cfg), P.ctypes.data_as(C.c_void_p), 4, C.byref(h)) == 1
+    cfg = nbody_b200.default_config()
+    assert lib.nbody_cuda_create(C.byref(cfg), P.ctypes.data_as(C.c_void_p), 0, C.byref(h)) == 1
+    assert lib.nbody_cuda_num_particles(None) == 0
+
+
+def test_oracle_is_not_linked_into_the_product():
+    # the product library must not depend on anything under oracle/
+    import subprocess
+    out = subprocess.run(["ldd", nbody_b200.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in out and "naive_ref" not in out
+    for root, _, files in os.walk(os.path.join(ROOT, "nbody_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                txt = open(os.path.join(root, f)).read()
+                assert "import oracle" not in txt and "liboracle" not in txt, f
