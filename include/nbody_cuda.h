@@ -76,7 +76,10 @@ typedef struct nbody_cuda_config {
 	uint32_t flags;
 	int32_t device;         /* CUDA device ordinal; -1 = current */
 	float pool_scale;       /* multiplies the initial sizes of the list pools; default 1 */
-	uint32_t _reserved[7];
+	float low_order_tau;    /* adaptive-order M2L: accepted pairs with 0.75 (dimA+dimB)^2 / d^2 < tau are evaluated at
+	                           order P-1 (same lists, less work; 0 = always order P). default 0.13: RMS error 4.4e-4 on
+	                           the Plummer model against 2.1e-4 at full order (tools/explore notes in DESIGN.md) */
+	uint32_t _reserved[6];
 } nbody_cuda_config;
 
 /* per-step statistics (tracing/metrics hook) */
@@ -85,6 +88,7 @@ typedef struct nbody_cuda_stats {
 	uint64_t n_nodes, n_leaves, n_levels;
 	uint64_t m2l_entries;      /* (source, target-mask) entries in the grouped M2L lists */
 	uint64_t m2l_interactions; /* directed target<-source M2L evaluations */
+	uint64_t m2l_interactions_low; /* ... of which evaluated at order P-1 (low_order_tau) */
 	uint64_t p2p_entries;      /* directed target-leaf <- source-leaf pairs */
 	uint64_t p2p_interactions; /* directed target-particle <- source-particle evaluations */
 	uint64_t near_entries;     /* total near-list entries written by the traversal */
@@ -98,7 +102,7 @@ typedef struct nbody_cuda_stats {
 typedef struct nbody_cuda_sim nbody_cuda_sim; /* opaque; single-threaded use */
 
 /* Fill cfg with the reference's constants (bounds 1,1,1; dt 0.001; G +1; eps 0.01;
- * MAC 0.5; capacity 8; depth 21; order 4; kick-drift). */
+ * MAC 0.5; capacity 8; depth 21; order 4; kick-drift; low_order_tau 0.13). */
 void nbody_cuda_default_config(nbody_cuda_config* cfg);
 
 /* Construct from host particles (copied; caller keeps ownership of `particles`).

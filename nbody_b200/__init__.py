@@ -33,12 +33,12 @@ class Config(C.Structure):
     _fields_ = [("abi_version", C.c_uint32), ("bounds", C.c_float * 4), ("time_step", C.c_float), ("force_constant", C.c_float),
                 ("softening", C.c_float), ("mac_ratio", C.c_float), ("leaf_capacity", C.c_uint32), ("max_depth", C.c_uint32),
                 ("order", C.c_uint32), ("integrator", C.c_uint32), ("flags", C.c_uint32), ("device", C.c_int32),
-                ("pool_scale", C.c_float), ("_reserved", C.c_uint32 * 7)]
+                ("pool_scale", C.c_float), ("low_order_tau", C.c_float), ("_reserved", C.c_uint32 * 6)]
 
 
 class Stats(C.Structure):
     _fields_ = [(k, C.c_uint64) for k in ("n_particles", "n_nodes", "n_leaves", "n_levels", "m2l_entries", "m2l_interactions",
-                                          "p2p_entries", "p2p_interactions", "near_entries", "retries", "device_bytes")] + \
+                                          "m2l_interactions_low", "p2p_entries", "p2p_interactions", "near_entries", "retries", "device_bytes")] + \
                [(k, C.c_float) for k in ("ms_total", "ms_sort", "ms_tree", "ms_upsweep", "ms_traverse", "ms_m2l", "ms_l2l",
                                          "ms_leaf", "ms_comm", "_pad")]
 

@@ -64,13 +64,14 @@ int alloc_pools(Sim& s, const PoolPlan& pl) {
 	if ((rc = dev_alloc(s, p.p2p, p.p2p_cap))) return rc;
 	if ((rc = dev_alloc(s, p.m2l_id, p.m2l_cap))) return rc;
 	if ((rc = dev_alloc(s, p.m2l_mask, p.m2l_cap))) return rc;
+	if ((rc = dev_alloc(s, p.m2l_mask_lo, p.m2l_cap))) return rc;
 	if ((rc = dev_alloc(s, p.seg, p.seg_cap))) return rc;
 	return NBODY_OK;
 }
 void free_pools(Sim& s) {
 	Pools& p = s.pools;
 	for (int k = 0; k < 2; ++k) { dev_free(s, p.near[k], p.near_cap); dev_free(s, p.gq[k], p.gq_cap); dev_free(s, p.items[k], p.items_cap); }
-	dev_free(s, p.p2p, p.p2p_cap); dev_free(s, p.m2l_id, p.m2l_cap); dev_free(s, p.m2l_mask, p.m2l_cap); dev_free(s, p.seg, p.seg_cap);
+	dev_free(s, p.p2p, p.p2p_cap); dev_free(s, p.m2l_id, p.m2l_cap); dev_free(s, p.m2l_mask, p.m2l_cap); dev_free(s, p.m2l_mask_lo, p.m2l_cap); dev_free(s, p.seg, p.seg_cap);
 }
 PoolPlan current_plan(const Sim& s) {
 	const Pools& p = s.pools;
@@ -110,6 +111,7 @@ int validate(const nbody_cuda_config* cfg, uint64_t n) {
 	if (cfg->leaf_capacity < 1) { set_error("leaf_capacity must be >= 1"); return NBODY_ERR_INVALID; }
 	if (!(cfg->softening >= 0) || !(cfg->mac_ratio > 0)) { set_error("softening must be >= 0 and mac_ratio > 0"); return NBODY_ERR_INVALID; }
 	if (cfg->integrator > 1) { set_error("unknown integrator"); return NBODY_ERR_INVALID; }
+	if (!(cfg->low_order_tau >= 0)) { set_error("low_order_tau must be >= 0"); return NBODY_ERR_INVALID; }
 	return NBODY_OK;
 }
 
@@ -296,6 +298,7 @@ void nbody_cuda_default_config(nbody_cuda_config* cfg) {
 	cfg->flags = 0;
 	cfg->device = -1;
 	cfg->pool_scale = 1.0f;
+	cfg->low_order_tau = 0.13f;
 }
 
 int nbody_cuda_create(const nbody_cuda_config* cfg, const nbody_particle* particles, uint64_t n, nbody_cuda_sim** out) {
@@ -342,7 +345,7 @@ int nbody_cuda_step(nbody_cuda_sim* sim, float* time_out) {
 	const Ctrl& c = *s->ctrl_host;
 	nbody_cuda_stats& t = s->stats;
 	t.n_particles = s->n; t.n_nodes = c.n_nodes; t.n_levels = c.n_levels; t.n_leaves = c.stat_leaves;
-	t.m2l_entries = c.m2l_cursor; t.m2l_interactions = c.stat_m2l_inter; t.p2p_entries = c.stat_p2p_entries;
+	t.m2l_entries = c.m2l_cursor; t.m2l_interactions = c.stat_m2l_inter; t.m2l_interactions_low = c.stat_m2l_low; t.p2p_entries = c.stat_p2p_entries;
 	t.p2p_interactions = c.stat_p2p_inter >= s->own_count ? c.stat_p2p_inter - s->own_count : 0;  // drop the i == j terms
 	t.near_entries = c.stat_near; t.device_bytes = s->device_bytes;
 	auto ms = [&](int a, int b) { float v = 0; cudaEventElapsedTime(&v, s->ev[a], s->ev[b]); return v; };

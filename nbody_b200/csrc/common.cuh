@@ -49,7 +49,7 @@ struct Ctrl {
 	unsigned long long near_cursor[2];   // near-list pools, ping-pong by round
 	unsigned long long p2p_cursor;
 	unsigned long long m2l_cursor;
-	unsigned long long stat_m2l_inter, stat_p2p_entries, stat_p2p_inter, stat_near, stat_leaves;
+	unsigned long long stat_m2l_inter, stat_m2l_low, stat_p2p_entries, stat_p2p_inter, stat_near, stat_leaves;
 	uint32_t work_ticket[4];             // dynamic work distribution of the persistent kernels
 };
 
@@ -59,7 +59,8 @@ struct Pools {
 	uint32_t* p2p = nullptr;
 	uint64_t p2p_cap = 0;
 	uint32_t* m2l_id = nullptr;
-	uint8_t* m2l_mask = nullptr;
+	uint8_t* m2l_mask = nullptr;     // bit t: target t of the group accepts this candidate
+	uint8_t* m2l_mask_lo = nullptr;  // bit t: ... and evaluates it at order P-1 (subset of m2l_mask)
 	uint64_t m2l_cap = 0;
 	Segment* seg = nullptr;
 	uint32_t seg_cap = 0;

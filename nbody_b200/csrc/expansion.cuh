@@ -118,16 +118,19 @@ struct Expansion {
 		}
 	}
 
-	// M2L: Lt_n += sum_{|m| <= P-|n|} (-1)^|m| M_m D_{n+m}.  LO = lowest local order
-	// kept: 1 when only the field (gradient) is needed, 0 to carry the potential too.
-	// Source-major loop order: one multipole coefficient is live at a time (it may
-	// come straight from shared memory), the P-dependent live set is L and D only.
-	template <int LO, typename MT>
-	NB_HD static void m2l(float (&L)[NC], const MT& M, const float (&D)[NC]) {
-		NB_FOR_MI(o2, a, b, c, 0, P - LO) {
+	// M2L: Lt_n += sum_{|m| <= PE-|n|} (-1)^|m| M_m D_{n+m} for LO <= |n| <= PE.
+	// LO = lowest local order kept: 1 when only the field (gradient) is needed, 0 to carry the
+	// potential too. PE <= P is the order this pair is evaluated at (adaptive-order M2L: well
+	// separated pairs run at P-1); D then only needs derivatives up to order PE.
+	// Source-major loop order: one multipole coefficient is live at a time (it may come straight
+	// from shared memory), the P-dependent live set is L and D only.
+	template <int LO, int PE = P, typename MT, int ND>
+	NB_HD static void m2l(float (&L)[NC], const MT& M, const float (&D)[ND]) {
+		static_assert(PE <= P && ND >= ncoef(PE), "derivative tensor too short for the evaluation order");
+		NB_FOR_MI(o2, a, b, c, 0, PE - LO) {
 			const float mraw = M[mi_index(a, b, c)];
 			const float m = (o2 & 1) ? -mraw : mraw;
-			NB_FOR_MI(o, i, j, k, LO, P - o2) {
+			NB_FOR_MI(o, i, j, k, LO, PE - o2) {
 				L[mi_index(i, j, k)] += m * D[mi_index(i + a, j + b, k + c)];
 			}
 		}

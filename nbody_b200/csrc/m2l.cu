@@ -17,8 +17,6 @@
 
 namespace nbody {
 
-constexpr int kM2LChunk = 128;
-
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 	const unsigned sa = (unsigned) __cvta_generic_to_shared(smem);
 	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
@@ -27,7 +25,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 // Multipole record in shared memory, read with LDS.128 (records are 16-byte aligned and the
-// record stride of 36/20/12 floats keeps a quarter warp on distinct banks).
+// record stride of 36/20/12 floats keeps consecutive slots of a quarter warp on distinct banks).
 struct SmemCoefs {
 	const float4* p;
 	__device__ __forceinline__ float operator[](int i) const {
@@ -36,42 +34,56 @@ struct SmemCoefs {
 	}
 };
 
-template <int P>
+// One (target, source) M2L evaluated at order PE <= P.
+template <int P, int PE>
 __device__ __forceinline__ void m2l_one(float (&Lacc)[Expansion<P>::NC], const float4& tg, const float4& sg, const float* sM, float eps2) {
-	using E = Expansion<P>;
-	float D[E::NC];
-	E::derivatives(tg.x - sg.x, tg.y - sg.y, tg.z - sg.z, eps2, D);
+	float D[Expansion<PE>::NC];
+	Expansion<PE>::derivatives(tg.x - sg.x, tg.y - sg.y, tg.z - sg.z, eps2, D);
 	const SmemCoefs M{reinterpret_cast<const float4*>(sM)};
-	E::template m2l<1>(Lacc, M, D);
+	Expansion<P>::template m2l<1, PE>(Lacc, M, D);
 }
 
-// One CTA per work item, items handed out by an atomic ticket. Candidate chunks are double
-// buffered with cp.async: while the warps evaluate chunk c, chunk c+1 (geometry + multipole
-// records, fetched by the 1-2 threads that own each slot) is in flight; one barrier per chunk.
+template <int P, int NT>
+struct M2LShared {
+	static constexpr int CH = NT == 8 ? 256 : 128;  // candidate slots per chunk = threads per CTA
+	static constexpr int STRIDE = coef_stride(P);
+	float sM[2][CH * STRIDE];
+	float4 sgeom[2][CH];
+	uint32_t sid[3][CH];                     // ids / masks of chunk k live in ring slot k % 3 (published two chunks ahead)
+	uint8_t smask[3][CH], smask_lo[3][CH];
+	uint8_t list_hi[8][CH], list_lo[8][CH];  // per-warp compacted slot numbers of the two order classes
+	uint32_t item;
+};
+
+// One CTA per work item (8 sibling targets, one warp each, or one carried target shared by 4 warps),
+// items handed out by an atomic ticket. Candidate chunks are double buffered with cp.async:
+// while the warps evaluate chunk c, chunk c+1 is in flight (fully coalesced 16-byte copies: thread
+// t moves piece t, t+CH, ... of the chunk's records), and the ids of chunk c+2 are already in
+// registers, so no address dependency sits between the one barrier per chunk and the math.
+// Inside a chunk each warp first compacts the slots its target accepts into two dense lists
+// (order P and order P-1), then all 32 lanes work through each list.
 template <int P, int NT>
 __global__ void __launch_bounds__(NT == 8 ? 256 : 128, NT == 8 ? 2 : 4)
 k_m2l(Ctrl* __restrict__ c, const Group* __restrict__ items, uint32_t items_cap, const float4* __restrict__ geom,
       const float* __restrict__ M, float* __restrict__ L, const uint32_t* __restrict__ m2l_id, const uint8_t* __restrict__ m2l_mask,
-      float eps2) {
+      const uint8_t* __restrict__ m2l_mask_lo, float eps2) {
 	using E = Expansion<P>;
+	using SH = M2LShared<P, NT>;
+	constexpr int CH = SH::CH;
 	constexpr int STRIDE = coef_stride(P);
 	constexpr int S4 = STRIDE / 4;
-	constexpr int NTHREADS = NT == 8 ? 256 : 128;
-	constexpr int TPS = NTHREADS / kM2LChunk;      // threads per candidate slot (2 or 1)
-	constexpr int PER = (S4 + TPS - 1) / TPS;      // float4 copies per thread
-	__shared__ __align__(16) float sM[2][kM2LChunk * STRIDE];
-	__shared__ float4 sgeom[2][kM2LChunk];
-	__shared__ uint8_t smask[2][kM2LChunk];
-	__shared__ uint32_t s_item;
-	const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
-	const unsigned my_slot = threadIdx.x / TPS, part = threadIdx.x % TPS;
+	constexpr int PL = P > 2 ? P - 1 : P;  // the low evaluation order
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	SH& S = *reinterpret_cast<SH*>(smem_raw);
+	const unsigned tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;
+	const unsigned lt_mask = (1u << lane) - 1u;
 	const uint32_t n_items = min(c->items_count[NT == 8 ? 0 : 1], items_cap);
 	const float4* M4 = reinterpret_cast<const float4*>(M);
 	for (;;) {
-		__syncthreads();  // everyone is done with the previous item (and with s_item)
-		if (threadIdx.x == 0) s_item = atomicAdd(&c->work_ticket[NT == 8 ? 0 : 1], 1u);
+		__syncthreads();  // everyone is done with the previous item (and with S.item)
+		if (tid == 0) S.item = atomicAdd(&c->work_ticket[NT == 8 ? 0 : 1], 1u);
 		__syncthreads();
-		const uint32_t it = s_item;
+		const uint32_t it = S.item;
 		if (it >= n_items) break;
 		const Group G = items[it];
 		const uint32_t target = NT == 8 ? G.first + w : G.first;
@@ -80,36 +92,78 @@ k_m2l(Ctrl* __restrict__ c, const Group* __restrict__ items, uint32_t items_cap,
 #pragma unroll
 		for (int a = 0; a < E::NC; ++a) Lacc[a] = 0.0f;
 		bool any = false;
-		const uint32_t nchunks = (G.list_cnt + kM2LChunk - 1) / kM2LChunk;
+		const uint32_t nchunks = (G.list_cnt + CH - 1) / CH;
+		auto fetch = [&](uint32_t chunk, uint32_t& id, uint32_t& mk) {
+			const uint32_t e = chunk * CH + tid;
+			id = 0; mk = 0;
+			if (chunk < nchunks && e < G.list_cnt) { id = m2l_id[G.list_off + e]; mk = m2l_mask[G.list_off + e] | (uint32_t) m2l_mask_lo[G.list_off + e] << 8; }
+		};
+		auto publish = [&](uint32_t chunk, uint32_t id, uint32_t mk) {  // my slot's id/masks, at least one barrier before the chunk is issued
+			const int r = chunk % 3;
+			S.sid[r][tid] = id; S.smask[r][tid] = (uint8_t) mk; S.smask_lo[r][tid] = (uint8_t) (mk >> 8);
+		};
 		auto issue = [&](uint32_t chunk, int buf) {
-			const uint32_t e = chunk * kM2LChunk + my_slot;
-			if (e < G.list_cnt) {
-				const uint32_t id = m2l_id[G.list_off + e];
-				float4* dst = reinterpret_cast<float4*>(sM[buf]) + my_slot * S4;
-				const float4* src = M4 + (size_t) id * S4;
+			const uint32_t ns = min((uint32_t) CH, G.list_cnt - chunk * CH);
+			const uint32_t* ids = S.sid[chunk % 3];
+			float4* dst = reinterpret_cast<float4*>(S.sM[buf]);
 #pragma unroll
-				for (int j = 0; j < PER; ++j)
-					if (part * PER + j < S4) cp_async16(dst + part * PER + j, src + part * PER + j);
-				if (part == 0) cp_async16(&sgeom[buf][my_slot], geom + id);
-				if (part == TPS - 1) smask[buf][my_slot] = m2l_mask[G.list_off + e];
+			for (int r = 0; r < S4; ++r) {
+				const uint32_t piece = tid + r * CH, slot = piece / S4, j = piece - slot * S4;
+				if (slot < ns) cp_async16(dst + piece, M4 + (size_t) ids[slot] * S4 + j);
 			}
+			if (tid < ns) cp_async16(&S.sgeom[buf][tid], geom + ids[tid]);
 			cp_async_commit();
 		};
+		uint32_t id_n, mk_n;
+		fetch(0, id_n, mk_n);
+		publish(0, id_n, mk_n);
+		fetch(1, id_n, mk_n);
+		publish(1, id_n, mk_n);
+		fetch(2, id_n, mk_n);
+		__syncthreads();
 		issue(0, 0);
 		for (uint32_t ch = 0; ch < nchunks; ++ch) {
 			const int cur = ch & 1;
 			cp_async_wait_all();
-			__syncthreads();  // chunk ch has landed for everyone; everyone has finished chunk ch-1
+			__syncthreads();  // chunk ch has landed for everyone; everyone has finished chunk ch-1; ids of ch+1 are visible
 			if (ch + 1 < nchunks) issue(ch + 1, cur ^ 1);
-			const uint32_t ns = min((uint32_t) kM2LChunk, G.list_cnt - ch * kM2LChunk);
-			if (NT == 8) {
-				for (uint32_t s = lane; s < ns; s += 32)
-					if (smask[cur][s] >> w & 1u) { m2l_one<P>(Lacc, tg, sgeom[cur][s], sM[cur] + s * STRIDE, eps2); any = true; }
-			} else {
-				for (uint32_t s = threadIdx.x; s < ns; s += NTHREADS) { m2l_one<P>(Lacc, tg, sgeom[cur][s], sM[cur] + s * STRIDE, eps2); any = true; }
+			const uint32_t ns = min((uint32_t) CH, G.list_cnt - ch * CH);
+			const uint8_t* mk_acc = S.smask[ch % 3];
+			const uint8_t* mk_lo = S.smask_lo[ch % 3];
+			// ---- compact the accepted slots of my target into the two order classes ----
+			uint32_t cnt_h = 0, cnt_l = 0;
+			constexpr int PERW = NT == 8 ? CH / 32 : 1;  // slots per lane
+			const uint32_t s0 = NT == 8 ? 0u : 32u * w;
+#pragma unroll
+			for (int i = 0; i < PERW; ++i) {
+				const uint32_t s = s0 + lane + 32 * i;
+				bool acc = false, lo = false;
+				if (s < ns) {
+					acc = NT == 8 ? (mk_acc[s] >> w & 1u) : true;
+					lo = (mk_lo[s] >> (NT == 8 ? w : 0u)) & 1u;
+				}
+				const bool hi = acc && !lo;
+				const unsigned bh = __ballot_sync(0xffffffffu, hi), bl = __ballot_sync(0xffffffffu, lo);
+				if (hi) S.list_hi[w][cnt_h + __popc(bh & lt_mask)] = (uint8_t) (s - s0);
+				if (lo) S.list_lo[w][cnt_l + __popc(bl & lt_mask)] = (uint8_t) (s - s0);
+				cnt_h += __popc(bh); cnt_l += __popc(bl);
 			}
+			__syncwarp();
+			any = any || (cnt_h + cnt_l) != 0;
+			for (uint32_t k = lane; k < cnt_h; k += 32) {
+				const uint32_t s = s0 + S.list_hi[w][k];
+				m2l_one<P, P>(Lacc, tg, S.sgeom[cur][s], S.sM[cur] + s * STRIDE, eps2);
+			}
+			for (uint32_t k = lane; k < cnt_l; k += 32) {
+				const uint32_t s = s0 + S.list_lo[w][k];
+				m2l_one<P, PL>(Lacc, tg, S.sgeom[cur][s], S.sM[cur] + s * STRIDE, eps2);
+			}
+			// ids of chunk ch+2 become visible at the next barrier (ring slot (ch+2)%3 was last read for chunk ch-1,
+			// which every warp finished before this iteration's barrier); the registers then prefetch chunk ch+3
+			publish(ch + 2, id_n, mk_n);
+			fetch(ch + 3, id_n, mk_n);
 		}
-		if (!__any_sync(0xffffffffu, any)) continue;
+		if (!any) continue;  // warp-uniform
 		// warp reduction, then lane a adds coefficient a (L[0], the potential term, is not carried)
 #pragma unroll
 		for (int a = 1; a < E::NC; ++a) {
@@ -154,10 +208,12 @@ __global__ void __launch_bounds__(128) k_l2l(const Ctrl* __restrict__ c, int l, 
 template <int P>
 static void m2l_t(Sim& s) {
 	const float eps2 = s.cfg.softening * s.cfg.softening;
-	k_m2l<P, 8><<<kNumSM * 16, 256, 0, s.stream>>>(s.ctrl, s.pools.items[0], s.pools.items_cap, s.geom, s.M, s.L, s.pools.m2l_id,
-	                                              s.pools.m2l_mask, eps2);
-	k_m2l<P, 1><<<kNumSM * 16, 128, 0, s.stream>>>(s.ctrl, s.pools.items[1], s.pools.items_cap, s.geom, s.M, s.L, s.pools.m2l_id,
-	                                              s.pools.m2l_mask, eps2);
+	cudaFuncSetAttribute(k_m2l<P, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(M2LShared<P, 8>));
+	cudaFuncSetAttribute(k_m2l<P, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(M2LShared<P, 1>));
+	k_m2l<P, 8><<<kNumSM * 2, 256, sizeof(M2LShared<P, 8>), s.stream>>>(s.ctrl, s.pools.items[0], s.pools.items_cap, s.geom, s.M, s.L,
+	                                                                  s.pools.m2l_id, s.pools.m2l_mask, s.pools.m2l_mask_lo, eps2);
+	k_m2l<P, 1><<<kNumSM * 4, 128, sizeof(M2LShared<P, 1>), s.stream>>>(s.ctrl, s.pools.items[1], s.pools.items_cap, s.geom, s.M, s.L,
+	                                                                  s.pools.m2l_id, s.pools.m2l_mask, s.pools.m2l_mask_lo, eps2);
 }
 template <int P>
 static void l2l_t(Sim& s) {

@@ -43,13 +43,17 @@ constexpr int kTravBatches = kTravCand / 32;      // 64
 // (the rounding boundary below 0.25, ties go to the even 0.25)  <=>  d2/4 - ext2 > d2 * 2^-27,
 // where d2/4 and d2*2^-27 are exact and the subtraction is exact whenever the outcome is in
 // doubt (Sterbenz: ext2 in [d2/8, d2/2]); outside that range the sign is unambiguous.
-__device__ __forceinline__ bool mac_accept(float ax, float ay, float az, float ad, const float4& b, float ratio_sq, bool quarter) {
+// Returns 0 = not accepted, 1 = accepted (order P), 2 = accepted and well enough separated for order P-1
+// (ext2 < tau * d2, an implementation choice that does not touch the lists; mirrored in FP32 by the oracle).
+__device__ __forceinline__ unsigned mac_classify(float ax, float ay, float az, float ad, const float4& b, float ratio_sq, bool quarter, float tau) {
 	const float dx = __fsub_rn(b.x, ax), dy = __fsub_rn(b.y, ay), dz = __fsub_rn(b.z, az);
 	const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 	const float ext = __fadd_rn(ad, b.w);
 	const float ext2 = __fmul_rn(__fmul_rn(0.75f, ext), ext);
-	if (quarter) return __fsub_rn(__fmul_rn(0.25f, d2), ext2) > __fmul_rn(d2, 7.450580596923828125e-9f);  // 2^-27
-	return __fdiv_rn(ext2, d2) < ratio_sq;
+	bool accept;
+	if (quarter) accept = __fsub_rn(__fmul_rn(0.25f, d2), ext2) > __fmul_rn(d2, 7.450580596923828125e-9f);  // 2^-27
+	else accept = __fdiv_rn(ext2, d2) < ratio_sq;
+	return accept ? (ext2 < __fmul_rn(tau, d2) ? 2u : 1u) : 0u;
 }
 
 __global__ void k_traverse_init(Ctrl* c, const uint2* __restrict__ info, uint32_t* near0, Group* q1) {
@@ -89,6 +93,7 @@ struct TraverseArgs {
 	uint64_t p2p_cap;
 	uint32_t* m2l_id;
 	uint8_t* m2l_mask;
+	uint8_t* m2l_mask_lo;
 	uint64_t m2l_cap;
 	Segment* seg;
 	uint32_t seg_cap;
@@ -99,6 +104,7 @@ struct TraverseArgs {
 	Group* items1;
 	uint32_t items_cap;
 	float ratio_sq;
+	float tau;
 	int round;
 };
 
@@ -106,11 +112,11 @@ struct TravSmem {
 	float4 cgeom[kTravCand];
 	uint32_t cid[kTravCand];
 	uint8_t cflag[kTravCand];               // bit0: non-empty, bit1: has children
-	uint32_t bal[3][8][kTravBatches];       // ballots per (list, target, batch): 0 = M2L, 1 = near, 2 = P2P
+	uint32_t bal[4][8][kTravBatches];       // ballots per (list, target, batch): 0 = M2L, 1 = near, 2 = P2P, 3 = M2L at low order
 	uint32_t pre[3][8][kTravBatches];       // exclusive prefix of their popcounts over the batches
 	uint32_t uni[kTravBatches], upre[kTravBatches];  // union of the M2L ballots over the targets, and its prefix
-	uint32_t chunk_cnt[4][8];               // per-chunk totals: 0 = M2L (per target), 1 = near, 2 = P2P, 3 = next-round candidate slots
-	uint32_t total[4][8];                   // per-group totals
+	uint32_t chunk_cnt[5][8];               // per-chunk totals: 0 = M2L (per target), 1 = near, 2 = P2P, 3 = next-round candidate slots, 4 = low-order M2L
+	uint32_t total[5][8];                   // per-group totals
 	uint32_t off[3][8];                     // reserved offsets: [0][0] = M2L group list, [1][t] near, [2][t] P2P
 	uint32_t running[3][8];
 	uint32_t warp_sums[32];
@@ -150,7 +156,7 @@ __global__ void __launch_bounds__(kTravThreads) k_traverse(const TraverseArgs a)
 		const float4 tg = a.geom[G.first + my_t];
 		const uint2 ti = a.info[G.first + my_t];
 		const bool t_act = ti.y > 0, t_ch = ti.x != 0;
-		if (tid < 32) { S.total[tid >> 3][tid & 7] = 0; }
+		if (tid < 40) { S.total[tid >> 3][tid & 7] = 0; }
 		const uint32_t nchunks = (G.list_cnt + kTravEntries - 1) / kTravEntries;
 		for (int pass = 0; pass < 2; ++pass) {
 			if (pass == 1) {
@@ -206,7 +212,7 @@ __global__ void __launch_bounds__(kTravThreads) k_traverse(const TraverseArgs a)
 						S.cgeom[s] = a.geom[id];
 						S.cflag[s] = (uint8_t) ((ci.y > 0 ? 1u : 0u) | (ci.x ? 2u : 0u));
 					}
-					if (tid < 32) S.chunk_cnt[tid >> 3][tid & 7] = 0;
+					if (tid < 40) S.chunk_cnt[tid >> 3][tid & 7] = 0;
 					__syncthreads();
 					// ---- B. classify: (target, batch) pairs round-robin over the warps ----
 					const uint32_t nb = (ncand + 31) / 32;
@@ -218,15 +224,17 @@ __global__ void __launch_bounds__(kTravThreads) k_traverse(const TraverseArgs a)
 							const unsigned fl = S.cflag[s];
 							if (fl & 1u) {
 								const bool same = S.cid[s] == G.first + t;
-								const bool accept = !same && mac_accept(tg.x, tg.y, tg.z, tg.w, S.cgeom[s], a.ratio_sq, quarter);
-								code = accept ? 1u : ((t_ch || (fl & 2u)) ? 2u : 3u);
+								const unsigned cls = same ? 0u : mac_classify(tg.x, tg.y, tg.z, tg.w, S.cgeom[s], a.ratio_sq, quarter, a.tau);
+								code = cls ? (cls == 2u ? 4u : 1u) : ((t_ch || (fl & 2u)) ? 2u : 3u);
 							}
 						}
-						const unsigned m_acc = __ballot_sync(0xffffffffu, code == 1u), m_near = __ballot_sync(0xffffffffu, code == 2u),
+						const unsigned m_lo = __ballot_sync(0xffffffffu, code == 4u);
+						const unsigned m_acc = __ballot_sync(0xffffffffu, code == 1u) | m_lo, m_near = __ballot_sync(0xffffffffu, code == 2u),
 						               m_p2p = __ballot_sync(0xffffffffu, code == 3u);
 						const unsigned m_ch = __ballot_sync(0xffffffffu, code == 2u && (S.cflag[s < ncand ? s : 0] & 2u));
 						if (lane == 0) {
-							S.bal[0][t][b] = m_acc; S.bal[1][t][b] = m_near; S.bal[2][t][b] = m_p2p;
+							S.bal[0][t][b] = m_acc; S.bal[1][t][b] = m_near; S.bal[2][t][b] = m_p2p; S.bal[3][t][b] = m_lo;
+							if (m_lo) atomicAdd(&S.chunk_cnt[4][t], (uint32_t) __popc(m_lo));
 							if (m_near) atomicAdd(&S.chunk_cnt[3][t], 8u * __popc(m_ch) + __popc(m_near & ~m_ch));
 						}
 					}
@@ -252,7 +260,7 @@ __global__ void __launch_bounds__(kTravThreads) k_traverse(const TraverseArgs a)
 					}
 					__syncthreads();
 					if (pass == 0) {
-						if (tid < 32) S.total[tid >> 3][tid & 7] += S.chunk_cnt[tid >> 3][tid & 7];
+						if (tid < 40) S.total[tid >> 3][tid & 7] += S.chunk_cnt[tid >> 3][tid & 7];
 						if (tid == 32) S.m2l_total += S.u_total;
 					}
 				}
@@ -269,11 +277,12 @@ __global__ void __launch_bounds__(kTravThreads) k_traverse(const TraverseArgs a)
 					for (uint32_t b = w; b < nb; b += 8) {
 						const uint32_t u = S.uni[b];
 						if (u >> lane & 1u) {
-							unsigned am = 0;
-							for (uint32_t tt = 0; tt < nt; ++tt) am |= (S.bal[0][tt][b] >> lane & 1u) << tt;
+							unsigned am = 0, al = 0;
+							for (uint32_t tt = 0; tt < nt; ++tt) { am |= (S.bal[0][tt][b] >> lane & 1u) << tt; al |= (S.bal[3][tt][b] >> lane & 1u) << tt; }
 							const uint32_t pos = S.off[0][0] + S.running[0][0] + S.upre[b] + __popc(u & lt_mask);
 							a.m2l_id[pos] = S.cid[32 * b + lane];
 							a.m2l_mask[pos] = (uint8_t) am;
+							a.m2l_mask_lo[pos] = (uint8_t) al;
 						}
 					}
 					__syncthreads();
@@ -310,8 +319,8 @@ __global__ void __launch_bounds__(kTravThreads) k_traverse(const TraverseArgs a)
 				}
 			}
 		} else if (tid == 32) {
-			uint32_t inter = 0, p2pn = 0, nearn = 0;
-			for (uint32_t t = 0; t < nt; ++t) { inter += S.total[0][t]; p2pn += S.total[2][t]; nearn += S.total[1][t]; }
+			uint32_t inter = 0, p2pn = 0, nearn = 0, low = 0;
+			for (uint32_t t = 0; t < nt; ++t) { inter += S.total[0][t]; p2pn += S.total[2][t]; nearn += S.total[1][t]; low += S.total[4][t]; }
 			if (S.m2l_total) {
 				const int which = nt == 8 ? 0 : 1;
 				const uint32_t ii = atomicAdd(&c->items_count[which], 1u);
@@ -322,6 +331,7 @@ __global__ void __launch_bounds__(kTravThreads) k_traverse(const TraverseArgs a)
 				} else atomicOr(&c->status, kOvfItems);
 			}
 			atomicAdd(&c->stat_m2l_inter, (unsigned long long) inter);
+			if (low) atomicAdd(&c->stat_m2l_low, (unsigned long long) low);
 			atomicAdd(&c->stat_p2p_entries, (unsigned long long) p2pn);
 			atomicAdd(&c->stat_near, (unsigned long long) nearn);
 		}
@@ -334,9 +344,10 @@ void launch_traversal(Sim& s) {
 	k_traverse_init<<<1, 32, 0, s.stream>>>(s.ctrl, s.info, p.near[0], p.gq[1]);
 	TraverseArgs a{};
 	a.c = s.ctrl; a.geom = s.geom; a.info = s.info; a.near_ref = s.near_ref; a.p2p_head = s.p2p_head;
-	a.near_cap = p.near_cap; a.p2p = p.p2p; a.p2p_cap = p.p2p_cap; a.m2l_id = p.m2l_id; a.m2l_mask = p.m2l_mask; a.m2l_cap = p.m2l_cap;
+	a.near_cap = p.near_cap; a.p2p = p.p2p; a.p2p_cap = p.p2p_cap; a.m2l_id = p.m2l_id; a.m2l_mask = p.m2l_mask; a.m2l_mask_lo = p.m2l_mask_lo; a.m2l_cap = p.m2l_cap;
 	a.seg = p.seg; a.seg_cap = p.seg_cap; a.gq_cap = p.gq_cap; a.items8 = p.items[0]; a.items1 = p.items[1]; a.items_cap = p.items_cap;
 	a.ratio_sq = s.cfg.mac_ratio * s.cfg.mac_ratio;
+	a.tau = s.cfg.order >= 3 ? s.cfg.low_order_tau : 0.0f;  // order P-1 >= 2 only
 	for (int r = 1; r <= (int) s.cfg.max_depth; ++r) {
 		k_round_prep<<<1, 32, 0, s.stream>>>(s.ctrl, r);
 		a.round = r;

@@ -53,6 +53,9 @@ def lib():
         L.orc_ncoef.restype = C.c_uint32
         L.orc_fmm_field.argtypes = [C.c_void_p, C.c_uint64, f32p, C.c_uint32, C.c_double, f64p, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_set_low_order_tau.argtypes = [C.c_double]
+        L.orc_low_count.restype = C.c_uint64
+        L.orc_all_count.restype = C.c_uint64
         L.orc_naive_step_as_written.argtypes = [C.c_uint64, f32p, C.c_float, C.c_float, C.c_uint32]
         L.orc_naive_step_as_written.restype = C.c_float
         L.orc_direct_step.argtypes = [C.c_uint64, f32p, C.c_float, C.c_float, C.c_float, C.c_uint32, C.c_int, C.c_int]
@@ -129,7 +132,10 @@ class Tree:
         self.rounds = lib().orc_traverse_rounds(self._h)
         return self.m2l, self.p2p
 
-    def fmm_field(self, posq_sorted, order, eps, want_phi=False, want_expansions=False):
+    def fmm_field(self, posq_sorted, order, eps, want_phi=False, want_expansions=False, low_order_tau=0.0):
+        """FP64 FMM over the traversal's lists. low_order_tau > 0 mirrors the product's adaptive-order
+        M2L (pairs with ext2 < tau*d2 at order-1); self.low_fraction reports how many pairs that was."""
+        lib().orc_set_low_order_tau(float(np.float32(low_order_tau)))
         posq = np.ascontiguousarray(posq_sorted, np.float32)
         n = posq.shape[0]
         g = np.empty((n, 3), np.float64)
@@ -138,6 +144,9 @@ class Tree:
         M = np.empty((self.num_nodes, nc), np.float64) if want_expansions else None
         L = np.empty((self.num_nodes, nc), np.float64) if want_expansions else None
         lib().orc_fmm_field(self._h, n, posq, order, eps, g, _ptr(phi), _ptr(M), _ptr(L), 1)
+        self.low_count = lib().orc_low_count()
+        self.low_fraction = self.low_count / max(1, lib().orc_all_count())
+        lib().orc_set_low_order_tau(0.0)
         out = [g]
         if want_phi:
             out.append(phi)

@@ -323,6 +323,12 @@ std::uint32_t orc_ncoef(std::uint32_t p) { return (p + 1) * (p + 2) * (p + 3) / 
 // 1 = centre of |charge| of the node's particles (exploration / product option).
 static int g_centre_mode = 0;
 void orc_set_centre_mode(int mode) { g_centre_mode = mode; }
+// Exploration: M2L pairs with ext2/d2 < g_low_tau are evaluated at order p-1 (0 = off).
+static double g_low_tau = 0.0;
+static unsigned long long g_low_count = 0, g_all_count = 0;
+void orc_set_low_order_tau(double tau) { g_low_tau = tau; g_low_count = g_all_count = 0; }
+unsigned long long orc_low_count(void) { return g_low_count; }
+unsigned long long orc_all_count(void) { return g_all_count; }
 
 void orc_fmm_field(void* h, std::uint64_t n, const float* posq, std::uint32_t order, double eps,
                    double* g3, double* phi, double* multipoles, double* locals, int threads) {
@@ -383,9 +389,22 @@ void orc_fmm_field(void* h, std::uint64_t n, const float* posq, std::uint32_t or
 		kernel_taylor(I, x, eps2, a.data());
 		const double* Ms = &M[src * nc];
 		double* Lt = &L[tgt * nc];
+		int pe = p;
+		++g_all_count;
+		if (g_low_tau > 0 && p >= 3) {
+			// FP32, same operation order as the device (traverse.cu mac_classify): ext2 < tau * d2
+			const float* ga = &t.geom[4 * tgt];
+			const float* gb = &t.geom[4 * src];
+			const float fx = gb[0] - ga[0], fy = gb[1] - ga[1], fz = gb[2] - ga[2];
+			const float d2 = (fx * fx + fy * fy) + fz * fz;
+			const float ext = ga[3] + gb[3];
+			const float ext2 = (0.75f * ext) * ext;
+			const float tau = (float) g_low_tau;
+			if (ext2 < tau * d2) { pe = p - 1; ++g_low_count; }
+		}
 		for (int nn = 0; nn < nc; ++nn)
 			for (int mm = 0; mm < nc; ++mm) {
-				if (I.ord[nn] + I.ord[mm] > p) continue;
+				if (I.ord[nn] + I.ord[mm] > pe) continue;
 				const int s = I.at(I.ex[nn] + I.ex[mm], I.ey[nn] + I.ey[mm], I.ez[nn] + I.ez[mm]);
 				const double sign = (I.ord[mm] & 1) ? -1.0 : 1.0;
 				// D_{n+m}/n! = (n+m)!/n! a_{n+m}

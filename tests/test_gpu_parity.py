@@ -64,15 +64,21 @@ def test_keys_tree_lists_bit_exact(kind, n, cap):
     sim.close()
 
 
-@pytest.mark.parametrize("kind,n,order", [("uniform", 20000, 4), ("plummer", 20000, 4), ("plummer", 20000, 3), ("uniform", 20000, 2)])
-def test_expansions_and_accelerations(kind, n, order):
+@pytest.mark.parametrize("kind,n,order,tau", [("uniform", 20000, 4, None), ("plummer", 20000, 4, None), ("plummer", 20000, 4, 0.0),
+                                               ("plummer", 20000, 3, None), ("uniform", 20000, 2, None)])
+def test_expansions_and_accelerations(kind, n, order, tau):
+    """tau = None: the default adaptive-order M2L (pairs with ext2 < 0.13 d2 at order P-1); 0.0: order P everywhere."""
     P = workloads.GENERATORS[kind](n)
-    sim = make_sim(P, order=order)
+    sim = make_sim(P, order=order) if tau is None else make_sim(P, order=order, low_order_tau=tau)
     sim.step()
     o = sorted_system(P)
     tr = o["tree"]
     tr.traverse(0.5)
-    g_fmm, Mo, Lo = tr.fmm_field(o["posq"], order, 0.01, want_expansions=True)
+    tau_eff = float(sim.config.low_order_tau) if order >= 3 else 0.0
+    g_fmm, Mo, Lo = tr.fmm_field(o["posq"], order, 0.01, want_expansions=True, low_order_tau=tau_eff)
+    assert sim.stats()["m2l_interactions_low"] == tr.low_count
+    if tau is None and order >= 3:
+        assert 0.4 < tr.low_fraction < 0.9
     M, L = sim.expansions()
     ne = tr.leaf_count > 0
     assert rms_rel(M[ne], Mo[ne]) < EXP_TOL
@@ -175,7 +181,9 @@ def test_edge_cases():
         assert np.array_equal(packed(m2l), directed(m2l_o)) and np.array_equal(packed(p2p), directed(p2p_o))
         gd = oracle.direct_field(o["posq"], None, 0.01)
         scale = (o["P"][:, 9] / o["P"][:, 8])[:, None]
-        assert rms_rel(sim.accelerations(), gd * scale) < ACC_TOL
+        g_fmm = o["tree"].fmm_field(o["posq"], 4, 0.01, low_order_tau=float(sim.config.low_order_tau))
+        assert rms_rel(sim.accelerations(), g_fmm * scale) < 2e-6      # identical to the FP64 FMM over the same lists
+        assert rms_rel(sim.accelerations(), gd * scale) < 3e-3         # a 300-body system with a 40-body point clump
         sim.close()
     # particles outside the root box are clamped into the boundary cells: keys, tree and lists still match the
     # oracle bit for bit (the expansions' error bound needs particles inside their cell, so no accuracy claim here)
