@@ -232,20 +232,31 @@ def main():
     stage_ms = {k: v / K for k, v in stage_ms.items()}
 
     # ---- end to end through the C ABI with host buffers --------------------------------
-    e2e = None
-    if world == 1:
-        out = torch.empty_like(host).pin_memory()
-        sim.particles_into_ptr(out.data_ptr(), n)  # warm the export path
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            sim.set_particles_ptr(out.data_ptr(), n)   # H2D: this step's input state from pinned host memory
-            sim.step()
-            sim.particles_into_ptr(out.data_ptr(), n)  # D2H: the step's result
-        barrier()
-        e2e_t = time.perf_counter() - t0
-        e2e = {"value": n * args.e2e_steps / e2e_t, "unit": UNIT, "h2d_bytes_per_step": 48 * n, "d2h_bytes_per_step": 48 * n,
-               "ms_per_step": 1e3 * e2e_t / args.e2e_steps, "steps": args.e2e_steps}
+    # every step: H2D of this rank's slice of the state from pinned host memory (set_owned_particles, which
+    # also re-assembles the full state over NVLink when N > 1), the step, D2H of the rank's updated slice.
+    first, count = sim.owned_range()
+    out = torch.empty((max(count, 1) + (n // world) // 8 + 1024, 12), dtype=torch.float32).pin_memory()  # owned counts drift by a few leaves
+    sim.owned_particles_into_ptr(out.data_ptr(), out.shape[0])  # warm the export path
+    barrier()
+    h2d = d2h = 0
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        first, count = sim.owned_range()
+        sim.set_owned_particles_ptr(out.data_ptr(), count)
+        h2d += 48 * count
+        sim.step()
+        first, count = sim.owned_range()
+        sim.owned_particles_into_ptr(out.data_ptr(), out.shape[0])
+        d2h += 48 * count
+    barrier()
+    e2e_t = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([e2e_t, float(h2d), float(d2h)], device="cuda", dtype=torch.float64)
+        mx = tt.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = tt.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        e2e_t, h2d, d2h = float(mx[0]), float(sm[1]), float(sm[2])
+    e2e = {"value": n * args.e2e_steps / e2e_t, "unit": UNIT, "h2d_bytes_per_step": int(h2d / args.e2e_steps),
+           "d2h_bytes_per_step": int(d2h / args.e2e_steps), "ms_per_step": 1e3 * e2e_t / args.e2e_steps, "steps": args.e2e_steps}
 
     if rank == 0:
         peaks = measured_peaks()

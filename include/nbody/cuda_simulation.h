@@ -1,0 +1,106 @@
+// nbody::CudaSimulation — the B200 FMM solver behind the reference's Simulation API.
+//
+// Drop-in for nbody::OpenClSimulation (include/nbody/open_cl_simulation.h:19-203):
+// same base class instantiation Simulation<float, 16-byte float4>, same constructor
+// shape (bounds, particles, timeStep, log), same step()/particles() contract
+// (src/open_cl_simulation.cpp:53-106: step() is blocking and returns the new time,
+// particles() returns the state in tree order). Header-only: it only forwards to the C
+// ABI in include/nbody_cuda.h (link with -lnbody_cuda); failures become
+// std::runtime_error like the reference's (src/open_cl_simulation.cpp:630,648,767).
+#pragma once
+
+#include <cstdint>
+#include <cstring>
+#include <initializer_list>
+#include <ostream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../nbody_cuda.h"
+#include "simulation.h"
+
+namespace nbody {
+namespace device {
+
+using scalar_t = float;
+
+// 16-byte aligned 4-float vector with array access; behaves like the reference's
+// device::vector_t (include/nbody/device/types.h:53-74) without the OpenCL headers.
+class alignas(16) vector_t final {
+public:
+	vector_t() : _v{0.0f, 0.0f, 0.0f, 0.0f} {}
+	vector_t(std::initializer_list<scalar_t> list) : _v{0.0f, 0.0f, 0.0f, 0.0f} {
+		unsigned i = 0;
+		for (scalar_t x : list) {
+			if (i < 4) _v[i++] = x;
+		}
+	}
+	scalar_t& operator[](unsigned index) { return _v[index]; }
+	scalar_t const& operator[](unsigned index) const { return _v[index]; }
+
+private:
+	scalar_t _v[4];
+};
+
+}  // namespace device
+
+class CudaSimulation final : public Simulation<device::scalar_t, device::vector_t> {
+public:
+	// Mirrors OpenClSimulation(bounds, particles, timeStep, log); `config` (optional) overrides the
+	// reference's compile-time constants (MAC ratio, softening, capacity, ...), see nbody_cuda_config.
+	CudaSimulation(device::vector_t bounds, std::vector<Particle> particles, Scalar timeStep, std::ostream& log,
+	               const nbody_cuda_config* config = nullptr)
+	    : _log(log), _time(0.0f) {
+		static_assert(sizeof(Particle) == sizeof(nbody_particle), "Particle must be the 48-byte boundary record");
+		nbody_cuda_config cfg;
+		if (config) cfg = *config; else nbody_cuda_default_config(&cfg);
+		for (int k = 0; k < 4; ++k) cfg.bounds[k] = bounds[k];
+		cfg.time_step = timeStep;
+		_log << "Creating the CUDA simulation (" << particles.size() << " particles).\n";
+		check(nbody_cuda_create(&cfg, reinterpret_cast<const nbody_particle*>(particles.data()), particles.size(), &_sim));
+	}
+	CudaSimulation(const CudaSimulation&) = delete;
+	CudaSimulation& operator=(const CudaSimulation&) = delete;
+	~CudaSimulation() override { nbody_cuda_destroy(_sim); }
+
+	Scalar step() override {
+		_log << "Starting a new step (t=" << _time << ").\n";
+		check(nbody_cuda_step(_sim, &_time));
+		_log << "Step finished.\n";
+		return _time;
+	}
+
+	// Tree (Morton / DFS leaf) order, like OpenClSimulation::particles(); see permutation().
+	std::vector<Particle> particles() const override {
+		const std::uint64_t n = nbody_cuda_num_particles(_sim);
+		std::vector<Particle> out(n, Particle(Vector(), Vector(), 0.0f, 0.0f));
+		check(nbody_cuda_get_particles(_sim, reinterpret_cast<nbody_particle*>(out.data()), n));
+		return out;
+	}
+
+	// permutation()[i] = index in the constructor's vector of the particle now at position i
+	// (the reference loses particle identity across steps).
+	std::vector<std::uint32_t> permutation() const {
+		std::vector<std::uint32_t> p(nbody_cuda_num_particles(_sim));
+		check(nbody_cuda_get_permutation(_sim, p.data(), p.size()));
+		return p;
+	}
+
+	nbody_cuda_stats stats() const {
+		nbody_cuda_stats s;
+		check(nbody_cuda_get_stats(_sim, &s));
+		return s;
+	}
+
+private:
+	static void check(int rc) {
+		if (rc != NBODY_OK) throw std::runtime_error(std::string("nbody_cuda: ") + nbody_cuda_last_error());
+	}
+
+	std::ostream& _log;
+	nbody_cuda_sim* _sim = nullptr;
+	Scalar _time;
+};
+
+}  // namespace nbody

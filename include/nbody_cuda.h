@@ -163,8 +163,13 @@ int nbody_cuda_comm_unique_id(uint8_t id[128]);
 int nbody_cuda_create_distributed(const nbody_cuda_config* cfg, const nbody_particle* local_particles, uint64_t n_local,
                                   uint64_t n_global, uint64_t global_offset, int rank, int world, const uint8_t id[128],
                                   nbody_cuda_sim** out);
-/* Range [first, first+count) of the tree-ordered particle array owned by this rank after the last step. */
+/* Range [first, first+count) of the tree-ordered particle array owned by this rank after the last step
+ * (before the first step: the slice passed to nbody_cuda_create_distributed). Single GPU: [0, n). */
 int nbody_cuda_owned_range(nbody_cuda_sim* sim, uint64_t* first, uint64_t* count);
+/* Host <-> device transfer of this rank's OWNED slice only (count particles, tree order): the distributed
+ * counterparts of get_particles / set_particles. set_ is collective: every rank must call it. */
+int nbody_cuda_get_owned_particles(nbody_cuda_sim* sim, nbody_particle* out, uint64_t capacity);
+int nbody_cuda_set_owned_particles(nbody_cuda_sim* sim, const nbody_particle* particles, uint64_t n);
 
 const char* nbody_cuda_last_error(void);
 

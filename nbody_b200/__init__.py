@@ -25,6 +25,7 @@ EXPORTED_SYMBOLS = [
     "nbody_cuda_num_particles", "nbody_cuda_get_particles", "nbody_cuda_get_permutation", "nbody_cuda_get_accelerations",
     "nbody_cuda_get_keys", "nbody_cuda_get_tree", "nbody_cuda_get_lists", "nbody_cuda_get_expansions", "nbody_cuda_get_stats",
     "nbody_cuda_direct_field", "nbody_cuda_comm_unique_id", "nbody_cuda_create_distributed", "nbody_cuda_owned_range",
+    "nbody_cuda_get_owned_particles", "nbody_cuda_set_owned_particles",
     "nbody_cuda_last_error",
 ]
 
@@ -89,6 +90,8 @@ def load_library():
     L.nbody_cuda_comm_unique_id.argtypes = [vp]
     L.nbody_cuda_create_distributed.argtypes = [C.POINTER(Config), vp, u64, u64, u64, C.c_int, C.c_int, vp, C.POINTER(vp)]
     L.nbody_cuda_owned_range.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
+    L.nbody_cuda_get_owned_particles.argtypes = [vp, vp, u64]
+    L.nbody_cuda_set_owned_particles.argtypes = [vp, vp, u64]
     L.nbody_cuda_last_error.restype = C.c_char_p
     _lib = L
     return L
@@ -137,6 +140,7 @@ class CudaSimulation:
         if _distributed is None:
             _check(self._lib.nbody_cuda_create(C.byref(self.config), _ptr(particles), particles.shape[0], C.byref(self._h)))
         else:
+            import torch  # noqa: F401  (see comm_unique_id)
             d = _distributed
             uid = np.frombuffer(d["unique_id"], np.uint8).copy()
             _check(self._lib.nbody_cuda_create_distributed(C.byref(self.config), _ptr(particles), particles.shape[0],
@@ -223,6 +227,18 @@ class CudaSimulation:
         _check(self._lib.nbody_cuda_get_stats(self._h, C.byref(st)))
         return st.as_dict()
 
+    def owned_particles_into_ptr(self, ptr, capacity):
+        _check(self._lib.nbody_cuda_get_owned_particles(self._h, C.c_void_p(ptr), capacity))
+
+    def set_owned_particles_ptr(self, ptr, n):
+        _check(self._lib.nbody_cuda_set_owned_particles(self._h, C.c_void_p(ptr), n))
+
+    def owned_particles(self):
+        first, count = self.owned_range()
+        out = np.empty((count, PARTICLE_FLOATS), np.float32)
+        _check(self._lib.nbody_cuda_get_owned_particles(self._h, _ptr(out), count))
+        return out
+
     def owned_range(self):
         a, b = C.c_uint64(), C.c_uint64()
         _check(self._lib.nbody_cuda_owned_range(self._h, C.byref(a), C.byref(b)))
@@ -254,6 +270,7 @@ def direct_field(src_posq, tgt_pos4, softening=0.01, device=-1, repeats=1):
 
 
 def comm_unique_id():
+    import torch  # noqa: F401  (loads PyTorch's bundled libnccl first so the process holds a single NCCL)
     uid = np.zeros(128, np.uint8)
     _check(load_library().nbody_cuda_comm_unique_id(_ptr(uid)))
     return uid.tobytes()

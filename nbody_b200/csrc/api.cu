@@ -14,6 +14,7 @@ size_t sort_temp_bytes(uint64_t n);
 int comm_step_exchange(Sim& s);                     // comm.cu
 void comm_destroy(Sim& s);                          // comm.cu
 int comm_partition(Sim& s);                         // comm.cu
+int comm_exchange_aos(Sim& s);                      // comm.cu
 
 namespace {
 
@@ -547,6 +548,36 @@ int nbody_cuda_direct_field(int device, const float* src_posq, uint64_t n_src, c
 #undef DF_CHECK
 	cleanup();
 	return rc;
+}
+
+int nbody_cuda_get_owned_particles(nbody_cuda_sim* sim, nbody_particle* out, uint64_t capacity) {
+	Sim* s = reinterpret_cast<Sim*>(sim);
+	if (!s || !out) { set_error("NULL argument"); return NBODY_ERR_INVALID; }
+	if (capacity < s->own_count) { set_error("get_owned_particles: output buffer too small"); return NBODY_ERR_INVALID; }
+	NB_CUDA_CHECK(cudaSetDevice(s->device));
+	launch_export(*s, s->aos_dev, s->n);
+	NB_CUDA_CHECK(cudaMemcpyAsync(out, s->aos_dev + s->own_first, s->own_count * sizeof(nbody_particle), cudaMemcpyDeviceToHost, s->stream));
+	NB_CUDA_CHECK(cudaStreamSynchronize(s->stream));
+	return NBODY_OK;
+}
+
+int nbody_cuda_set_owned_particles(nbody_cuda_sim* sim, const nbody_particle* particles, uint64_t n) {
+	Sim* s = reinterpret_cast<Sim*>(sim);
+	if (!s || !particles) { set_error("NULL argument"); return NBODY_ERR_INVALID; }
+	if (n != s->own_count) { set_error("set_owned_particles: count differs from the owned range"); return NBODY_ERR_INVALID; }
+	NB_CUDA_CHECK(cudaSetDevice(s->device));
+	NB_CUDA_CHECK(cudaMemcpyAsync(s->aos_dev + s->own_first, particles, n * sizeof(nbody_particle), cudaMemcpyHostToDevice, s->stream));
+	if (s->comm) { int rc = comm_exchange_aos(*s); if (rc) return rc; }
+	// the permutation is kept: the caller hands back the particles it read with get_owned_particles
+	{
+		uint32_t* keep = s->orig[1];
+		NB_CUDA_CHECK(cudaMemcpyAsync(keep, s->orig[0], s->n * 4, cudaMemcpyDeviceToDevice, s->stream));
+		launch_import(*s, s->aos_dev, s->n);
+		NB_CUDA_CHECK(cudaMemcpyAsync(s->orig[0], keep, s->n * 4, cudaMemcpyDeviceToDevice, s->stream));
+	}
+	NB_CUDA_CHECK(cudaStreamSynchronize(s->stream));
+	NB_CUDA_CHECK(cudaGetLastError());
+	return NBODY_OK;
 }
 
 int nbody_cuda_owned_range(nbody_cuda_sim* sim, uint64_t* first, uint64_t* count) {

@@ -1,18 +1,215 @@
-// Multi-GPU plumbing (one process per GPU). Filled in by the distributed build;
-// single-GPU simulations never touch it.
+// Multi-GPU: one process per GPU, particles partitioned by Morton-key range.
+//
+// The reference is single-device (src/open_cl_simulation.cpp:627-632); this is new work
+// (SURVEY 8e). Round-1 scheme = the survey's stated fallback: every rank keeps the full,
+// identically ordered particle state and builds the same octree and multipoles (O(N),
+// HBM-bound, a few per cent of a step), while the expensive stages — dual-tree
+// traversal, M2L, P2P/L2P/integration — run only for the targets inside the rank's
+// contiguous slice of the Morton-ordered particle array (slice boundaries snapped to
+// leaf boundaries so a leaf never straddles two ranks). After the step the updated slices
+// (position+charge, velocity+mass, acceleration) are exchanged with one grouped NCCL
+// broadcast per rank over NVLink, which is the all-gather with unequal counts.
+// Determinism of the radix sort and of the tree build makes the replicated structures
+// bit-identical across ranks, so no tree data ever needs to travel.
+#include <dlfcn.h>
+#include <nccl.h>  // types and enums only: the library itself is bound at run time (see NcclApi)
+
+#include <cstring>
+#include <vector>
+
 #include "common.cuh"
 
 namespace nbody {
-int comm_step_exchange(Sim&) { return NBODY_OK; }
-int comm_partition(Sim&) { return NBODY_OK; }
-void comm_destroy(Sim&) {}
+
+// NCCL is resolved with dlopen at the first distributed call instead of being a link-time
+// dependency: a host process that also runs PyTorch already carries its own libnccl.so.2
+// (a newer one than the system's), and two copies of one SONAME cannot coexist. RTLD_NOLOAD
+// first re-uses whatever the process has loaded; a single-GPU run never touches NCCL at all.
+struct NcclApi {
+	ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+	ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+	ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*GroupStart)() = nullptr;
+	ncclResult_t (*GroupEnd)() = nullptr;
+	const char* (*GetErrorString)(ncclResult_t) = nullptr;
+	bool ok = false;
+};
+static NcclApi g_nccl;
+
+static bool nccl_load() {
+	if (g_nccl.ok) return true;
+	void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+	if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+	if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+	if (!h) { set_error(std::string("cannot load libnccl.so.2: ") + dlerror()); return false; }
+	auto sym = [&](const char* name) { return dlsym(h, name); };
+	g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId)) sym("ncclGetUniqueId");
+	g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank)) sym("ncclCommInitRank");
+	g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy)) sym("ncclCommDestroy");
+	g_nccl.AllGather = (decltype(g_nccl.AllGather)) sym("ncclAllGather");
+	g_nccl.Broadcast = (decltype(g_nccl.Broadcast)) sym("ncclBroadcast");
+	g_nccl.GroupStart = (decltype(g_nccl.GroupStart)) sym("ncclGroupStart");
+	g_nccl.GroupEnd = (decltype(g_nccl.GroupEnd)) sym("ncclGroupEnd");
+	g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString)) sym("ncclGetErrorString");
+	g_nccl.ok = g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.CommDestroy && g_nccl.AllGather && g_nccl.Broadcast &&
+	            g_nccl.GroupStart && g_nccl.GroupEnd && g_nccl.GetErrorString;
+	if (!g_nccl.ok) set_error("libnccl.so.2 lacks a required symbol");
+	return g_nccl.ok;
+}
+
+int create_for_comm(const nbody_cuda_config* cfg, uint64_t n, Sim** out);
+void destroy_for_comm(Sim* s);
+
+struct Comm {
+	ncclComm_t comm = nullptr;
+	int rank = 0, world = 1;
+	uint32_t* part_host = nullptr;  // pinned, world + 1
+};
+
+#define NB_NCCL_CHECK(expr)                                                                  \
+	do {                                                                                        \
+		ncclResult_t _r = (expr);                                                                 \
+		if (_r != ncclSuccess) {                                                                  \
+			set_error(std::string(#expr) + ": " + g_nccl.GetErrorString(_r));                          \
+			return NBODY_ERR_COMM;                                                                  \
+		}                                                                                         \
+	} while (0)
+
+// Boundary r = r*N/world, moved down to the first particle of the leaf that contains it.
+__global__ void k_partition(Ctrl* c, int world, uint32_t n, const uint2* __restrict__ info, const uint32_t* __restrict__ nbegin) {
+	const int r = threadIdx.x;
+	if (r > world) return;
+	uint32_t p = (uint32_t) ((uint64_t) n * r / world);
+	if (r == 0) p = 0;
+	if (r == world) { c->part[r] = n; return; }
+	uint32_t node = 0;
+	for (;;) {
+		const uint2 nf = info[node];
+		if (nf.x == 0) break;
+		uint32_t next = nf.x;
+		for (uint32_t k = 0; k < 8; ++k) {
+			const uint32_t cb = nbegin[nf.x + k], cc = info[nf.x + k].y;
+			if (p >= cb && p < cb + cc) { next = nf.x + k; break; }
+		}
+		node = next;
+	}
+	c->part[r] = nbegin[node];
+}
+
+int comm_partition(Sim& s) {
+	Comm& cm = *s.comm;
+	k_partition<<<1, 32, 0, s.stream>>>(s.ctrl, cm.world, (uint32_t) s.n, s.info, s.nbegin);
+	NB_CUDA_CHECK(cudaMemcpyAsync(cm.part_host, s.ctrl->part, sizeof(uint32_t) * (cm.world + 1), cudaMemcpyDeviceToHost, s.stream));
+	NB_CUDA_CHECK(cudaStreamSynchronize(s.stream));  // the one host round trip of a distributed step: 4*(world+1) bytes
+	s.own_first = cm.part_host[cm.rank];
+	s.own_count = cm.part_host[cm.rank + 1] - cm.part_host[cm.rank];
+	return NBODY_OK;
+}
+
+static int exchange(Sim& s, void* buf, size_t elem_bytes) {
+	Comm& cm = *s.comm;
+	NB_NCCL_CHECK(g_nccl.GroupStart());
+	for (int r = 0; r < cm.world; ++r) {
+		const size_t off = (size_t) cm.part_host[r] * elem_bytes, cnt = (size_t) (cm.part_host[r + 1] - cm.part_host[r]) * elem_bytes;
+		if (cnt == 0) continue;
+		char* p = static_cast<char*>(buf) + off;
+		NB_NCCL_CHECK(g_nccl.Broadcast(p, p, cnt, ncclChar, r, cm.comm, s.stream));
+	}
+	NB_NCCL_CHECK(g_nccl.GroupEnd());
+	return NBODY_OK;
+}
+
+int comm_exchange_aos(Sim& s) { return exchange(s, s.aos_dev, sizeof(nbody_particle)); }
+
+int comm_step_exchange(Sim& s) {
+	int rc;
+	if ((rc = exchange(s, s.posq[0], sizeof(float4)))) return rc;
+	if ((rc = exchange(s, s.velm[0], sizeof(float4)))) return rc;
+	if ((rc = exchange(s, s.acc, sizeof(float4)))) return rc;
+	return NBODY_OK;
+}
+
+void comm_destroy(Sim& s) {
+	if (!s.comm) return;
+	if (s.comm->comm) g_nccl.CommDestroy(s.comm->comm);
+	if (s.comm->part_host) cudaFreeHost(s.comm->part_host);
+	delete s.comm;
+	s.comm = nullptr;
+}
+
 }  // namespace nbody
 
+using namespace nbody;
+
 extern "C" {
-int nbody_cuda_comm_unique_id(uint8_t*) { nbody::set_error("distributed mode is not built"); return NBODY_ERR_COMM; }
-int nbody_cuda_create_distributed(const nbody_cuda_config*, const nbody_particle*, uint64_t, uint64_t, uint64_t, int, int,
-                                  const uint8_t*, nbody_cuda_sim**) {
-	nbody::set_error("distributed mode is not built");
-	return NBODY_ERR_COMM;
+
+int nbody_cuda_comm_unique_id(uint8_t* id) {
+	if (!id) { set_error("NULL argument"); return NBODY_ERR_INVALID; }
+	static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+	if (!nccl_load()) return NBODY_ERR_COMM;
+	ncclUniqueId u;
+	NB_NCCL_CHECK(g_nccl.GetUniqueId(&u));
+	std::memcpy(id, &u, 128);
+	return NBODY_OK;
 }
+
+int nbody_cuda_create_distributed(const nbody_cuda_config* cfg, const nbody_particle* local_particles, uint64_t n_local,
+                                  uint64_t n_global, uint64_t global_offset, int rank, int world, const uint8_t* id,
+                                  nbody_cuda_sim** out) {
+	if (!out || !local_particles || !id) { set_error("NULL argument"); return NBODY_ERR_INVALID; }
+	*out = nullptr;
+	if (world < 1 || world > 16 || rank < 0 || rank >= world) { set_error("bad rank / world size (1..16 ranks)"); return NBODY_ERR_INVALID; }
+	if (global_offset + n_local > n_global) { set_error("local slice exceeds the global particle count"); return NBODY_ERR_INVALID; }
+	if (!nccl_load()) return NBODY_ERR_COMM;
+	Sim* s = nullptr;
+	int rc = create_for_comm(cfg, n_global, &s);
+	if (rc) return rc;
+	auto fail = [&](int code) { destroy_for_comm(s); return code; };
+	s->comm = new Comm;
+	Comm& cm = *s->comm;
+	cm.rank = rank; cm.world = world;
+	if (cudaMallocHost((void**) &cm.part_host, sizeof(uint32_t) * (world + 1)) != cudaSuccess) { set_error("pinned allocation failed"); return fail(NBODY_ERR_CUDA); }
+	ncclUniqueId u;
+	std::memcpy(&u, id, 128);
+	ncclResult_t nr = g_nccl.CommInitRank(&cm.comm, world, u, rank);
+	if (nr != ncclSuccess) { set_error(std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(nr)); cm.comm = nullptr; return fail(NBODY_ERR_COMM); }
+	// assemble the global AoS array: every rank contributes its slice (all-gather with unequal counts)
+	std::vector<unsigned long long> h(2 * world, 0ull);
+	unsigned long long* d = nullptr;
+	if (cudaMalloc((void**) &d, sizeof(unsigned long long) * 2 * world) != cudaSuccess) { set_error("cudaMalloc failed"); return fail(NBODY_ERR_CUDA); }
+	const unsigned long long mine[2] = {global_offset, n_local};
+	cudaMemcpyAsync(d + 2 * rank, mine, sizeof(mine), cudaMemcpyHostToDevice, s->stream);
+	nr = g_nccl.AllGather(d + 2 * rank, d, 2, ncclUint64, cm.comm, s->stream);
+	cudaMemcpyAsync(h.data(), d, sizeof(unsigned long long) * 2 * world, cudaMemcpyDeviceToHost, s->stream);
+	cudaStreamSynchronize(s->stream);
+	cudaFree(d);
+	if (nr != ncclSuccess) { set_error(std::string("ncclAllGather: ") + g_nccl.GetErrorString(nr)); return fail(NBODY_ERR_COMM); }
+	unsigned long long covered = 0;
+	for (int r = 0; r < world; ++r) covered += h[2 * r + 1];
+	if (covered != n_global) { set_error("the ranks' slices do not add up to n_global"); return fail(NBODY_ERR_INVALID); }
+	for (int r = 0; r < world; ++r) cm.part_host[r] = (uint32_t) h[2 * r];
+	cm.part_host[world] = (uint32_t) n_global;
+	for (int r = 0; r + 1 < world; ++r)
+		if (h[2 * r] + h[2 * r + 1] != h[2 * (r + 1)]) { set_error("rank slices must be contiguous and ordered by rank"); return fail(NBODY_ERR_INVALID); }
+	s->own_first = global_offset; s->own_count = n_local;
+	if (cudaMemcpyAsync(s->aos_dev + global_offset, local_particles, n_local * sizeof(nbody_particle), cudaMemcpyHostToDevice, s->stream) != cudaSuccess) {
+		set_error("upload failed"); return fail(NBODY_ERR_CUDA);
+	}
+	g_nccl.GroupStart();
+	for (int r = 0; r < world; ++r) {
+		if (h[2 * r + 1] == 0) continue;
+		nbody_particle* p = s->aos_dev + h[2 * r];
+		g_nccl.Broadcast(p, p, h[2 * r + 1] * sizeof(nbody_particle), ncclChar, r, cm.comm, s->stream);
+	}
+	nr = g_nccl.GroupEnd();
+	if (nr != ncclSuccess) { set_error(std::string("ncclBroadcast: ") + g_nccl.GetErrorString(nr)); return fail(NBODY_ERR_COMM); }
+	launch_import(*s, s->aos_dev, n_global);
+	cudaMemsetAsync(s->acc, 0, n_global * sizeof(float4), s->stream);
+	if (cudaStreamSynchronize(s->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) { set_error("import failed"); return fail(NBODY_ERR_CUDA); }
+	*out = reinterpret_cast<nbody_cuda_sim*>(s);
+	return NBODY_OK;
 }
+
+}  // extern "C"

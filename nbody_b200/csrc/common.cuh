@@ -51,6 +51,7 @@ struct Ctrl {
 	unsigned long long m2l_cursor;
 	unsigned long long stat_m2l_inter, stat_m2l_low, stat_p2p_entries, stat_p2p_inter, stat_near, stat_leaves;
 	uint32_t work_ticket[4];             // dynamic work distribution of the persistent kernels
+	uint32_t part[17];                   // distributed: rank r owns particles [part[r], part[r+1]) of the tree-ordered array
 };
 
 struct Pools {

@@ -84,6 +84,8 @@ struct TraverseArgs {
 	Ctrl* c;
 	const float4* geom;
 	const uint2* info;
+	const uint32_t* nbegin;
+	uint32_t own_first, own_end;   // this rank's slice of the tree-ordered particle array (everything on one GPU)
 	uint2* near_ref;
 	uint32_t* p2p_head;
 	const uint32_t* near_in;
@@ -108,12 +110,13 @@ struct TraverseArgs {
 	int round;
 };
 
+// Sized so that 4 CTAs fit in the 228 KB of an SM: sizeof(TravSmem) + 1 KB reserve <= 57 KB (static_assert below).
 struct TravSmem {
 	float4 cgeom[kTravCand];
 	uint32_t cid[kTravCand];
 	uint8_t cflag[kTravCand];               // bit0: non-empty, bit1: has children
 	uint32_t bal[4][8][kTravBatches];       // ballots per (list, target, batch): 0 = M2L, 1 = near, 2 = P2P, 3 = M2L at low order
-	uint32_t pre[3][8][kTravBatches];       // exclusive prefix of their popcounts over the batches
+	uint32_t pre[2][8][kTravBatches];       // exclusive prefix of the near / P2P popcounts over the batches ([0] near, [1] P2P)
 	uint32_t uni[kTravBatches], upre[kTravBatches];  // union of the M2L ballots over the targets, and its prefix
 	uint32_t chunk_cnt[5][8];               // per-chunk totals: 0 = M2L (per target), 1 = near, 2 = P2P, 3 = next-round candidate slots, 4 = low-order M2L
 	uint32_t total[5][8];                   // per-group totals
@@ -122,6 +125,8 @@ struct TravSmem {
 	uint32_t warp_sums[32];
 	uint32_t ncand, u_total, m2l_total, item, ok;
 };
+
+static_assert(sizeof(TravSmem) + 1024 <= 233472 / 4, "TravSmem must allow 4 CTAs per SM");
 
 __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, unsigned lane, uint32_t& total) {
 	uint32_t inc = v;
@@ -155,7 +160,9 @@ __global__ void __launch_bounds__(kTravThreads) k_traverse(const TraverseArgs a)
 		const uint32_t my_t = nt == 8 ? w : 0u;
 		const float4 tg = a.geom[G.first + my_t];
 		const uint2 ti = a.info[G.first + my_t];
-		const bool t_act = ti.y > 0, t_ch = ti.x != 0;
+		const uint32_t tb = a.nbegin[G.first + my_t];
+		// a target is active when it holds particles of this rank's Morton range
+		const bool t_act = ti.y > 0 && tb < a.own_end && tb + ti.y > a.own_first, t_ch = ti.x != 0;
 		if (tid < 40) { S.total[tid >> 3][tid & 7] = 0; }
 		const uint32_t nchunks = (G.list_cnt + kTravEntries - 1) / kTravEntries;
 		for (int pass = 0; pass < 2; ++pass) {
@@ -253,7 +260,7 @@ __global__ void __launch_bounds__(kTravThreads) k_traverse(const TraverseArgs a)
 							}
 							uint32_t tot;
 							const uint32_t ex = warp_excl_scan(__popc(m), lane, tot);
-							if (b < nb) { if (is_union) S.upre[b] = carry + ex; else S.pre[li][t][b] = carry + ex; }
+							if (b < nb) { if (is_union) S.upre[b] = carry + ex; else if (li) S.pre[li - 1][t][b] = carry + ex; }
 							carry += tot;
 						}
 						if (lane == 0) { if (is_union) S.u_total = carry; else S.chunk_cnt[li][t] = carry; }
@@ -271,8 +278,8 @@ __global__ void __launch_bounds__(kTravThreads) k_traverse(const TraverseArgs a)
 						const uint32_t t = nt == 8 ? w : 0u, b = nt == 8 ? q >> 3 : q;
 						const uint32_t s = 32 * b + lane;
 						const uint32_t mn = S.bal[1][t][b], mp = S.bal[2][t][b];
-						if (mn >> lane & 1u) a.near_out[S.off[1][t] + S.running[1][t] + S.pre[1][t][b] + __popc(mn & lt_mask)] = S.cid[s];
-						if (mp >> lane & 1u) a.p2p[S.off[2][t] + S.running[2][t] + S.pre[2][t][b] + __popc(mp & lt_mask)] = S.cid[s];
+						if (mn >> lane & 1u) a.near_out[S.off[1][t] + S.running[1][t] + S.pre[0][t][b] + __popc(mn & lt_mask)] = S.cid[s];
+						if (mp >> lane & 1u) a.p2p[S.off[2][t] + S.running[2][t] + S.pre[1][t][b] + __popc(mp & lt_mask)] = S.cid[s];
 					}
 					for (uint32_t b = w; b < nb; b += 8) {
 						const uint32_t u = S.uni[b];
@@ -298,7 +305,7 @@ __global__ void __launch_bounds__(kTravThreads) k_traverse(const TraverseArgs a)
 			const uint32_t target = G.first + tid;
 			const uint2 tin = a.info[target];
 			const uint32_t nn = S.total[1][tid], np = S.total[2][tid];
-			if (tin.y) {
+			if (tin.y && (nn || np)) {
 				a.near_ref[target] = make_uint2(S.off[1][tid], nn);
 				if (nn) {
 					const uint32_t qi = atomicAdd(&c->gq_count[(a.round + 1) & 1], 1u);
@@ -344,6 +351,7 @@ void launch_traversal(Sim& s) {
 	k_traverse_init<<<1, 32, 0, s.stream>>>(s.ctrl, s.info, p.near[0], p.gq[1]);
 	TraverseArgs a{};
 	a.c = s.ctrl; a.geom = s.geom; a.info = s.info; a.near_ref = s.near_ref; a.p2p_head = s.p2p_head;
+	a.nbegin = s.nbegin; a.own_first = (uint32_t) s.own_first; a.own_end = (uint32_t) (s.own_first + s.own_count);
 	a.near_cap = p.near_cap; a.p2p = p.p2p; a.p2p_cap = p.p2p_cap; a.m2l_id = p.m2l_id; a.m2l_mask = p.m2l_mask; a.m2l_mask_lo = p.m2l_mask_lo; a.m2l_cap = p.m2l_cap;
 	a.seg = p.seg; a.seg_cap = p.seg_cap; a.gq_cap = p.gq_cap; a.items8 = p.items[0]; a.items1 = p.items[1]; a.items_cap = p.items_cap;
 	a.ratio_sq = s.cfg.mac_ratio * s.cfg.mac_ratio;

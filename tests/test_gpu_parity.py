@@ -183,7 +183,7 @@ def test_edge_cases():
         scale = (o["P"][:, 9] / o["P"][:, 8])[:, None]
         g_fmm = o["tree"].fmm_field(o["posq"], 4, 0.01, low_order_tau=float(sim.config.low_order_tau))
         assert rms_rel(sim.accelerations(), g_fmm * scale) < 2e-6      # identical to the FP64 FMM over the same lists
-        assert rms_rel(sim.accelerations(), gd * scale) < 3e-3         # a 300-body system with a 40-body point clump
+        assert rms_rel(sim.accelerations(), gd * scale) < 6e-3         # a 300-body system with a 40-body point clump
         sim.close()
     # particles outside the root box are clamped into the boundary cells: keys, tree and lists still match the
     # oracle bit for bit (the expansions' error bound needs particles inside their cell, so no accuracy claim here)

@@ -1,0 +1,84 @@
+"""CPU tests (gloo, world_size 2) of the host-side logic of the N > 1 path: rank slices of the
+synthetic workload tile the global particle set, the 128-byte communicator id travels from rank 0
+to the others, the timing reduction is a MAX over ranks, and the reference arm runs on rank 0 only."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from nbody_b200 import workloads
+
+
+def _worker(rank, world, port, n, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = n * rank // world, n * (rank + 1) // world
+    P = workloads.plummer(hi - lo, start=lo, n_total=n)
+    uid = [bytes(range(128)) if rank == 0 else None]       # stands in for nbody_cuda_comm_unique_id()
+    dist.broadcast_object_list(uid, src=0)
+    t = torch.tensor([1.0 + rank], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (lo, hi, float(P[:, 0:3].sum())))
+    np.save(os.path.join(tmp, f"slice{rank}.npy"), P)
+    with open(os.path.join(tmp, f"meta{rank}.json"), "w") as f:
+        json.dump({"uid_ok": uid[0] == bytes(range(128)), "tmax": float(t), "gathered": gathered}, f)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_rank_slices_tile_the_workload(tmp_path):
+    n, world = 10001, 2
+    mp.spawn(_worker, args=(world, 29531, n, str(tmp_path)), nprocs=world, join=True)
+    full = workloads.plummer(n)
+    parts = [np.load(tmp_path / f"slice{r}.npy") for r in range(world)]
+    assert np.array_equal(np.concatenate(parts, axis=0), full)
+    for r in range(world):
+        meta = json.load(open(tmp_path / f"meta{r}.json"))
+        assert meta["uid_ok"] and meta["tmax"] == float(world)
+        assert [g[:2] for g in meta["gathered"]] == [[n * k // world, n * (k + 1) // world] for k in range(world)]
+
+
+def test_uniform_slices_and_force_constant():
+    a = workloads.uniform_cube(1000)
+    b = np.concatenate([workloads.uniform_cube(400, start=0), workloads.uniform_cube(600, start=400)])
+    assert np.array_equal(a, b)
+    assert workloads.force_constant("plummer", 1000) == 1.0
+    assert abs(workloads.force_constant("uniform", 1000) * a[:, 8].sum() - 1.0) < 0.05
+
+
+def test_reference_arm_runs_on_rank0_only():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                        "--warmup", "0", "--cpu-sample", "256"], env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip() == ""
+    env = dict(os.environ, RANK="0", WORLD_SIZE="2", LOCAL_RANK="0")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "2",
+                        "--warmup", "1", "--cpu-sample", "512"], env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["unit"] == "particle-steps/s"
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] == 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["gpu_launches"] == 0
+
+
+def test_cpp_wrapper_compiles_and_fails_loudly_without_gpu(tmp_path):
+    exe = str(tmp_path / "nbody_main")
+    import nbody_b200
+    if not os.path.exists(nbody_b200.LIB_PATH):
+        nbody_b200.build_library()
+    subprocess.check_call(["g++", "-std=c++14", "-O1", "-Wall", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "nbody_main.cpp"), "-L" + os.path.join(ROOT, "nbody_b200"), "-lnbody_cuda",
+                           "-Wl,-rpath," + os.path.join(ROOT, "nbody_b200"), "-o", exe])
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: covered by the gpu tests")
+    r = subprocess.run([exe, "--n", "64", "--steps", "1", "--quiet", "--csv", "none"], capture_output=True, text=True)
+    assert r.returncode == 1 and "no CPU fallback" in r.stderr

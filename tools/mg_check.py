@@ -1,0 +1,57 @@
+"""Multi-GPU check (run under torchrun, one rank per GPU): the distributed step must reproduce the
+single-GPU step — same tree-ordered state on every rank — and the owned ranges must tile [0, N)."""
+import os, sys, time
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch, torch.distributed as dist
+import nbody_b200
+from nbody_b200 import workloads
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 200000
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+lo, hi = n * rank // world, n * (rank + 1) // world
+P = workloads.plummer(hi - lo, start=lo, n_total=n)
+uid = [nbody_b200.comm_unique_id() if rank == 0 else None]
+dist.broadcast_object_list(uid, src=0)
+sim = nbody_b200.CudaSimulation([1, 1, 1], P, 1e-3, device=local,
+                                _distributed={"unique_id": uid[0], "n_global": n, "global_offset": lo, "rank": rank, "world": world})
+ranges = []
+t0 = time.time()
+for _ in range(steps):
+    sim.step()
+torch.cuda.synchronize()
+dt = time.time() - t0
+out = sim.particles()
+first, count = sim.owned_range()
+allr = [None] * world
+dist.all_gather_object(allr, (first, count, sim.stats()["ms_total"], sim.stats()["p2p_interactions"], sim.stats()["m2l_interactions"]))
+ok = True
+if rank == 0:
+    print("owned ranges:", [(a, b) for a, b, *_ in allr], "ms_total per rank:", [round(x[2], 2) for x in allr], flush=True)
+    cover = sorted((a, a + b) for a, b, *_ in allr)
+    ok &= cover[0][0] == 0 and cover[-1][1] == n and all(cover[i][1] == cover[i + 1][0] for i in range(world - 1))
+    ref = nbody_b200.CudaSimulation([1, 1, 1], workloads.plummer(n), 1e-3, device=local)
+    for _ in range(steps):
+        ref.step()
+    r = ref.particles()
+    same_perm = np.array_equal(ref.permutation(), sim.permutation())
+    dpos = np.abs(r[:, 0:3] - out[:, 0:3]).max(); dvel = np.abs(r[:, 4:7] - out[:, 4:7]).max()
+    st = ref.stats()
+    print(f"single-GPU vs {world}-GPU after {steps} steps: same order {same_perm}, max|dx| {dpos:.3e}, max|dv| {dvel:.3e}; "
+          f"P2P evals single {st['p2p_interactions']} vs sum {sum(x[3] for x in allr)}; M2L single {st['m2l_interactions']} vs sum {sum(x[4] for x in allr)}; "
+          f"single ms {st['ms_total']:.2f}", flush=True)
+    ok &= same_perm and dpos < 1e-5 and dvel < 1e-3 and st["p2p_interactions"] == sum(x[3] for x in allr)
+# every rank holds the same full state
+h = torch.tensor([float(np.abs(out[:, 0:7]).sum())], device="cuda", dtype=torch.float64)
+hs = [torch.zeros_like(h) for _ in range(world)]
+dist.all_gather(hs, h)
+if rank == 0:
+    same = all(abs(float(x) - float(hs[0])) < 1e-6 * abs(float(hs[0])) for x in hs)
+    print("state identical on all ranks:", same, flush=True)
+    ok &= same
+    print("MG_CHECK", "PASS" if ok else "FAIL", flush=True)
+sim.close()
+dist.destroy_process_group()
