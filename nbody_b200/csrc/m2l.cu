@@ -43,19 +43,33 @@ __device__ __forceinline__ void m2l_one(float (&Lacc)[Expansion<P>::NC], const f
 	Expansion<P>::template m2l<1, PE>(Lacc, M, D);
 }
 
+// Two independent interactions at order PE: both derivative tensors first, then both contractions, so the
+// compiler can interleave two dependency chains (the order-3 tensors are small enough to keep two in registers).
+template <int P, int PE>
+__device__ __forceinline__ void m2l_two(float (&Lacc)[Expansion<P>::NC], const float4& tg, const float4& ga, const float* Ma, const float4& gb,
+                                        const float* Mb, float eps2) {
+	float Da[Expansion<PE>::NC], Db[Expansion<PE>::NC];
+	Expansion<PE>::derivatives(tg.x - ga.x, tg.y - ga.y, tg.z - ga.z, eps2, Da);
+	Expansion<PE>::derivatives(tg.x - gb.x, tg.y - gb.y, tg.z - gb.z, eps2, Db);
+	const SmemCoefs A{reinterpret_cast<const float4*>(Ma)}, B{reinterpret_cast<const float4*>(Mb)};
+	Expansion<P>::template m2l<1, PE>(Lacc, A, Da);
+	Expansion<P>::template m2l<1, PE>(Lacc, B, Db);
+}
+
 template <int P, int NT>
 struct M2LShared {
-	static constexpr int CH = NT == 8 ? 256 : 128;  // candidate slots per chunk = threads per CTA
+	static constexpr int CH = NT == 8 ? 256 : 32;   // candidate slots per chunk = threads per CTA
 	static constexpr int STRIDE = coef_stride(P);
 	float sM[2][CH * STRIDE];
 	float4 sgeom[2][CH];
 	uint32_t sid[3][CH];                     // ids / masks of chunk k live in ring slot k % 3 (published two chunks ahead)
 	uint8_t smask[3][CH], smask_lo[3][CH];
-	uint8_t list_hi[8][CH], list_lo[8][CH];  // per-warp compacted slot numbers of the two order classes
+	uint8_t list_hi[NT == 8 ? 8 : 1][CH], list_lo[NT == 8 ? 8 : 1][CH];  // per-warp compacted slot numbers of the two order classes
 	uint32_t item;
 };
 
-// One CTA per work item (8 sibling targets, one warp each, or one carried target shared by 4 warps),
+// One CTA per work item: 8 warps for 8 sibling targets (one warp each), or a single-warp CTA for a carried
+// target (their lists are short, so a multi-warp CTA would spend its time in barriers),
 // items handed out by an atomic ticket. Candidate chunks are double buffered with cp.async:
 // while the warps evaluate chunk c, chunk c+1 is in flight (fully coalesced 16-byte copies: thread
 // t moves piece t, t+CH, ... of the chunk's records), and the ids of chunk c+2 are already in
@@ -63,7 +77,7 @@ struct M2LShared {
 // Inside a chunk each warp first compacts the slots its target accepts into two dense lists
 // (order P and order P-1), then all 32 lanes work through each list.
 template <int P, int NT>
-__global__ void __launch_bounds__(NT == 8 ? 256 : 128, NT == 8 ? 2 : 4)
+__global__ void __launch_bounds__(NT == 8 ? 256 : 32, NT == 8 ? 2 : 16)
 k_m2l(Ctrl* __restrict__ c, const Group* __restrict__ items, uint32_t items_cap, const float4* __restrict__ geom,
       const float* __restrict__ M, float* __restrict__ L, const uint32_t* __restrict__ m2l_id, const uint8_t* __restrict__ m2l_mask,
       const uint8_t* __restrict__ m2l_mask_lo, float eps2) {
@@ -132,8 +146,8 @@ k_m2l(Ctrl* __restrict__ c, const Group* __restrict__ items, uint32_t items_cap,
 			const uint8_t* mk_lo = S.smask_lo[ch % 3];
 			// ---- compact the accepted slots of my target into the two order classes ----
 			uint32_t cnt_h = 0, cnt_l = 0;
-			constexpr int PERW = NT == 8 ? CH / 32 : 1;  // slots per lane
-			const uint32_t s0 = NT == 8 ? 0u : 32u * w;
+			constexpr int PERW = CH / 32;  // slots per lane
+			const uint32_t s0 = 0u;
 #pragma unroll
 			for (int i = 0; i < PERW; ++i) {
 				const uint32_t s = s0 + lane + 32 * i;
@@ -154,7 +168,14 @@ k_m2l(Ctrl* __restrict__ c, const Group* __restrict__ items, uint32_t items_cap,
 				const uint32_t s = s0 + S.list_hi[w][k];
 				m2l_one<P, P>(Lacc, tg, S.sgeom[cur][s], S.sM[cur] + s * STRIDE, eps2);
 			}
-			for (uint32_t k = lane; k < cnt_l; k += 32) {
+			// order P-1 pairs: two interactions per lane in flight while whole 64-slot strides remain (their
+			// derivative chains and FMA streams interleave), then the remainder one at a time
+			uint32_t base = 0;
+			for (; base + 64 <= cnt_l; base += 64) {
+				const uint32_t sa = s0 + S.list_lo[w][base + lane], sb = s0 + S.list_lo[w][base + 32 + lane];
+				m2l_two<P, PL>(Lacc, tg, S.sgeom[cur][sa], S.sM[cur] + sa * STRIDE, S.sgeom[cur][sb], S.sM[cur] + sb * STRIDE, eps2);
+			}
+			for (uint32_t k = base + lane; k < cnt_l; k += 32) {
 				const uint32_t s = s0 + S.list_lo[w][k];
 				m2l_one<P, PL>(Lacc, tg, S.sgeom[cur][s], S.sM[cur] + s * STRIDE, eps2);
 			}
@@ -212,7 +233,7 @@ static void m2l_t(Sim& s) {
 	cudaFuncSetAttribute(k_m2l<P, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(M2LShared<P, 1>));
 	k_m2l<P, 8><<<kNumSM * 2, 256, sizeof(M2LShared<P, 8>), s.stream>>>(s.ctrl, s.pools.items[0], s.pools.items_cap, s.geom, s.M, s.L,
 	                                                                  s.pools.m2l_id, s.pools.m2l_mask, s.pools.m2l_mask_lo, eps2);
-	k_m2l<P, 1><<<kNumSM * 4, 128, sizeof(M2LShared<P, 1>), s.stream>>>(s.ctrl, s.pools.items[1], s.pools.items_cap, s.geom, s.M, s.L,
+	k_m2l<P, 1><<<kNumSM * 16, 32, sizeof(M2LShared<P, 1>), s.stream>>>(s.ctrl, s.pools.items[1], s.pools.items_cap, s.geom, s.M, s.L,
 	                                                                  s.pools.m2l_id, s.pools.m2l_mask, s.pools.m2l_mask_lo, eps2);
 }
 template <int P>
