@@ -468,9 +468,14 @@ int nbody_cuda_get_lists(nbody_cuda_sim* sim, uint64_t* n_m2l, uint32_t* m2l_pai
 		if (w != *n_m2l) { set_error("get_lists: M2L count mismatch"); return NBODY_ERR_STATE; }
 	}
 	if (p2p_pairs) {
-		std::vector<uint32_t> src(c.p2p_cursor), head(t.n_nodes);
+		std::vector<uint2> src(c.p2p_cursor);
+		std::vector<uint32_t> head(t.n_nodes);
+		// entries carry {first particle, count}: the source leaf is the non-empty childless node that starts there
+		std::vector<uint32_t> leaf_at(s->n, 0xffffffffu);
+		for (uint32_t id = 0; id < t.n_nodes; ++id)
+			if (t.info[id].x == 0 && t.info[id].y > 0) leaf_at[t.nbegin[id]] = id;
 		std::vector<Segment> segs(c.seg_cursor);
-		NB_CUDA_CHECK(cudaMemcpy(src.data(), s->pools.p2p, src.size() * 4, cudaMemcpyDeviceToHost));
+		NB_CUDA_CHECK(cudaMemcpy(src.data(), s->pools.p2p, src.size() * sizeof(uint2), cudaMemcpyDeviceToHost));
 		NB_CUDA_CHECK(cudaMemcpy(segs.data(), s->pools.seg, segs.size() * sizeof(Segment), cudaMemcpyDeviceToHost));
 		NB_CUDA_CHECK(cudaMemcpy(head.data(), s->p2p_head, head.size() * 4, cudaMemcpyDeviceToHost));
 		uint64_t w = 0;
@@ -478,7 +483,7 @@ int nbody_cuda_get_lists(nbody_cuda_sim* sim, uint64_t* n_m2l, uint32_t* m2l_pai
 			for (uint32_t si = head[id]; si != 0xffffffffu; si = segs[si].next)
 				for (uint32_t e = 0; e < segs[si].cnt; ++e) {
 					p2p_pairs[2 * w] = t.dfs_of[id];
-					p2p_pairs[2 * w + 1] = t.dfs_of[src[segs[si].off + e]];
+					p2p_pairs[2 * w + 1] = t.dfs_of[leaf_at[src[segs[si].off + e].x]];
 					++w;
 				}
 		if (w != *n_p2p) { set_error("get_lists: P2P count mismatch"); return NBODY_ERR_STATE; }

@@ -57,7 +57,7 @@ struct Ctrl {
 struct Pools {
 	uint32_t* near[2] = {nullptr, nullptr};
 	uint64_t near_cap = 0;
-	uint32_t* p2p = nullptr;
+	uint2* p2p = nullptr;            // P2P source lists: {first particle, particle count} of each source leaf
 	uint64_t p2p_cap = 0;
 	uint32_t* m2l_id = nullptr;
 	uint8_t* m2l_mask = nullptr;     // bit t: target t of the group accepts this candidate

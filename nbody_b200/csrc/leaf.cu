@@ -16,8 +16,16 @@
 
 namespace nbody {
 
-constexpr int kLeafWarps = 8;
-constexpr int kLeafBuf = 256;  // source particles per warp tile (4 KB)
+constexpr int kLeafWarps = 4;
+constexpr int kLeafTile = 256;  // source particles per tile; two tiles (8 KB) per warp
+
+__device__ __forceinline__ void leaf_cp_async16(void* smem, const void* gmem) {
+	const unsigned sa = (unsigned) __cvta_generic_to_shared(smem);
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void leaf_cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void leaf_cp_async_wait1() { asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
+__device__ __forceinline__ void leaf_cp_async_wait0() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 template <bool SOFT>
 __device__ __forceinline__ void p2p_interact(const float4& s, float tx, float ty, float tz, float eps2, float& ax, float& ay, float& az) {
@@ -44,11 +52,12 @@ struct LeafArgs {
 	const uint32_t* nbegin;
 	const uint32_t* p2p_head;
 	const Segment* seg;
-	const uint32_t* p2p;
+	const uint2* p2p;        // {first particle, count} per source leaf
 	const float* L;
 	float eps2, G, dt;
 	int integrator, no_integrate;
 	uint32_t own_first, own_end;  // this rank's slice of the tree-ordered particle array
+	uint32_t batch_entries;       // source leaves staged per tile (batch_entries * quota <= kLeafTile)
 	unsigned long long* stat_inter;
 	unsigned long long* stat_leaves;
 };
@@ -69,16 +78,20 @@ __device__ __forceinline__ void tile_compute(const float4* buf, uint32_t fill, u
 	__syncwarp();
 }
 
+// One warp per target leaf. Its source list is a chain of segments of {first particle, count} entries;
+// batches of `batch_entries` source leaves are expanded into a shared-memory tile with cp.async while the
+// previous tile is being evaluated (two tiles per warp), and the entries of the batch after that are already
+// in registers — so neither the list walk nor the particle fetch sits on the critical path.
 template <int P, bool SOFT>
 __global__ void __launch_bounds__(kLeafWarps * 32) k_leaf(const LeafArgs a) {
 	using E = Expansion<P>;
 	constexpr int STRIDE = coef_stride(P);
-	__shared__ float4 sbuf[kLeafWarps][kLeafBuf];
+	__shared__ float4 sbuf[kLeafWarps][2][kLeafTile];
 	const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
-	float4* buf = sbuf[w];
 	if (a.c->status) return;  // a pool overflowed: the host grows it and re-runs the step; leave the state untouched
 	const uint32_t n_nodes = a.c->n_nodes;
 	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+	const uint32_t EB = a.batch_entries, quota = kLeafTile / EB;
 	unsigned long long inter = 0, leaves = 0;
 	for (uint32_t node = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; node < n_nodes; node += warps) {
 		const uint2 nf = a.info[node];
@@ -97,58 +110,69 @@ __global__ void __launch_bounds__(kLeafWarps * 32) k_leaf(const LeafArgs a) {
 			float4 tp = make_float4(0.f, 0.f, 0.f, 0.f);
 			if (has_t) tp = a.posq[b + t0 + t];
 			float ax = 0.f, ay = 0.f, az = 0.f;
-			uint32_t fill = 0;
 			unsigned long long nsrc = 0;
-			for (uint32_t si = a.p2p_head[node]; si != 0xffffffffu;) {
-				const Segment sg = a.seg[si];
-				si = sg.next;
-				for (uint32_t e0 = 0; e0 < sg.cnt; e0 += 32) {
-					uint32_t sb = 0, sc = 0;
-					if (e0 + lane < sg.cnt) {
-						const uint32_t src = a.p2p[sg.off + e0 + lane];
-						sb = a.nbegin[src];
-						sc = a.info[src].y;
-					}
-					unsigned pending = __ballot_sync(0xffffffffu, sc > 0);
-					while (pending) {
-						const uint32_t v = (pending >> lane & 1u) ? sc : 0u;
-						uint32_t inc = v;
-#pragma unroll
-						for (int d = 1; d < 32; d <<= 1) {
-							const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d);
-							if (lane >= (unsigned) d) inc += u;
-						}
-						const bool fits = v > 0 && fill + inc <= (uint32_t) kLeafBuf;
-						const unsigned fm = __ballot_sync(0xffffffffu, fits);
-						if (fm == 0) {
-							if (fill > 0) {  // tile full: consume it and retry
-								tile_compute<SOFT>(buf, fill, sl, S, tp.x, tp.y, tp.z, a.eps2, ax, ay, az);
-								nsrc += fill; fill = 0;
-								continue;
-							}
-							// a single source leaf larger than the tile (only possible at max depth): stream it
-							const int first = __ffs(pending) - 1;
-							const uint32_t fb = __shfl_sync(0xffffffffu, sb, first), fc = __shfl_sync(0xffffffffu, sc, first);
-							for (uint32_t q0 = 0; q0 < fc; q0 += kLeafBuf) {
-								const uint32_t m = min((uint32_t) kLeafBuf, fc - q0);
-								for (uint32_t q = lane; q < m; q += 32) buf[q] = a.posq[fb + q0 + q];
-								tile_compute<SOFT>(buf, m, sl, S, tp.x, tp.y, tp.z, a.eps2, ax, ay, az);
-							}
-							nsrc += fc;
-							pending &= ~(1u << first);
-							continue;
-						}
-						const uint32_t maxc = __reduce_max_sync(0xffffffffu, fits ? v : 0u);
-						const uint32_t dst = fill + inc - v;
-						for (uint32_t k = 0; k < maxc; ++k)
-							if (fits && k < v) buf[dst + k] = a.posq[sb + k];
-						const int last = 31 - __clz(fm);
-						fill += __shfl_sync(0xffffffffu, inc, last);
-						pending &= ~fm;
-					}
+			// ---- cursor over the segment chain ----
+			uint32_t si = a.p2p_head[node], e0 = 0;
+			Segment sg; sg.off = 0; sg.cnt = 0; sg.next = 0xffffffffu;
+			auto fetch = [&](uint2& ent) -> bool {  // next batch of <= EB entries, lane l holds entry l; warp-uniform result
+				while (e0 >= sg.cnt) {
+					if (si == 0xffffffffu) return false;
+					sg = a.seg[si]; si = sg.next; e0 = 0;
 				}
+				ent = make_uint2(0u, 0u);
+				if (lane < EB && e0 + lane < sg.cnt) ent = a.p2p[sg.off + e0 + lane];
+				e0 += EB;
+				return true;
+			};
+			auto stage = [&](const uint2& ent, float4* tile, uint32_t& fill, unsigned& big) {  // issue the tile fill of one batch
+				const bool bigl = ent.y > quota;  // an over-full source leaf (only at max depth): streamed separately
+				const uint32_t v = bigl ? 0u : ent.y;
+				uint32_t inc = v;
+#pragma unroll
+				for (int d = 1; d < 32; d <<= 1) {
+					const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d);
+					if (lane >= (unsigned) d) inc += u;
+				}
+				fill = __shfl_sync(0xffffffffu, inc, 31);
+				big = __ballot_sync(0xffffffffu, bigl);
+				const uint32_t dst = inc - v, maxc = __reduce_max_sync(0xffffffffu, v);
+				for (uint32_t k = 0; k < maxc; ++k)
+					if (k < v) leaf_cp_async16(tile + dst + k, a.posq + ent.x + k);
+				leaf_cp_async_commit();
+			};
+			uint2 ent_cur = make_uint2(0u, 0u), ent_nxt = make_uint2(0u, 0u);
+			uint32_t fill_cur = 0;
+			unsigned big_cur = 0;
+			int cur = 0;
+			bool has_cur = fetch(ent_cur);
+			if (has_cur) stage(ent_cur, sbuf[w][0], fill_cur, big_cur);
+			bool has_nxt = has_cur && fetch(ent_nxt);
+			while (has_cur) {
+				uint32_t fill_nxt = 0;
+				unsigned big_nxt = 0;
+				if (has_nxt) stage(ent_nxt, sbuf[w][cur ^ 1], fill_nxt, big_nxt);
+				else leaf_cp_async_commit();  // empty group keeps the wait_group arithmetic uniform
+				uint2 ent_nn = make_uint2(0u, 0u);
+				const bool has_nn = has_nxt && fetch(ent_nn);  // entries of the batch after next: in flight during the math
+				leaf_cp_async_wait1();
+				tile_compute<SOFT>(sbuf[w][cur], fill_cur, sl, S, tp.x, tp.y, tp.z, a.eps2, ax, ay, az);
+				nsrc += fill_cur;
+				while (big_cur) {  // stream an over-full source leaf through the tile that has just been consumed
+					const int first = __ffs(big_cur) - 1;
+					const uint32_t fb = __shfl_sync(0xffffffffu, ent_cur.x, first), fc = __shfl_sync(0xffffffffu, ent_cur.y, first);
+					for (uint32_t q0 = 0; q0 < fc; q0 += kLeafTile) {
+						const uint32_t m = min((uint32_t) kLeafTile, fc - q0);
+						for (uint32_t q = lane; q < m; q += 32) sbuf[w][cur][q] = a.posq[fb + q0 + q];
+						tile_compute<SOFT>(sbuf[w][cur], m, sl, S, tp.x, tp.y, tp.z, a.eps2, ax, ay, az);
+					}
+					nsrc += fc;
+					big_cur &= big_cur - 1;
+				}
+				ent_cur = ent_nxt; fill_cur = fill_nxt; big_cur = big_nxt; has_cur = has_nxt;
+				ent_nxt = ent_nn; has_nxt = has_nn;
+				cur ^= 1;
 			}
-			if (fill) { tile_compute<SOFT>(buf, fill, sl, S, tp.x, tp.y, tp.z, a.eps2, ax, ay, az); nsrc += fill; }
+			leaf_cp_async_wait0();
 			for (unsigned d = T; d < 32u; d <<= 1) {
 				ax += __shfl_xor_sync(0xffffffffu, ax, d);
 				ay += __shfl_xor_sync(0xffffffffu, ay, d);
@@ -192,8 +216,8 @@ __global__ void __launch_bounds__(kLeafWarps * 32) k_leaf(const LeafArgs a) {
 
 template <int P>
 static void leaf_t(Sim& s, const LeafArgs& a) {
-	if (s.cfg.softening > 0.0f) k_leaf<P, true><<<kNumSM * 6, kLeafWarps * 32, 0, s.stream>>>(a);
-	else k_leaf<P, false><<<kNumSM * 6, kLeafWarps * 32, 0, s.stream>>>(a);
+	if (s.cfg.softening > 0.0f) k_leaf<P, true><<<kNumSM * 7, kLeafWarps * 32, 0, s.stream>>>(a);
+	else k_leaf<P, false><<<kNumSM * 7, kLeafWarps * 32, 0, s.stream>>>(a);
 }
 
 void launch_leaf(Sim& s) {
@@ -203,6 +227,10 @@ void launch_leaf(Sim& s) {
 	a.eps2 = s.cfg.softening * s.cfg.softening; a.G = s.cfg.force_constant; a.dt = s.cfg.time_step;
 	a.integrator = (int) s.cfg.integrator; a.no_integrate = (s.cfg.flags & NBODY_FLAG_NO_INTEGRATE) ? 1 : 0;
 	a.own_first = (uint32_t) s.own_first; a.own_end = (uint32_t) (s.own_first + s.own_count);
+	{  // batch_entries * leaf_capacity <= kLeafTile, at most one entry per lane
+		uint32_t eb = kLeafTile / (s.cfg.leaf_capacity ? s.cfg.leaf_capacity : 1u);
+		a.batch_entries = eb < 1u ? 1u : (eb > 32u ? 32u : eb);
+	}
 	a.stat_inter = &s.ctrl->stat_p2p_inter; a.stat_leaves = &s.ctrl->stat_leaves;
 	switch (s.cfg.order) {
 		case 2: leaf_t<2>(s, a); break;

@@ -91,7 +91,7 @@ struct TraverseArgs {
 	const uint32_t* near_in;
 	uint32_t* near_out;
 	uint64_t near_cap;
-	uint32_t* p2p;
+	uint2* p2p;
 	uint64_t p2p_cap;
 	uint32_t* m2l_id;
 	uint8_t* m2l_mask;
@@ -279,7 +279,10 @@ __global__ void __launch_bounds__(kTravThreads) k_traverse(const TraverseArgs a)
 						const uint32_t s = 32 * b + lane;
 						const uint32_t mn = S.bal[1][t][b], mp = S.bal[2][t][b];
 						if (mn >> lane & 1u) a.near_out[S.off[1][t] + S.running[1][t] + S.pre[0][t][b] + __popc(mn & lt_mask)] = S.cid[s];
-						if (mp >> lane & 1u) a.p2p[S.off[2][t] + S.running[2][t] + S.pre[1][t][b] + __popc(mp & lt_mask)] = S.cid[s];
+						if (mp >> lane & 1u) {
+							const uint32_t src = S.cid[s];
+							a.p2p[S.off[2][t] + S.running[2][t] + S.pre[1][t][b] + __popc(mp & lt_mask)] = make_uint2(a.nbegin[src], a.info[src].y);
+						}
 					}
 					for (uint32_t b = w; b < nb; b += 8) {
 						const uint32_t u = S.uni[b];

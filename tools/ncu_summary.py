@@ -28,16 +28,22 @@ for k, r in sorted(best.items(), key=lambda kv: -tot[kv[0]]):
 if len(sys.argv) > 2:
     src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + sys.argv[2]], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(src)))
-    hi = [i for i, r in enumerate(rows) if r and r[0] == "Address"][0]
-    h = rows[hi]; ci = {n: i for i, n in enumerate(h)}
-    stalls = [n for n in h if n.startswith("stall_") and "Not Issued" not in n]
-    total = {s: 0 for s in stalls}; recs = []; samples = 0
-    for r in rows[hi + 1:]:
-        if len(r) < len(h) or r[0] == "Address": break
-        n = int(r[ci["# Samples"]]); samples += n
-        d = {s: int(r[ci[s]]) for s in stalls if int(r[ci[s]])}
-        for s, v in d.items(): total[s] += v
-        recs.append((n, r[ci["Source"]].strip(), int(r[ci["Instructions Executed"]]), d))
-    print("samples", samples, {k: f"{100*v/samples:.1f}%" for k, v in sorted(total.items(), key=lambda kv: -kv[1]) if v})
-    for n, s, ie, d in sorted(recs, key=lambda x: -x[0])[:int(sys.argv[3]) if len(sys.argv) > 3 else 16]:
-        print(f"{n:7d} {ie:10d} {s[:56]:56s} " + " ".join(f"{k[6:]}={v}" for k, v in sorted(d.items(), key=lambda kv: -kv[1])[:3]))
+    # sections: ["Kernel Name", name] / header row / data rows
+    sections = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+    top = int(sys.argv[3]) if len(sys.argv) > 3 else 16
+    for si, start in enumerate(sections):
+        end = sections[si + 1] if si + 1 < len(sections) else len(rows)
+        name = rows[start][1][:70]
+        h = rows[start + 1]; ci = {n: i for i, n in enumerate(h)}
+        stalls = [n for n in h if n.startswith("stall_") and "Not Issued" not in n]
+        total = {s_: 0 for s_ in stalls}; recs = []; samples = 0
+        for r in rows[start + 2:end]:
+            if len(r) < len(h): continue
+            n = int(r[ci["# Samples"]]); samples += n
+            d = {s_: int(r[ci[s_]]) for s_ in stalls if int(r[ci[s_]])}
+            for s_, v in d.items(): total[s_] += v
+            recs.append((n, r[ci["Source"]].strip(), int(r[ci["Instructions Executed"]]), d))
+        if not samples: continue
+        print("#####", name, "samples", samples, {k[6:]: f"{100*v/samples:.1f}%" for k, v in sorted(total.items(), key=lambda kv: -kv[1]) if v})
+        for n, s_, ie, d in sorted(recs, key=lambda x: -x[0])[:top]:
+            print(f"{n:7d} {ie:10d} {s_[:56]:56s} " + " ".join(f"{k[6:]}={v}" for k, v in sorted(d.items(), key=lambda kv: -kv[1])[:3]))
