@@ -33,7 +33,7 @@
 namespace nbody {
 
 constexpr int kTravThreads = 256;
-constexpr int kTravEntries = 256;                 // near entries expanded per chunk
+constexpr int kTravEntries = 192;                 // near entries expanded per chunk
 constexpr int kTravCand = kTravEntries * 8;       // candidate slots per chunk
 constexpr int kTravBatches = kTravCand / 32;      // 64
 
@@ -45,13 +45,14 @@ constexpr int kTravBatches = kTravCand / 32;      // 64
 // doubt (Sterbenz: ext2 in [d2/8, d2/2]); outside that range the sign is unambiguous.
 // Returns 0 = not accepted, 1 = accepted (order P), 2 = accepted and well enough separated for order P-1
 // (ext2 < tau * d2, an implementation choice that does not touch the lists; mirrored in FP32 by the oracle).
-__device__ __forceinline__ unsigned mac_classify(float ax, float ay, float az, float ad, const float4& b, float ratio_sq, bool quarter, float tau) {
+template <bool QUARTER>
+__device__ __forceinline__ unsigned mac_classify(float ax, float ay, float az, float ad, const float4& b, float ratio_sq, float tau) {
 	const float dx = __fsub_rn(b.x, ax), dy = __fsub_rn(b.y, ay), dz = __fsub_rn(b.z, az);
 	const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 	const float ext = __fadd_rn(ad, b.w);
 	const float ext2 = __fmul_rn(__fmul_rn(0.75f, ext), ext);
 	bool accept;
-	if (quarter) accept = __fsub_rn(__fmul_rn(0.25f, d2), ext2) > __fmul_rn(d2, 7.450580596923828125e-9f);  // 2^-27
+	if (QUARTER) accept = __fsub_rn(__fmul_rn(0.25f, d2), ext2) > __fmul_rn(d2, 7.450580596923828125e-9f);  // 2^-27
 	else accept = __fdiv_rn(ext2, d2) < ratio_sq;
 	return accept ? (ext2 < __fmul_rn(tau, d2) ? 2u : 1u) : 0u;
 }
@@ -126,7 +127,7 @@ struct TravSmem {
 	uint32_t ncand, u_total, m2l_total, item, ok;
 };
 
-static_assert(sizeof(TravSmem) + 1024 <= 233472 / 4, "TravSmem must allow 4 CTAs per SM");
+static_assert(sizeof(TravSmem) + 1024 <= 233472 / 5, "TravSmem must allow 5 CTAs per SM");
 
 __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, unsigned lane, uint32_t& total) {
 	uint32_t inc = v;
@@ -139,6 +140,7 @@ __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, unsigned lane, ui
 	return inc - v;
 }
 
+template <bool QUARTER>
 __global__ void __launch_bounds__(kTravThreads) k_traverse(const TraverseArgs a) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	TravSmem& S = *reinterpret_cast<TravSmem*>(smem_raw);
@@ -147,7 +149,6 @@ __global__ void __launch_bounds__(kTravThreads) k_traverse(const TraverseArgs a)
 	const unsigned lt_mask = (1u << lane) - 1u;
 	const uint32_t n_groups = min(c->gq_count[a.round & 1], a.gq_cap);
 	const int out = a.round & 1;
-	const bool quarter = a.ratio_sq == 0.25f;
 	for (;;) {
 		__syncthreads();
 		if (tid == 0) S.item = atomicAdd(&c->work_ticket[2], 1u);
@@ -231,7 +232,7 @@ __global__ void __launch_bounds__(kTravThreads) k_traverse(const TraverseArgs a)
 							const unsigned fl = S.cflag[s];
 							if (fl & 1u) {
 								const bool same = S.cid[s] == G.first + t;
-								const unsigned cls = same ? 0u : mac_classify(tg.x, tg.y, tg.z, tg.w, S.cgeom[s], a.ratio_sq, quarter, a.tau);
+								const unsigned cls = same ? 0u : mac_classify<QUARTER>(tg.x, tg.y, tg.z, tg.w, S.cgeom[s], a.ratio_sq, a.tau);
 								code = cls ? (cls == 2u ? 4u : 1u) : ((t_ch || (fl & 2u)) ? 2u : 3u);
 							}
 						}
@@ -350,7 +351,9 @@ __global__ void __launch_bounds__(kTravThreads) k_traverse(const TraverseArgs a)
 
 void launch_traversal(Sim& s) {
 	Pools& p = s.pools;
-	cudaFuncSetAttribute(k_traverse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(TravSmem));
+	const bool quarter = s.cfg.mac_ratio * s.cfg.mac_ratio == 0.25f;
+	cudaFuncSetAttribute(k_traverse<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(TravSmem));
+	cudaFuncSetAttribute(k_traverse<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(TravSmem));
 	k_traverse_init<<<1, 32, 0, s.stream>>>(s.ctrl, s.info, p.near[0], p.gq[1]);
 	TraverseArgs a{};
 	a.c = s.ctrl; a.geom = s.geom; a.info = s.info; a.near_ref = s.near_ref; a.p2p_head = s.p2p_head;
@@ -366,7 +369,8 @@ void launch_traversal(Sim& s) {
 		a.near_out = p.near[r & 1];
 		a.q_in = p.gq[r & 1];
 		a.q_out = p.gq[(r + 1) & 1];
-		k_traverse<<<kNumSM * 4, kTravThreads, sizeof(TravSmem), s.stream>>>(a);
+		if (quarter) k_traverse<true><<<kNumSM * 5, kTravThreads, sizeof(TravSmem), s.stream>>>(a);
+		else k_traverse<false><<<kNumSM * 5, kTravThreads, sizeof(TravSmem), s.stream>>>(a);
 	}
 }
 
