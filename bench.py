@@ -223,10 +223,16 @@ def main():
     barrier()
     elapsed = time.perf_counter() - t0
     clocks = sampler.stop()
+    rank_ms = None
     if world > 1:
         tt = torch.tensor([elapsed], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         elapsed = float(tt.item())
+        mine = torch.tensor([stage_ms.get(k, 0.0) / args.steps for k in ("ms_traverse", "ms_m2l", "ms_leaf", "ms_comm")],
+                            device="cuda", dtype=torch.float64)
+        allm = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allm, mine)
+        rank_ms = [[round(float(x), 2) for x in t] for t in allm]
     value = n * args.steps / elapsed
     K = args.steps
     stage_ms = {k: v / K for k, v in stage_ms.items()}
@@ -292,6 +298,8 @@ def main():
             "p2p_fp32_tflops": p2p_tf, "p2p_frac_of_fp32_peak": p2p_tf / peak, "m2l_fp32_tflops": m2l_tf,
             "stage_ms": stage_ms, "counts": counts,
         }
+        if rank_ms is not None:
+            line["per_rank_ms"] = {"columns": ["traverse", "m2l", "leaf", "comm"], "rows": rank_ms}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args)
         print(json.dumps(line), flush=True)

@@ -59,7 +59,8 @@ enum {
 enum {
 	NBODY_FLAG_KEEP_LISTS = 1u,   /* keep interaction lists after step() for nbody_cuda_get_lists */
 	NBODY_FLAG_NO_INTEGRATE = 2u, /* step() computes accelerations only (state is re-ordered, not advanced) */
-	NBODY_FLAG_DIRECT = 4u        /* all-pairs direct sum instead of the FMM (validation / P2P microbenchmark) */
+	NBODY_FLAG_DIRECT = 4u,       /* all-pairs direct sum instead of the FMM (validation / P2P microbenchmark) */
+	NBODY_FLAG_CUB_SORT = 8u      /* sort with CUB's DeviceRadixSort instead of the built-in radix sort (comparison only) */
 };
 
 typedef struct nbody_cuda_config {
@@ -127,7 +128,8 @@ int nbody_cuda_get_particles(nbody_cuda_sim* sim, nbody_particle* out, uint64_t 
 /* orig_index[i] = index in the constructor's array of the particle now at i. */
 int nbody_cuda_get_permutation(nbody_cuda_sim* sim, uint32_t* orig_index, uint64_t capacity);
 
-/* Accelerations of the last step, xyz per particle, same order as get_particles. */
+/* Accelerations of the last step, xyz per particle, same order as get_particles.
+ * (Distributed: collective — every rank must call it; the slices are exchanged on first use.) */
 int nbody_cuda_get_accelerations(nbody_cuda_sim* sim, float* xyz, uint64_t capacity);
 
 /* ---- parity exports (tests only) ---------------------------------------- */

@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libnbody_cuda.so")
-SOURCES = ["api.cu", "tree.cu", "upsweep.cu", "traverse.cu", "m2l.cu", "leaf.cu", "comm.cu"]
+SOURCES = ["api.cu", "tree.cu", "sort.cu", "upsweep.cu", "traverse.cu", "m2l.cu", "leaf.cu", "comm.cu"]
 HEADERS = ["common.cuh", "expansion.cuh", os.path.join("..", "..", "include", "nbody_cuda.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",

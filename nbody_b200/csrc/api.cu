@@ -15,6 +15,7 @@ int comm_step_exchange(Sim& s);                     // comm.cu
 void comm_destroy(Sim& s);                          // comm.cu
 int comm_partition(Sim& s);                         // comm.cu
 int comm_exchange_aos(Sim& s);                      // comm.cu
+int comm_exchange_acc(Sim& s);                      // comm.cu
 
 namespace {
 
@@ -382,6 +383,11 @@ int nbody_cuda_get_accelerations(nbody_cuda_sim* sim, float* xyz, uint64_t capac
 	Sim* s = reinterpret_cast<Sim*>(sim);
 	if (!s || !xyz || capacity < s->n) { set_error("get_accelerations: bad argument"); return NBODY_ERR_INVALID; }
 	NB_CUDA_CHECK(cudaSetDevice(s->device));
+	if (s->comm) {  // collective in distributed mode: the slices are exchanged on first use
+		int rc = comm_exchange_acc(*s);
+		if (rc) return rc;
+		NB_CUDA_CHECK(cudaStreamSynchronize(s->stream));
+	}
 	std::vector<float4> h(s->n);
 	NB_CUDA_CHECK(cudaMemcpy(h.data(), s->acc, s->n * sizeof(float4), cudaMemcpyDeviceToHost));
 	for (uint64_t i = 0; i < s->n; ++i) { xyz[3 * i] = h[i].x; xyz[3 * i + 1] = h[i].y; xyz[3 * i + 2] = h[i].z; }

@@ -127,7 +127,15 @@ int comm_step_exchange(Sim& s) {
 	int rc;
 	if ((rc = exchange(s, s.posq[0], sizeof(float4)))) return rc;
 	if ((rc = exchange(s, s.velm[0], sizeof(float4)))) return rc;
-	if ((rc = exchange(s, s.acc, sizeof(float4)))) return rc;
+	s.acc_partial = true;  // accelerations stay rank-local until somebody asks for them (comm_exchange_acc)
+	return NBODY_OK;
+}
+
+int comm_exchange_acc(Sim& s) {
+	if (!s.acc_partial) return NBODY_OK;
+	int rc = exchange(s, s.acc, sizeof(float4));
+	if (rc) return rc;
+	s.acc_partial = false;
 	return NBODY_OK;
 }
 

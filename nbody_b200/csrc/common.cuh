@@ -118,6 +118,7 @@ struct Sim {
 	cudaEvent_t ev[12] = {};
 	uint64_t device_bytes = 0;
 	bool lists_valid = false;
+	bool acc_partial = false;  // distributed: `acc` holds only this rank's slice until comm_exchange_acc()
 };
 
 // ---- error plumbing ---------------------------------------------------------

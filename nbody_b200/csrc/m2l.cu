@@ -164,16 +164,34 @@ k_m2l(Ctrl* __restrict__ c, const Group* __restrict__ items, uint32_t items_cap,
 			}
 			__syncwarp();
 			any = any || (cnt_h + cnt_l) != 0;
-			for (uint32_t k = lane; k < cnt_h; k += 32) {
-				const uint32_t s = s0 + S.list_hi[w][k];
-				m2l_one<P, P>(Lacc, tg, S.sgeom[cur][s], S.sM[cur] + s * STRIDE, eps2);
+			// order P pairs; the slot number and geometry of the next iteration are fetched before the math of this one
+			{
+				uint32_t k = lane;
+				uint32_t sc = 0; float4 gc = make_float4(0.f, 0.f, 0.f, 0.f);
+				if (k < cnt_h) { sc = s0 + S.list_hi[w][k]; gc = S.sgeom[cur][sc]; }
+				while (k < cnt_h) {
+					const uint32_t kn = k + 32;
+					uint32_t sn = 0; float4 gn = gc;
+					if (kn < cnt_h) { sn = s0 + S.list_hi[w][kn]; gn = S.sgeom[cur][sn]; }
+					m2l_one<P, P>(Lacc, tg, gc, S.sM[cur] + sc * STRIDE, eps2);
+					k = kn; sc = sn; gc = gn;
+				}
 			}
 			// order P-1 pairs: two interactions per lane in flight while whole 64-slot strides remain (their
 			// derivative chains and FMA streams interleave), then the remainder one at a time
 			uint32_t base = 0;
-			for (; base + 64 <= cnt_l; base += 64) {
-				const uint32_t sa = s0 + S.list_lo[w][base + lane], sb = s0 + S.list_lo[w][base + 32 + lane];
-				m2l_two<P, PL>(Lacc, tg, S.sgeom[cur][sa], S.sM[cur] + sa * STRIDE, S.sgeom[cur][sb], S.sM[cur] + sb * STRIDE, eps2);
+			if (cnt_l >= 64) {
+				uint32_t sa = s0 + S.list_lo[w][lane], sb = s0 + S.list_lo[w][32 + lane];
+				float4 ga = S.sgeom[cur][sa], gb = S.sgeom[cur][sb];
+				for (; base + 64 <= cnt_l; base += 64) {
+					uint32_t san = sa, sbn = sb; float4 gan = ga, gbn = gb;
+					if (base + 128 <= cnt_l) {
+						san = s0 + S.list_lo[w][base + 64 + lane]; sbn = s0 + S.list_lo[w][base + 96 + lane];
+						gan = S.sgeom[cur][san]; gbn = S.sgeom[cur][sbn];
+					}
+					m2l_two<P, PL>(Lacc, tg, ga, S.sM[cur] + sa * STRIDE, gb, S.sM[cur] + sb * STRIDE, eps2);
+					sa = san; sb = sbn; ga = gan; gb = gbn;
+				}
 			}
 			for (uint32_t k = base + lane; k < cnt_l; k += 32) {
 				const uint32_t s = s0 + S.list_lo[w][k];
@@ -199,12 +217,16 @@ k_m2l(Ctrl* __restrict__ c, const Group* __restrict__ items, uint32_t items_cap,
 // L2L: every non-empty node adds the shifted local expansion of its parent; levels ascending.
 template <int P>
 __global__ void __launch_bounds__(128) k_l2l(const Ctrl* __restrict__ c, int l, const float4* __restrict__ geom,
-                                             const uint2* __restrict__ info, const uint32_t* __restrict__ nparent, float* __restrict__ L) {
+                                             const uint2* __restrict__ info, const uint32_t* __restrict__ nparent,
+                                             const uint32_t* __restrict__ nbegin, uint32_t own_first, uint32_t own_end, float* __restrict__ L) {
 	using E = Expansion<P>;
 	constexpr int STRIDE = coef_stride(P);
 	const uint32_t lo = c->level_off[l], hi = c->level_off[l + 1];
 	for (uint32_t node = lo + blockIdx.x * blockDim.x + threadIdx.x; node < hi; node += gridDim.x * blockDim.x) {
-		if (info[node].y == 0u) continue;
+		const uint32_t cnt = info[node].y;
+		if (cnt == 0u) continue;
+		const uint32_t nb0 = nbegin[node];
+		if (nb0 >= own_end || nb0 + cnt <= own_first) continue;  // holds none of this rank's particles: its local expansion is never read
 		const uint32_t par = nparent[node];
 		const float4 g = geom[node], gp = geom[par];
 		float lp[E::NC], lc[E::NC];
@@ -239,7 +261,8 @@ static void m2l_t(Sim& s) {
 template <int P>
 static void l2l_t(Sim& s) {
 	for (int l = 1; l <= (int) s.cfg.max_depth; ++l)
-		k_l2l<P><<<kNumSM * 4, 128, 0, s.stream>>>(s.ctrl, l, s.geom, s.info, s.nparent, s.L);
+		k_l2l<P><<<kNumSM * 4, 128, 0, s.stream>>>(s.ctrl, l, s.geom, s.info, s.nparent, s.nbegin, (uint32_t) s.own_first,
+		                                          (uint32_t) (s.own_first + s.own_count), s.L);
 }
 
 void launch_m2l(Sim& s) {

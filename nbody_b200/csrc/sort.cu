@@ -1,0 +1,170 @@
+// Stage 1a: stable LSD radix sort of (63-bit Morton key, 32-bit index) pairs, hand-written.
+// 8 passes of 8 bits. Each pass: (1) per-tile digit histograms, (2) one exclusive scan over the
+// digit-major histogram table, (3) stable scatter — every warp ranks its elements with
+// __match_any_sync (equal digits inside a warp-row keep lane order, rows keep row order, warps and
+// tiles keep index order), so the permutation is identical to a stable CPU sort (the oracle's
+// std::stable_sort): ties between equal keys keep their previous order.
+// HBM traffic per pass: 8 B (histogram read) + 12 B read + 12 B write per element.
+#include "common.cuh"
+
+namespace nbody {
+
+constexpr int kSortThreads = 256;
+constexpr int kSortItems = 16;                          // elements per thread
+constexpr int kSortTile = kSortThreads * kSortItems;    // 4096 elements per CTA
+constexpr int kSortWarps = kSortThreads / 32;
+
+__global__ void __launch_bounds__(kSortThreads) k_sort_hist(uint64_t n, const uint64_t* __restrict__ keys, int shift, uint32_t nblocks,
+                                                            uint32_t* __restrict__ hist) {
+	__shared__ uint32_t h[256];
+	h[threadIdx.x] = 0;
+	__syncthreads();
+	const uint64_t base = (uint64_t) blockIdx.x * kSortTile;
+#pragma unroll
+	for (int j = 0; j < kSortItems; ++j) {
+		const uint64_t i = base + (uint64_t) j * kSortThreads + threadIdx.x;
+		if (i < n) atomicAdd(&h[(uint32_t) (keys[i] >> shift) & 255u], 1u);
+	}
+	__syncthreads();
+	hist[(size_t) threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];  // digit-major: one scan gives every tile's base
+}
+
+// ---- exclusive scan of a uint32 array (three launches: tile sums, scan of the sums, apply) ----
+constexpr int kScanTile = 2048;  // 256 threads x 8
+
+__device__ __forceinline__ uint32_t block_scan_256(uint32_t v, uint32_t* ws, uint32_t& total) {
+	const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+	uint32_t inc = v;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+		if (lane >= (unsigned) d) inc += t;
+	}
+	if (lane == 31) ws[w] = inc;
+	__syncthreads();
+	if (w == 0) {
+		uint32_t x = lane < 8 ? ws[lane] : 0u;
+#pragma unroll
+		for (int d = 1; d < 8; d <<= 1) {
+			const uint32_t t = __shfl_up_sync(0xffffffffu, x, d);
+			if (lane >= (unsigned) d) x += t;
+		}
+		if (lane < 8) ws[lane] = x;
+	}
+	__syncthreads();
+	total = ws[7];
+	const uint32_t base = w ? ws[w - 1] : 0u;
+	__syncthreads();
+	return base + inc - v;
+}
+
+__global__ void __launch_bounds__(256) k_scan_sums(uint32_t n, const uint32_t* __restrict__ in, uint32_t* __restrict__ sums) {
+	__shared__ uint32_t ws[8];
+	const uint32_t base = blockIdx.x * kScanTile + threadIdx.x * 8;
+	uint32_t s = 0;
+#pragma unroll
+	for (int k = 0; k < 8; ++k) if (base + k < n) s += in[base + k];
+	uint32_t total;
+	block_scan_256(s, ws, total);
+	if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(256) k_scan_top(uint32_t m, uint32_t* sums) {  // single CTA: exclusive scan of the tile sums in place
+	__shared__ uint32_t ws[8];
+	uint32_t carry = 0;
+	for (uint32_t b0 = 0; b0 < m; b0 += 256) {
+		const uint32_t i = b0 + threadIdx.x;
+		const uint32_t v = i < m ? sums[i] : 0u;
+		uint32_t total;
+		const uint32_t ex = block_scan_256(v, ws, total);
+		if (i < m) sums[i] = carry + ex;
+		carry += total;
+	}
+}
+__global__ void __launch_bounds__(256) k_scan_apply(uint32_t n, uint32_t* data, const uint32_t* __restrict__ sums) {
+	__shared__ uint32_t ws[8];
+	const uint32_t base = blockIdx.x * kScanTile + threadIdx.x * 8;
+	uint32_t v[8], s = 0;
+#pragma unroll
+	for (int k = 0; k < 8; ++k) { v[k] = base + k < n ? data[base + k] : 0u; s += v[k]; }
+	uint32_t total;
+	uint32_t run = sums[blockIdx.x] + block_scan_256(s, ws, total);
+#pragma unroll
+	for (int k = 0; k < 8; ++k) { if (base + k < n) data[base + k] = run; run += v[k]; }
+}
+
+// ---- stable scatter ----
+__global__ void __launch_bounds__(kSortThreads) k_sort_scatter(uint64_t n, const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                                                               uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int shift,
+                                                               uint32_t nblocks, const uint32_t* __restrict__ offsets) {
+	__shared__ uint32_t whist[kSortWarps][256];  // per warp: running count per digit, then exclusive base inside the tile
+	__shared__ uint32_t gbase[256];
+	const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+	for (int k = threadIdx.x; k < kSortWarps * 256; k += kSortThreads) (&whist[0][0])[k] = 0;
+	gbase[threadIdx.x] = offsets[(size_t) threadIdx.x * nblocks + blockIdx.x];
+	__syncthreads();
+	// warp w owns the contiguous range [w*512, (w+1)*512) of the tile, visited row by row (32 consecutive elements per row)
+	const uint64_t wbase = (uint64_t) blockIdx.x * kSortTile + (uint64_t) w * (32 * kSortItems);
+	uint64_t key[kSortItems];
+	uint32_t rank[kSortItems];
+#pragma unroll
+	for (int j = 0; j < kSortItems; ++j) {
+		const uint64_t i = wbase + 32 * j + lane;
+		const bool ok = i < n;
+		key[j] = ok ? keys_in[i] : ~0ull;
+		const uint32_t d = (uint32_t) (key[j] >> shift) & 255u;
+		const unsigned peers = __match_any_sync(0xffffffffu, ok ? d : 256u + lane);  // out-of-range lanes match nobody
+		const uint32_t before = whist[w][d];
+		rank[j] = before + __popc(peers & ((1u << lane) - 1u));
+		__syncwarp();
+		if (ok && (peers >> lane) == 1u) whist[w][d] = before + __popc(peers);  // the highest peer lane updates the count
+		__syncwarp();
+	}
+	__syncthreads();
+	{  // exclusive prefix over the warps, per digit (thread = digit)
+		uint32_t run = 0;
+#pragma unroll
+		for (int ww = 0; ww < kSortWarps; ++ww) { const uint32_t c = whist[ww][threadIdx.x]; whist[ww][threadIdx.x] = run; run += c; }
+	}
+	__syncthreads();
+#pragma unroll
+	for (int j = 0; j < kSortItems; ++j) {
+		const uint64_t i = wbase + 32 * j + lane;
+		if (i < n) {
+			const uint32_t d = (uint32_t) (key[j] >> shift) & 255u;
+			const uint32_t pos = gbase[d] + whist[w][d] + rank[j];
+			keys_out[pos] = key[j];
+			vals_out[pos] = vals_in[i];
+		}
+	}
+}
+
+size_t own_sort_temp_bytes(uint64_t n) {
+	const uint64_t nblocks = (n + kSortTile - 1) / kSortTile;
+	const uint64_t hist = 256 * nblocks;
+	const uint64_t sums = (hist + kScanTile - 1) / kScanTile;
+	return (size_t) (hist + sums + 64) * sizeof(uint32_t);
+}
+
+// Sorts (keys[0], idx[0]) ascending by the low 63 key bits; the result ends in keys[0] / idx[0] (8 passes = even).
+void launch_own_sort(Sim& s) {
+	const uint64_t n = s.n;
+	const uint32_t nblocks = (uint32_t) ((n + kSortTile - 1) / kSortTile);
+	const uint32_t hist_n = 256u * nblocks;
+	const uint32_t nsums = (hist_n + kScanTile - 1) / kScanTile;
+	uint32_t* hist = static_cast<uint32_t*>(s.sort_tmp);
+	uint32_t* sums = hist + hist_n;
+	uint64_t* kin = s.keys[0]; uint64_t* kout = s.keys[1];
+	uint32_t* vin = s.idx[0]; uint32_t* vout = s.idx[1];
+	for (int pass = 0; pass < 8; ++pass) {
+		const int shift = 8 * pass;
+		k_sort_hist<<<nblocks, kSortThreads, 0, s.stream>>>(n, kin, shift, nblocks, hist);
+		k_scan_sums<<<nsums, 256, 0, s.stream>>>(hist_n, hist, sums);
+		k_scan_top<<<1, 256, 0, s.stream>>>(nsums, sums);
+		k_scan_apply<<<nsums, 256, 0, s.stream>>>(hist_n, hist, sums);
+		k_sort_scatter<<<nblocks, kSortThreads, 0, s.stream>>>(n, kin, vin, kout, vout, shift, nblocks, hist);
+		uint64_t* tk = kin; kin = kout; kout = tk;
+		uint32_t* tv = vin; vin = vout; vout = tv;
+	}
+}
+
+}  // namespace nbody

@@ -91,12 +91,15 @@ __global__ void k_gather(uint64_t n, const uint32_t* __restrict__ idx, const flo
 	}
 }
 
+size_t own_sort_temp_bytes(uint64_t n);  // sort.cu
+void launch_own_sort(Sim& s);            // sort.cu
+
 size_t sort_temp_bytes(uint64_t n) {
 	size_t bytes = 0;
 	cub::DoubleBuffer<uint64_t> k(nullptr, nullptr);
 	cub::DoubleBuffer<uint32_t> v(nullptr, nullptr);
 	cub::DeviceRadixSort::SortPairs(nullptr, bytes, k, v, (int64_t) n, 0, 63);
-	return bytes;
+	return bytes > own_sort_temp_bytes(n) ? bytes : own_sort_temp_bytes(n);
 }
 
 // keys of state order -> stable radix sort -> gather the state into sorted order (posq[1], velm[1], orig[1]).
@@ -105,12 +108,17 @@ int launch_keys_sort_permute(Sim& s) {
 	const uint64_t n = s.n;
 	const float sx = 2097152.0f / s.cfg.bounds[0], sy = 2097152.0f / s.cfg.bounds[1], sz = 2097152.0f / s.cfg.bounds[2];
 	k_keys<<<grid_for(n, 256), 256, 0, s.stream>>>(n, s.posq[0], sx, sy, sz, s.keys[0], s.idx[0]);
-	cub::DoubleBuffer<uint64_t> k(s.keys[0], s.keys[1]);
-	cub::DoubleBuffer<uint32_t> v(s.idx[0], s.idx[1]);
-	size_t bytes = s.sort_tmp_bytes;
-	NB_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(s.sort_tmp, bytes, k, v, (int64_t) n, 0, 63, s.stream));
-	if (k.Current() != s.keys[0]) { std::swap(s.keys[0], s.keys[1]); }
-	if (v.Current() != s.idx[0]) { std::swap(s.idx[0], s.idx[1]); }
+	if (s.cfg.flags & NBODY_FLAG_CUB_SORT) {
+		// comparison path only: CUB's onesweep sort, the bar the hand-written sort is measured against
+		cub::DoubleBuffer<uint64_t> k(s.keys[0], s.keys[1]);
+		cub::DoubleBuffer<uint32_t> v(s.idx[0], s.idx[1]);
+		size_t bytes = s.sort_tmp_bytes;
+		NB_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(s.sort_tmp, bytes, k, v, (int64_t) n, 0, 63, s.stream));
+		if (k.Current() != s.keys[0]) { std::swap(s.keys[0], s.keys[1]); }
+		if (v.Current() != s.idx[0]) { std::swap(s.idx[0], s.idx[1]); }
+	} else {
+		launch_own_sort(s);
+	}
 	k_gather<<<grid_for(n, 256), 256, 0, s.stream>>>(n, s.idx[0], s.posq[0], s.velm[0], s.orig[0], s.posq[1], s.velm[1], s.orig[1]);
 	return NBODY_OK;
 }
