@@ -5,8 +5,12 @@
   (N > 1: launched by torchrun, one rank per GPU)
 
 A "step" is one Simulation::step() on the metric's configuration: a Plummer sphere
-of N = 16M particles (BASELINE.json configs[2]), at the reference's constants (MAC
-0.5, softening 0.01, leaf capacity 8). One JSON line on stdout (rank 0).
+of N = 16M particles (BASELINE.json configs[2]), at the reference's physics constants
+(MAC 0.5, softening 0.01). The octree node capacity — hard-coded to 8 in the reference
+with a "should be adjustable" FIXME (src/open_cl_simulation.cpp:41-47) — is a tuning
+parameter here: the headline runs at 32, and the same workload at the reference's 8 is
+measured in the same run and reported under "reference_capacity". One JSON line on
+stdout (rank 0).
   value     whole-job particle-steps/s, state resident in HBM
   e2e       the same through the C ABI with HOST buffers: set_particles (H2D) +
             step + get_particles (D2H) inside the timed region
@@ -151,7 +155,9 @@ def main():
     ap.add_argument("--workload", default="plummer", choices=["plummer", "uniform", "two_galaxies"])
     ap.add_argument("--n", type=int, default=1 << 24)
     ap.add_argument("--order", type=int, default=4)
-    ap.add_argument("--leaf-capacity", type=int, default=8)
+    ap.add_argument("--leaf-capacity", type=int, default=32,
+                    help="octree node capacity; the reference hard-codes 8 with a FIXME (src/open_cl_simulation.cpp:41-47), 32 is the B200 tuning")
+    ap.add_argument("--no-reference-capacity", action="store_true", help="skip the additional measurement at the reference's capacity 8")
     ap.add_argument("--dt", type=float, default=1e-3)
     ap.add_argument("--cpu-sample", type=int, default=16384)
     ap.add_argument("--cpu-steps", type=int, default=8)
@@ -188,14 +194,14 @@ def main():
     host = torch.from_numpy(P).pin_memory()
     Pn = host.numpy()
 
-    cfgkw = dict(order=args.order, leaf_capacity=args.leaf_capacity, device=local_rank, pool_scale=args.pool_scale,
-                 force_constant=workloads.force_constant(args.workload, n))
-    if world == 1:
-        sim = nbody_b200.CudaSimulation([1.0, 1.0, 1.0], Pn, args.dt, **cfgkw)
-    else:
+    def make_sim(capacity):
+        cfgkw = dict(order=args.order, leaf_capacity=capacity, device=local_rank, pool_scale=args.pool_scale,
+                     force_constant=workloads.force_constant(args.workload, n))
+        if world == 1:
+            return nbody_b200.CudaSimulation([1.0, 1.0, 1.0], Pn, args.dt, **cfgkw)
         uid = [nbody_b200.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
-        sim = nbody_b200.CudaSimulation([1.0, 1.0, 1.0], Pn, args.dt, _distributed={
+        return nbody_b200.CudaSimulation([1.0, 1.0, 1.0], Pn, args.dt, _distributed={
             "unique_id": uid[0], "n_global": n, "global_offset": lo, "rank": rank, "world": world}, **cfgkw)
 
     def barrier():
@@ -204,38 +210,42 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        sim.step()
+    def timed_steps(sim, warm, k, sampler=None):
+        """`warm` untimed steps, then exactly k steps between barriers; returns (seconds [max over ranks], per-step stage ms, counts)."""
+        for _ in range(warm):
+            sim.step()
+        barrier()
+        if sampler is not None:
+            sampler.start()
+        sums, cnts = {}, {}
+        t0 = time.perf_counter()
+        for _ in range(k):
+            sim.step()
+            for key, v in sim.stats().items():
+                if key.startswith("ms_"):
+                    sums[key] = sums.get(key, 0.0) + v
+                else:
+                    cnts[key] = v
+        barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+        return dt, {key: v / k for key, v in sums.items()}, cnts
+
+    sim = make_sim(args.leaf_capacity)
     sampler = ClockSampler(local_rank)
-    barrier()
-    sampler.start()
-    stage_ms = {}
-    counts = {}
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        sim.step()
-        st = sim.stats()
-        for k, v in st.items():
-            if k.startswith("ms_"):
-                stage_ms[k] = stage_ms.get(k, 0.0) + v
-            else:
-                counts[k] = v
-    barrier()
-    elapsed = time.perf_counter() - t0
+    elapsed, stage_ms, counts = timed_steps(sim, max(args.warmup, 3), args.steps, sampler)
     clocks = sampler.stop()
+    value = n * args.steps / elapsed
+    K = args.steps
     rank_ms = None
     if world > 1:
-        tt = torch.tensor([elapsed], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        elapsed = float(tt.item())
-        mine = torch.tensor([stage_ms.get(k, 0.0) / args.steps for k in ("ms_traverse", "ms_m2l", "ms_leaf", "ms_comm")],
-                            device="cuda", dtype=torch.float64)
+        mine = torch.tensor([stage_ms.get(k, 0.0) for k in ("ms_traverse", "ms_m2l", "ms_leaf", "ms_comm")], device="cuda", dtype=torch.float64)
         allm = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(allm, mine)
         rank_ms = [[round(float(x), 2) for x in t] for t in allm]
-    value = n * args.steps / elapsed
-    K = args.steps
-    stage_ms = {k: v / K for k, v in stage_ms.items()}
 
     # ---- end to end through the C ABI with host buffers --------------------------------
     # every step: H2D of this rank's slice of the state from pinned host memory (set_owned_particles, which
@@ -263,6 +273,24 @@ def main():
         e2e_t, h2d, d2h = float(mx[0]), float(sm[1]), float(sm[2])
     e2e = {"value": n * args.e2e_steps / e2e_t, "unit": UNIT, "h2d_bytes_per_step": int(h2d / args.e2e_steps),
            "d2h_bytes_per_step": int(d2h / args.e2e_steps), "ms_per_step": 1e3 * e2e_t / args.e2e_steps, "steps": args.e2e_steps}
+
+    sim.close()
+    ref_cap = None
+    if args.leaf_capacity != 8 and not args.no_reference_capacity:
+        # the same workload at the reference's hard-coded node capacity (src/open_cl_simulation.cpp:41-47), for the record
+        sim8 = make_sim(8)
+        dt8, st8, c8 = timed_steps(sim8, 3, min(args.steps, 3))
+        sim8.close()
+        ref_cap = {"leaf_capacity": 8, "value": n * min(args.steps, 3) / dt8, "unit": UNIT, "ms_per_step": 1e3 * dt8 / min(args.steps, 3),
+                   "stage_ms": st8, "m2l_interactions": c8.get("m2l_interactions"), "p2p_interactions": c8.get("p2p_interactions")}
+    p2p_micro = None
+    if rank == 0:
+        # P2P FP32 microbenchmark (BASELINE metric, second half): the all-pairs tiled kernel on 2^18 x 2^20 bodies of the workload
+        nm = min(Pn.shape[0], 1 << 20)
+        ntg = min(nm, N_SM * 2 * 1024)  # 2 CTAs of 1024 targets per SM: whole waves
+        src = np.ascontiguousarray(np.concatenate([Pn[:nm, 0:3], Pn[:nm, 9:10]], axis=1))
+        _, ms = nbody_b200.direct_field(src, src[:ntg], 0.01, device=local_rank, repeats=3)
+        p2p_micro = {"kernel": "k_direct", "targets": ntg, "sources": nm, "ms": ms, "tflops": 20.0 * ntg * nm / (ms * 1e-3) / 1e12}
 
     if rank == 0:
         peaks = measured_peaks()
@@ -295,7 +323,10 @@ def main():
                        "partition": "morton-range" if world > 1 else "single"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": K * launches_per_step(sim, world),
             "roofline": roof,
-            "p2p_fp32_tflops": p2p_tf, "p2p_frac_of_fp32_peak": p2p_tf / peak, "m2l_fp32_tflops": m2l_tf,
+            "p2p_fp32_tflops": {"tree_p2p_kernel": p2p_tf, "tree_p2p_frac_of_peak": p2p_tf / peak,
+                                "all_pairs_kernel": p2p_micro["tflops"], "all_pairs_frac_of_peak": p2p_micro["tflops"] / peak,
+                                "all_pairs_config": p2p_micro},
+            "m2l_fp32_tflops": m2l_tf, "reference_capacity": ref_cap,
             "stage_ms": stage_ms, "counts": counts,
         }
         if rank_ms is not None:

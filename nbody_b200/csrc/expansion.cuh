@@ -95,7 +95,8 @@ struct Expansion {
 		monomials(x, y, z, mono);
 		const float R2 = x * x + y * y + z * z + eps2;
 #if defined(__CUDA_ARCH__)
-		const float inv = rsqrtf(R2);
+		float inv;  // one MUFU.RSQ: R2 >= eps^2 or a cell separation squared, never denormal, so no fix-up code is wanted
+		asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(R2));
 #else
 		const float inv = 1.0f / sqrtf(R2);
 #endif

@@ -31,8 +31,9 @@ template <bool SOFT>
 __device__ __forceinline__ void p2p_interact(const float4& s, float tx, float ty, float tz, float eps2, float& ax, float& ay, float& az) {
 	const float dx = s.x - tx, dy = s.y - ty, dz = s.z - tz;
 	const float r2 = fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, eps2)));
-	float inv = rsqrtf(r2);
-	if (!SOFT) inv = r2 > 0.0f ? inv : 0.0f;  // eps = 0: coincident points (and i == j) exert no force
+	float inv;
+	if (SOFT) asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(r2));  // r2 >= eps^2: a bare MUFU.RSQ, no denormal fix-up
+	else inv = r2 > 0.0f ? rsqrtf(r2) : 0.0f;  // eps = 0: coincident points (and i == j) exert no force
 	const float inv2 = inv * inv;
 	const float w = (s.w * inv) * inv2;
 	ax = fmaf(w, dx, ax);
@@ -62,19 +63,28 @@ struct LeafArgs {
 	unsigned long long* stat_leaves;
 };
 
-template <bool SOFT>
-__device__ __forceinline__ void tile_compute(const float4* buf, uint32_t fill, unsigned sl, unsigned S, float tx, float ty, float tz,
-                                             float eps2, float& ax, float& ay, float& az) {
+// Every lane walks its slice of the tile (sources sl, sl+S, ...) for one target, or two when TWO.
+template <bool SOFT, bool TWO>
+__device__ __forceinline__ void tile_compute(const float4* buf, uint32_t fill, unsigned sl, unsigned S, const float4& ta, const float4& tb,
+                                             float eps2, float (&acc)[6]) {
 	__syncwarp();
 	uint32_t j = sl;
 	for (; j + 3 * S < fill; j += 4 * S) {
 		const float4 s0 = buf[j], s1 = buf[j + S], s2 = buf[j + 2 * S], s3 = buf[j + 3 * S];
-		p2p_interact<SOFT>(s0, tx, ty, tz, eps2, ax, ay, az);
-		p2p_interact<SOFT>(s1, tx, ty, tz, eps2, ax, ay, az);
-		p2p_interact<SOFT>(s2, tx, ty, tz, eps2, ax, ay, az);
-		p2p_interact<SOFT>(s3, tx, ty, tz, eps2, ax, ay, az);
+		p2p_interact<SOFT>(s0, ta.x, ta.y, ta.z, eps2, acc[0], acc[1], acc[2]);
+		if (TWO) p2p_interact<SOFT>(s0, tb.x, tb.y, tb.z, eps2, acc[3], acc[4], acc[5]);
+		p2p_interact<SOFT>(s1, ta.x, ta.y, ta.z, eps2, acc[0], acc[1], acc[2]);
+		if (TWO) p2p_interact<SOFT>(s1, tb.x, tb.y, tb.z, eps2, acc[3], acc[4], acc[5]);
+		p2p_interact<SOFT>(s2, ta.x, ta.y, ta.z, eps2, acc[0], acc[1], acc[2]);
+		if (TWO) p2p_interact<SOFT>(s2, tb.x, tb.y, tb.z, eps2, acc[3], acc[4], acc[5]);
+		p2p_interact<SOFT>(s3, ta.x, ta.y, ta.z, eps2, acc[0], acc[1], acc[2]);
+		if (TWO) p2p_interact<SOFT>(s3, tb.x, tb.y, tb.z, eps2, acc[3], acc[4], acc[5]);
 	}
-	for (; j < fill; j += S) p2p_interact<SOFT>(buf[j], tx, ty, tz, eps2, ax, ay, az);
+	for (; j < fill; j += S) {
+		const float4 s0 = buf[j];
+		p2p_interact<SOFT>(s0, ta.x, ta.y, ta.z, eps2, acc[0], acc[1], acc[2]);
+		if (TWO) p2p_interact<SOFT>(s0, tb.x, tb.y, tb.z, eps2, acc[3], acc[4], acc[5]);
+	}
 	__syncwarp();
 }
 
@@ -103,13 +113,19 @@ __global__ void __launch_bounds__(kLeafWarps * 32) k_leaf(const LeafArgs a) {
 		const float4 g = a.geom[node];
 		for (uint32_t t0 = 0; t0 < nt; t0 += 32) {
 			const uint32_t ntc = min(32u, nt - t0);
-			const unsigned T = ntc <= 1 ? 1u : 1u << (32 - __clz(ntc - 1));  // power of two >= ntc
-			const unsigned S = 32u / T;
-			const unsigned t = lane & (T - 1u), sl = lane / T;
-			const bool has_t = t < ntc;
-			float4 tp = make_float4(0.f, 0.f, 0.f, 0.f);
-			if (has_t) tp = a.posq[b + t0 + t];
-			float ax = 0.f, ay = 0.f, az = 0.f;
+			// Warp layout: T target lanes x S source slices, one or two targets per lane, whichever wastes fewer
+			// lanes: T = ntc (or ceil(ntc/2) with two targets per lane), S = floor(32 / T); lanes >= T*S stay idle.
+			const unsigned T1 = ntc, S1 = 32u / T1, T2 = (ntc + 1u) / 2u, S2 = 32u / T2;
+			const bool two = ntc * S2 > 2u * ntc * S1;  // useful fraction ntc*S2/64 against ntc*S1/32
+			const unsigned T = two ? T2 : T1, S = two ? S2 : S1;
+			const unsigned sl_raw = lane / T, t = lane - sl_raw * T;
+			const bool lane_on = lane < T * S;
+			const unsigned sl = lane_on ? sl_raw : (unsigned) kLeafTile;  // idle lanes: an empty slice
+			const bool has_a = lane_on && t < ntc, has_b = two && lane_on && t + T < ntc;
+			float4 tp = make_float4(0.f, 0.f, 0.f, 0.f), tq = tp;
+			if (has_a) tp = a.posq[b + t0 + t];
+			if (has_b) tq = a.posq[b + t0 + t + T];
+			float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 			unsigned long long nsrc = 0;
 			// ---- cursor over the segment chain ----
 			uint32_t si = a.p2p_head[node], e0 = 0;
@@ -155,7 +171,8 @@ __global__ void __launch_bounds__(kLeafWarps * 32) k_leaf(const LeafArgs a) {
 				uint2 ent_nn = make_uint2(0u, 0u);
 				const bool has_nn = has_nxt && fetch(ent_nn);  // entries of the batch after next: in flight during the math
 				leaf_cp_async_wait1();
-				tile_compute<SOFT>(sbuf[w][cur], fill_cur, sl, S, tp.x, tp.y, tp.z, a.eps2, ax, ay, az);
+				if (two) tile_compute<SOFT, true>(sbuf[w][cur], fill_cur, sl, S, tp, tq, a.eps2, acc);
+				else tile_compute<SOFT, false>(sbuf[w][cur], fill_cur, sl, S, tp, tq, a.eps2, acc);
 				nsrc += fill_cur;
 				while (big_cur) {  // stream an over-full source leaf through the tile that has just been consumed
 					const int first = __ffs(big_cur) - 1;
@@ -163,7 +180,8 @@ __global__ void __launch_bounds__(kLeafWarps * 32) k_leaf(const LeafArgs a) {
 					for (uint32_t q0 = 0; q0 < fc; q0 += kLeafTile) {
 						const uint32_t m = min((uint32_t) kLeafTile, fc - q0);
 						for (uint32_t q = lane; q < m; q += 32) sbuf[w][cur][q] = a.posq[fb + q0 + q];
-						tile_compute<SOFT>(sbuf[w][cur], m, sl, S, tp.x, tp.y, tp.z, a.eps2, ax, ay, az);
+						if (two) tile_compute<SOFT, true>(sbuf[w][cur], m, sl, S, tp, tq, a.eps2, acc);
+						else tile_compute<SOFT, false>(sbuf[w][cur], m, sl, S, tp, tq, a.eps2, acc);
 					}
 					nsrc += fc;
 					big_cur &= big_cur - 1;
@@ -173,14 +191,24 @@ __global__ void __launch_bounds__(kLeafWarps * 32) k_leaf(const LeafArgs a) {
 				cur ^= 1;
 			}
 			leaf_cp_async_wait0();
-			for (unsigned d = T; d < 32u; d <<= 1) {
-				ax += __shfl_xor_sync(0xffffffffu, ax, d);
-				ay += __shfl_xor_sync(0xffffffffu, ay, d);
-				az += __shfl_xor_sync(0xffffffffu, az, d);
+			// sum over the S slices into the lanes of slice 0 (lane t collects lanes t + s*T)
+#pragma unroll
+			for (int q = 0; q < 6; ++q) {
+				if (q >= 3 && !two) break;
+				float v = acc[q];
+				if ((T & (T - 1u)) == 0u) {  // T*S == 32: butterfly
+					for (unsigned d = T; d < 32u; d <<= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+				} else {
+					const float mine = lane_on ? v : 0.f;
+					float sum = mine;
+					for (unsigned sidx = 1; sidx < S; ++sidx) sum += __shfl_sync(0xffffffffu, mine, (lane + sidx * T) & 31u);
+					v = sum;
+				}
+				acc[q] = v;
 			}
 			if (lane == 0) inter += nsrc * ntc;
-			if (sl == 0 && has_t) {
-				// far field: L2P of this leaf's local expansion
+			if (lane_on && sl_raw == 0) {
+				// far field: L2P of this leaf's local expansion, then the integrator — for each target of the lane
 				float l[E::NC];
 				const float4* L4 = reinterpret_cast<const float4*>(a.L + (size_t) node * STRIDE);
 #pragma unroll
@@ -191,22 +219,27 @@ __global__ void __launch_bounds__(kLeafWarps * 32) k_leaf(const LeafArgs a) {
 					if (4 * q + 2 < E::NC) l[4 * q + 2] = v.z;
 					if (4 * q + 3 < E::NC) l[4 * q + 3] = v.w;
 				}
-				float fx, fy, fz;
-				E::l2p(l, tp.x - g.x, tp.y - g.y, tp.z - g.z, fx, fy, fz);
-				const uint32_t i = b + t0 + t;
-				const float4 vm = a.velm_in[i];
-				const float sc = a.G * tp.w / vm.w;  // a = G q/m * field (src/force.cl:4-10, src/open_cl_simulation.cpp:602-604)
-				const float axx = sc * (ax + fx), ayy = sc * (ay + fy), azz = sc * (az + fz);
-				a.acc[i] = make_float4(axx, ayy, azz, 0.f);
-				if (!a.no_integrate) {
-					const float vx = fmaf(axx, a.dt, vm.x), vy = fmaf(ayy, a.dt, vm.y), vz = fmaf(azz, a.dt, vm.z);
-					const float ux = a.integrator == NBODY_KICK_DRIFT ? vx : vm.x, uy = a.integrator == NBODY_KICK_DRIFT ? vy : vm.y,
-					            uz = a.integrator == NBODY_KICK_DRIFT ? vz : vm.z;
-					a.posq_out[i] = make_float4(fmaf(ux, a.dt, tp.x), fmaf(uy, a.dt, tp.y), fmaf(uz, a.dt, tp.z), tp.w);
-					a.velm_out[i] = make_float4(vx, vy, vz, vm.w);
-				} else {
-					a.posq_out[i] = tp;
-					a.velm_out[i] = vm;
+#pragma unroll 1
+				for (int r = 0; r < 2; ++r) {
+					if (r == 0 ? !has_a : !has_b) continue;
+					const float4 tt = r == 0 ? tp : tq;
+					const float px = r == 0 ? acc[0] : acc[3], py = r == 0 ? acc[1] : acc[4], pz = r == 0 ? acc[2] : acc[5];
+					float fx, fy, fz;
+					E::l2p(l, tt.x - g.x, tt.y - g.y, tt.z - g.z, fx, fy, fz);
+					const uint32_t i = b + t0 + t + (r ? T : 0u);
+					const float4 vm = a.velm_in[i];
+					const float sc = a.G * tt.w / vm.w;  // a = G q/m * field (src/force.cl:4-10, src/open_cl_simulation.cpp:602-604)
+					const float axx = sc * (px + fx), ayy = sc * (py + fy), azz = sc * (pz + fz);
+					a.acc[i] = make_float4(axx, ayy, azz, 0.f);
+					if (!a.no_integrate) {
+						const float vx = fmaf(axx, a.dt, vm.x), vy = fmaf(ayy, a.dt, vm.y), vz = fmaf(azz, a.dt, vm.z);
+						const bool kd = a.integrator == NBODY_KICK_DRIFT;
+						a.posq_out[i] = make_float4(fmaf(kd ? vx : vm.x, a.dt, tt.x), fmaf(kd ? vy : vm.y, a.dt, tt.y), fmaf(kd ? vz : vm.z, a.dt, tt.z), tt.w);
+						a.velm_out[i] = make_float4(vx, vy, vz, vm.w);
+					} else {
+						a.posq_out[i] = tt;
+						a.velm_out[i] = vm;
+					}
 				}
 			}
 		}
@@ -245,17 +278,24 @@ void launch_leaf(Sim& s) {
 // through a double-buffered shared-memory tile.
 // ---------------------------------------------------------------------------
 constexpr int kDirThreads = 256;
-constexpr int kDirTile = 512;
+constexpr int kDirTile = 1024;
+constexpr int kDirTargets = 4;  // targets per thread: one LDS.128 feeds 4 interactions
 
 template <bool SOFT>
 __global__ void __launch_bounds__(kDirThreads) k_direct(const float4* __restrict__ src, uint64_t n_src, const float4* __restrict__ tgt,
                                                         uint64_t n_tgt, float eps2, float4* __restrict__ out) {
 	__shared__ float4 tile[kDirTile];
-	const uint64_t i0 = (uint64_t) blockIdx.x * (2 * kDirThreads) + threadIdx.x, i1 = i0 + kDirThreads;
-	float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0;
-	if (i0 < n_tgt) p0 = tgt[i0];
-	if (i1 < n_tgt) p1 = tgt[i1];
-	float ax0 = 0.f, ay0 = 0.f, az0 = 0.f, ax1 = 0.f, ay1 = 0.f, az1 = 0.f;
+	const uint64_t i0 = (uint64_t) blockIdx.x * (kDirTargets * kDirThreads) + threadIdx.x;
+	float tx[kDirTargets], ty[kDirTargets], tz[kDirTargets], ax[kDirTargets], ay[kDirTargets], az[kDirTargets];
+	// running totals with Kahan compensation across tiles: a plain FP32 sum over 10^7 sources loses ~1e-2
+	float sx[kDirTargets], sy[kDirTargets], sz[kDirTargets], cx[kDirTargets], cy[kDirTargets], cz[kDirTargets];
+#pragma unroll
+	for (int t = 0; t < kDirTargets; ++t) {
+		const uint64_t i = i0 + (uint64_t) t * kDirThreads;
+		const float4 p = i < n_tgt ? tgt[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+		tx[t] = p.x; ty[t] = p.y; tz[t] = p.z; ax[t] = ay[t] = az[t] = 0.f;
+		sx[t] = sy[t] = sz[t] = cx[t] = cy[t] = cz[t] = 0.f;
+	}
 	for (uint64_t base = 0; base < n_src; base += kDirTile) {
 		__syncthreads();
 		for (int q = threadIdx.x; q < kDirTile; q += kDirThreads) {
@@ -263,19 +303,29 @@ __global__ void __launch_bounds__(kDirThreads) k_direct(const float4* __restrict
 			tile[q] = j < n_src ? src[j] : make_float4(0.f, 0.f, 0.f, 0.f);  // q = 0 padding exerts no force
 		}
 		__syncthreads();
-#pragma unroll 8
+#pragma unroll 4
 		for (int q = 0; q < kDirTile; ++q) {
 			const float4 s = tile[q];
-			p2p_interact<SOFT>(s, p0.x, p0.y, p0.z, eps2, ax0, ay0, az0);
-			p2p_interact<SOFT>(s, p1.x, p1.y, p1.z, eps2, ax1, ay1, az1);
+#pragma unroll
+			for (int t = 0; t < kDirTargets; ++t) p2p_interact<SOFT>(s, tx[t], ty[t], tz[t], eps2, ax[t], ay[t], az[t]);
+		}
+#pragma unroll
+		for (int t = 0; t < kDirTargets; ++t) {  // fold the tile's partial sum into the compensated total
+			float y, u;
+			y = __fsub_rn(ax[t], cx[t]); u = __fadd_rn(sx[t], y); cx[t] = __fsub_rn(__fsub_rn(u, sx[t]), y); sx[t] = u; ax[t] = 0.f;
+			y = __fsub_rn(ay[t], cy[t]); u = __fadd_rn(sy[t], y); cy[t] = __fsub_rn(__fsub_rn(u, sy[t]), y); sy[t] = u; ay[t] = 0.f;
+			y = __fsub_rn(az[t], cz[t]); u = __fadd_rn(sz[t], y); cz[t] = __fsub_rn(__fsub_rn(u, sz[t]), y); sz[t] = u; az[t] = 0.f;
 		}
 	}
-	if (i0 < n_tgt) out[i0] = make_float4(ax0, ay0, az0, 0.f);
-	if (i1 < n_tgt) out[i1] = make_float4(ax1, ay1, az1, 0.f);
+#pragma unroll
+	for (int t = 0; t < kDirTargets; ++t) {
+		const uint64_t i = i0 + (uint64_t) t * kDirThreads;
+		if (i < n_tgt) out[i] = make_float4(sx[t], sy[t], sz[t], 0.f);
+	}
 }
 
 int direct_field_device(const float4* src, uint64_t n_src, const float4* tgt, uint64_t n_tgt, float eps2, float4* out, cudaStream_t st) {
-	const unsigned grid = (unsigned) ((n_tgt + 2 * kDirThreads - 1) / (2 * kDirThreads));
+	const unsigned grid = (unsigned) ((n_tgt + kDirTargets * kDirThreads - 1) / (kDirTargets * kDirThreads));
 	if (grid == 0) return NBODY_OK;
 	if (eps2 > 0.0f) k_direct<true><<<grid, kDirThreads, 0, st>>>(src, n_src, tgt, n_tgt, eps2, out);
 	else k_direct<false><<<grid, kDirThreads, 0, st>>>(src, n_src, tgt, n_tgt, eps2, out);
