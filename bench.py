@@ -46,6 +46,21 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0, "source": "fallback (B200_PROFILING.md)"}
 
 
+def measured_traffic(kernel, args):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full
+    capture of exactly this workload (profiles/r01h_traffic.json); None for any other workload."""
+    p = os.path.join(ROOT, "profiles", "r01h_traffic.json")
+    try:
+        with open(p) as f:
+            d = json.load(f)
+        w = d["workload"]
+        if (w["kind"], w["n"], w["order"], w["leaf_capacity"]) == (args.workload, args.n, args.order, args.leaf_capacity) and args.gpus == 1:
+            return d["dram_bytes_per_launch"].get(kernel)
+    except Exception:
+        pass
+    return None
+
+
 def fp32_peak_tflops(sm_mhz):
     return N_SM * 128 * 2 * sm_mhz * 1e6 / 1e12
 
@@ -305,7 +320,8 @@ def main():
         roof = {
             "bound": "fp32", "kernel": "k_m2l (M2L, both launches)" if dominant == "m2l" else "k_leaf (P2P+L2P+integrate)",
             "achieved": m2l_tf if dominant == "m2l" else p2p_tf, "peak": peak, "unit": "TFLOP/s",
-            "frac": (m2l_tf if dominant == "m2l" else p2p_tf) / peak, "traffic": None,
+            "frac": (m2l_tf if dominant == "m2l" else p2p_tf) / peak,
+            "traffic": measured_traffic("k_m2l" if dominant == "m2l" else "k_leaf", args),
             "peak_source": f"148 SM x 128 lanes x 2 x {peaks['sm_max_mhz']} MHz ({peaks['source']}; FP32 FMA peak, derived)",
             "algorithmic_flops_per_unit": (f"{m2l_flops} per order-{args.order} M2L, {m2l_flops_lo} per order-{args.order - 1} M2L "
                                            f"({n_lo} of {counts['m2l_interactions']} run at the lower order)") if dominant == "m2l" else 20,
