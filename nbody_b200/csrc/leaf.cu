@@ -116,7 +116,9 @@ __global__ void __launch_bounds__(kLeafWarps * 32) k_leaf(const LeafArgs a) {
 			// Warp layout: T target lanes x S source slices, one or two targets per lane, whichever wastes fewer
 			// lanes: T = ntc (or ceil(ntc/2) with two targets per lane), S = floor(32 / T); lanes >= T*S stay idle.
 			const unsigned T1 = ntc, S1 = 32u / T1, T2 = (ntc + 1u) / 2u, S2 = 32u / T2;
-			const bool two = ntc * S2 > 2u * ntc * S1;  // useful fraction ntc*S2/64 against ntc*S1/32
+			// estimated issue slots per useful interaction: 17 / (ntc*S1/32) with one target per lane, 15 / (ntc*S2/64) with
+			// two (one LDS.128 and one loop step feed two interactions): two targets per lane when 544*S2 > 960*S1
+			const bool two = 544u * S2 > 960u * S1;
 			const unsigned T = two ? T2 : T1, S = two ? S2 : S1;
 			const unsigned sl_raw = lane / T, t = lane - sl_raw * T;
 			const bool lane_on = lane < T * S;
