@@ -16,6 +16,7 @@ void comm_destroy(Sim& s);                          // comm.cu
 int comm_partition(Sim& s);                         // comm.cu
 int comm_exchange_aos(Sim& s);                      // comm.cu
 int comm_exchange_acc(Sim& s);                      // comm.cu
+void comm_adopt_partition(Sim& s);                  // comm.cu
 
 namespace {
 
@@ -143,11 +144,19 @@ int run_pipeline(Sim& s) {
 		launch_direct(s);
 	}
 	NB_CUDA_CHECK(cudaEventRecord(s.ev[7], st));
-	if (s.comm && (rc = comm_step_exchange(s))) return rc;
-	NB_CUDA_CHECK(cudaEventRecord(s.ev[8], st));
 	NB_CUDA_CHECK(cudaMemcpyAsync(s.ctrl_host, s.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
-	NB_CUDA_CHECK(cudaStreamSynchronize(st));
+	NB_CUDA_CHECK(cudaStreamSynchronize(st));  // the one synchronisation of a step
 	NB_CUDA_CHECK(cudaGetLastError());
+	if (s.comm && s.ctrl_host->status == 0) {
+		// distributed: the slice boundaries were computed on the device; now that the host has them, exchange the slices
+		comm_adopt_partition(s);
+		if ((rc = comm_step_exchange(s))) return rc;
+		NB_CUDA_CHECK(cudaEventRecord(s.ev[8], st));
+		NB_CUDA_CHECK(cudaStreamSynchronize(st));
+	} else {
+		NB_CUDA_CHECK(cudaEventRecord(s.ev[8], st));
+		NB_CUDA_CHECK(cudaEventSynchronize(s.ev[8]));
+	}
 	return NBODY_OK;
 }
 

@@ -98,14 +98,20 @@ __global__ void k_partition(Ctrl* c, int world, uint32_t n, const uint2* __restr
 	c->part[r] = nbegin[node];
 }
 
+// Enqueues the partition kernel; the kernels of the step read the boundaries from the control block on the device.
 int comm_partition(Sim& s) {
 	Comm& cm = *s.comm;
 	k_partition<<<1, 32, 0, s.stream>>>(s.ctrl, cm.world, (uint32_t) s.n, s.info, s.nbegin);
-	NB_CUDA_CHECK(cudaMemcpyAsync(cm.part_host, s.ctrl->part, sizeof(uint32_t) * (cm.world + 1), cudaMemcpyDeviceToHost, s.stream));
-	NB_CUDA_CHECK(cudaStreamSynchronize(s.stream));  // the one host round trip of a distributed step: 4*(world+1) bytes
+	return NBODY_OK;
+}
+
+// After the step's single synchronisation: the host learns the slice boundaries (they arrive with the control block)
+// and uses them for the exchange.
+void comm_adopt_partition(Sim& s) {
+	Comm& cm = *s.comm;
+	for (int r = 0; r <= cm.world; ++r) cm.part_host[r] = s.ctrl_host->part[r];
 	s.own_first = cm.part_host[cm.rank];
 	s.own_count = cm.part_host[cm.rank + 1] - cm.part_host[cm.rank];
-	return NBODY_OK;
 }
 
 static int exchange(Sim& s, void* buf, size_t elem_bytes) {
@@ -178,6 +184,7 @@ int nbody_cuda_create_distributed(const nbody_cuda_config* cfg, const nbody_part
 	s->comm = new Comm;
 	Comm& cm = *s->comm;
 	cm.rank = rank; cm.world = world;
+	s->rank = rank;
 	if (cudaMallocHost((void**) &cm.part_host, sizeof(uint32_t) * (world + 1)) != cudaSuccess) { set_error("pinned allocation failed"); return fail(NBODY_ERR_CUDA); }
 	ncclUniqueId u;
 	std::memcpy(&u, id, 128);

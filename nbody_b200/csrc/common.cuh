@@ -113,6 +113,7 @@ struct Sim {
 	Comm* comm = nullptr;
 	// distributed: this rank's slice of the tree-ordered particle array
 	uint64_t own_first = 0, own_count = 0;
+	int rank = 0;                // index into Ctrl::part (0 on a single GPU)
 
 	nbody_cuda_stats stats{};
 	cudaEvent_t ev[12] = {};

@@ -57,7 +57,7 @@ struct LeafArgs {
 	const float* L;
 	float eps2, G, dt;
 	int integrator, no_integrate;
-	uint32_t own_first, own_end;  // this rank's slice of the tree-ordered particle array
+	int rank;                     // this rank's slice of the tree-ordered particle array: [c->part[rank], c->part[rank+1])
 	uint32_t batch_entries;       // source leaves staged per tile (batch_entries * quota <= kLeafTile)
 	unsigned long long* stat_inter;
 	unsigned long long* stat_leaves;
@@ -100,6 +100,7 @@ __global__ void __launch_bounds__(kLeafWarps * 32) k_leaf(const LeafArgs a) {
 	const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
 	if (a.c->status) return;  // a pool overflowed: the host grows it and re-runs the step; leave the state untouched
 	const uint32_t n_nodes = a.c->n_nodes;
+	const uint32_t own_first = a.c->part[a.rank], own_end = a.c->part[a.rank + 1];
 	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
 	const uint32_t EB = a.batch_entries, quota = kLeafTile / EB;
 	unsigned long long inter = 0, leaves = 0;
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(kLeafWarps * 32) k_leaf(const LeafArgs a) {
 		const uint2 nf = a.info[node];
 		if (nf.x != 0u || nf.y == 0u) continue;  // internal or empty
 		const uint32_t b = a.nbegin[node];
-		if (b < a.own_first || b >= a.own_end) continue;  // another rank's leaf
+		if (b < own_first || b >= own_end) continue;  // another rank's leaf
 		++leaves;
 		const uint32_t nt = nf.y;
 		const float4 g = a.geom[node];
@@ -261,7 +262,7 @@ void launch_leaf(Sim& s) {
 	a.geom = s.geom; a.info = s.info; a.nbegin = s.nbegin; a.p2p_head = s.p2p_head; a.seg = s.pools.seg; a.p2p = s.pools.p2p; a.L = s.L;
 	a.eps2 = s.cfg.softening * s.cfg.softening; a.G = s.cfg.force_constant; a.dt = s.cfg.time_step;
 	a.integrator = (int) s.cfg.integrator; a.no_integrate = (s.cfg.flags & NBODY_FLAG_NO_INTEGRATE) ? 1 : 0;
-	a.own_first = (uint32_t) s.own_first; a.own_end = (uint32_t) (s.own_first + s.own_count);
+	a.rank = s.rank;
 	{  // batch_entries * leaf_capacity <= kLeafTile, at most one entry per lane
 		uint32_t eb = kLeafTile / (s.cfg.leaf_capacity ? s.cfg.leaf_capacity : 1u);
 		a.batch_entries = eb < 1u ? 1u : (eb > 32u ? 32u : eb);

@@ -218,10 +218,11 @@ k_m2l(Ctrl* __restrict__ c, const Group* __restrict__ items, uint32_t items_cap,
 template <int P>
 __global__ void __launch_bounds__(128) k_l2l(const Ctrl* __restrict__ c, int l, const float4* __restrict__ geom,
                                              const uint2* __restrict__ info, const uint32_t* __restrict__ nparent,
-                                             const uint32_t* __restrict__ nbegin, uint32_t own_first, uint32_t own_end, float* __restrict__ L) {
+                                             const uint32_t* __restrict__ nbegin, int rank, float* __restrict__ L) {
 	using E = Expansion<P>;
 	constexpr int STRIDE = coef_stride(P);
 	const uint32_t lo = c->level_off[l], hi = c->level_off[l + 1];
+	const uint32_t own_first = c->part[rank], own_end = c->part[rank + 1];
 	for (uint32_t node = lo + blockIdx.x * blockDim.x + threadIdx.x; node < hi; node += gridDim.x * blockDim.x) {
 		const uint32_t cnt = info[node].y;
 		if (cnt == 0u) continue;
@@ -261,8 +262,7 @@ static void m2l_t(Sim& s) {
 template <int P>
 static void l2l_t(Sim& s) {
 	for (int l = 1; l <= (int) s.cfg.max_depth; ++l)
-		k_l2l<P><<<kNumSM * 4, 128, 0, s.stream>>>(s.ctrl, l, s.geom, s.info, s.nparent, s.nbegin, (uint32_t) s.own_first,
-		                                          (uint32_t) (s.own_first + s.own_count), s.L);
+		k_l2l<P><<<kNumSM * 4, 128, 0, s.stream>>>(s.ctrl, l, s.geom, s.info, s.nparent, s.nbegin, s.rank, s.L);
 }
 
 void launch_m2l(Sim& s) {

@@ -86,7 +86,7 @@ struct TraverseArgs {
 	const float4* geom;
 	const uint2* info;
 	const uint32_t* nbegin;
-	uint32_t own_first, own_end;   // this rank's slice of the tree-ordered particle array (everything on one GPU)
+	int rank;                      // this rank's slice of the tree-ordered particle array is [c->part[rank], c->part[rank+1])
 	uint2* near_ref;
 	uint32_t* p2p_head;
 	const uint32_t* near_in;
@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(kTravThreads) k_traverse(const TraverseArgs a)
 	const unsigned lt_mask = (1u << lane) - 1u;
 	const uint32_t n_groups = min(c->gq_count[a.round & 1], a.gq_cap);
 	const int out = a.round & 1;
+	const uint32_t own_first = c->part[a.rank], own_end = c->part[a.rank + 1];
 	for (;;) {
 		__syncthreads();
 		if (tid == 0) S.item = atomicAdd(&c->work_ticket[2], 1u);
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(kTravThreads) k_traverse(const TraverseArgs a)
 		const uint2 ti = a.info[G.first + my_t];
 		const uint32_t tb = a.nbegin[G.first + my_t];
 		// a target is active when it holds particles of this rank's Morton range
-		const bool t_act = ti.y > 0 && tb < a.own_end && tb + ti.y > a.own_first, t_ch = ti.x != 0;
+		const bool t_act = ti.y > 0 && tb < own_end && tb + ti.y > own_first, t_ch = ti.x != 0;
 		if (tid < 40) { S.total[tid >> 3][tid & 7] = 0; }
 		const uint32_t nchunks = (G.list_cnt + kTravEntries - 1) / kTravEntries;
 		for (int pass = 0; pass < 2; ++pass) {
@@ -357,7 +358,7 @@ void launch_traversal(Sim& s) {
 	k_traverse_init<<<1, 32, 0, s.stream>>>(s.ctrl, s.info, p.near[0], p.gq[1]);
 	TraverseArgs a{};
 	a.c = s.ctrl; a.geom = s.geom; a.info = s.info; a.near_ref = s.near_ref; a.p2p_head = s.p2p_head;
-	a.nbegin = s.nbegin; a.own_first = (uint32_t) s.own_first; a.own_end = (uint32_t) (s.own_first + s.own_count);
+	a.nbegin = s.nbegin; a.rank = s.rank;
 	a.near_cap = p.near_cap; a.p2p = p.p2p; a.p2p_cap = p.p2p_cap; a.m2l_id = p.m2l_id; a.m2l_mask = p.m2l_mask; a.m2l_mask_lo = p.m2l_mask_lo; a.m2l_cap = p.m2l_cap;
 	a.seg = p.seg; a.seg_cap = p.seg_cap; a.gq_cap = p.gq_cap; a.items8 = p.items[0]; a.items1 = p.items[1]; a.items_cap = p.items_cap;
 	a.ratio_sq = s.cfg.mac_ratio * s.cfg.mac_ratio;
