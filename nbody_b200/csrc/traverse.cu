@@ -222,29 +222,37 @@ __global__ void __launch_bounds__(kTravThreads) k_traverse(const TraverseArgs a)
 						S.cflag[s] = (uint8_t) ((ci.y > 0 ? 1u : 0u) | (ci.x ? 2u : 0u));
 					}
 					if (tid < 40) S.chunk_cnt[tid >> 3][tid & 7] = 0;
+					if (tid < 32 && ncand + tid < kTravCand) S.cflag[ncand + tid] = 0;  // the tail of the last batch: flag 0 = not a candidate
 					__syncthreads();
-					// ---- B. classify: (target, batch) pairs round-robin over the warps ----
+					// ---- B. classify: (target, batch) pairs round-robin over the warps; branch-free inside the loop ----
+					// (slots past ncand carry flag 0, the MAC is evaluated unconditionally and masked, counters stay in
+					//  registers and reach shared memory once per warp)
 					const uint32_t nb = (ncand + 31) / 32;
-					for (uint32_t q = w; q < nt * nb; q += 8) {
-						const uint32_t t = nt == 8 ? w : 0u, b = nt == 8 ? q >> 3 : q;
-						const uint32_t s = 32 * b + lane;
-						unsigned code = 0;
-						if (s < ncand && t_act) {
+					uint32_t c_lo = 0, c_nc = 0;
+					const uint32_t tgt_id = G.first + (nt == 8 ? w : 0u);
+					const uint32_t trow = nt == 8 ? w : 0u;
+					if (t_act) {
+						for (uint32_t q = w; q < nt * nb; q += 8) {
+							const uint32_t b = nt == 8 ? q >> 3 : q;
+							const uint32_t s = 32 * b + lane;
 							const unsigned fl = S.cflag[s];
-							if (fl & 1u) {
-								const bool same = S.cid[s] == G.first + t;
-								const unsigned cls = same ? 0u : mac_classify<QUARTER>(tg.x, tg.y, tg.z, tg.w, S.cgeom[s], a.ratio_sq, a.tau);
-								code = cls ? (cls == 2u ? 4u : 1u) : ((t_ch || (fl & 2u)) ? 2u : 3u);
-							}
+							const unsigned cls = mac_classify<QUARTER>(tg.x, tg.y, tg.z, tg.w, S.cgeom[s], a.ratio_sq, a.tau);
+							const bool valid = (fl & 1u) != 0;
+							const bool accept = valid && cls != 0u && S.cid[s] != tgt_id;
+							const bool rest = valid && !accept;
+							const bool nearb = rest && (t_ch || (fl & 2u));
+							const unsigned m_acc = __ballot_sync(0xffffffffu, accept), m_lo = __ballot_sync(0xffffffffu, accept && cls == 2u);
+							const unsigned m_near = __ballot_sync(0xffffffffu, nearb), m_p2p = __ballot_sync(0xffffffffu, rest && !nearb);
+							const unsigned m_ch = __ballot_sync(0xffffffffu, nearb && (fl & 2u));
+							c_lo += __popc(m_lo);
+							c_nc += 8u * __popc(m_ch) + __popc(m_near & ~m_ch);
+							if (lane == 0) { S.bal[0][trow][b] = m_acc; S.bal[1][trow][b] = m_near; S.bal[2][trow][b] = m_p2p; S.bal[3][trow][b] = m_lo; }
 						}
-						const unsigned m_lo = __ballot_sync(0xffffffffu, code == 4u);
-						const unsigned m_acc = __ballot_sync(0xffffffffu, code == 1u) | m_lo, m_near = __ballot_sync(0xffffffffu, code == 2u),
-						               m_p2p = __ballot_sync(0xffffffffu, code == 3u);
-						const unsigned m_ch = __ballot_sync(0xffffffffu, code == 2u && (S.cflag[s < ncand ? s : 0] & 2u));
-						if (lane == 0) {
-							S.bal[0][t][b] = m_acc; S.bal[1][t][b] = m_near; S.bal[2][t][b] = m_p2p; S.bal[3][t][b] = m_lo;
-							if (m_lo) atomicAdd(&S.chunk_cnt[4][t], (uint32_t) __popc(m_lo));
-							if (m_near) atomicAdd(&S.chunk_cnt[3][t], 8u * __popc(m_ch) + __popc(m_near & ~m_ch));
+						if (lane == 0 && (c_lo | c_nc)) { atomicAdd(&S.chunk_cnt[4][trow], c_lo); atomicAdd(&S.chunk_cnt[3][trow], c_nc); }
+					} else {
+						for (uint32_t q = w; q < nt * nb; q += 8) {  // an empty / foreign target: all-zero ballot rows
+							const uint32_t b = nt == 8 ? q >> 3 : q;
+							if (lane < 4) S.bal[lane][trow][b] = 0u;
 						}
 					}
 					__syncthreads();
