@@ -14,7 +14,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnbody_cuda.so")
+LIB_PATH = os.environ.get("NBODY_CUDA_LIB") or os.path.join(_HERE, "libnbody_cuda.so")  # override: an experimental build of the same library
 PARTICLE_FLOATS = 12  # 48-byte AoS record: position[4], velocity[4], mass, charge, pad[2]
 
 KICK_DRIFT, EXPLICIT_EULER = 0, 1

@@ -12,12 +12,19 @@
 // Field of source j on target i: q_j (x_j - x_i) / (|x_j - x_i|^2 + eps^2)^(3/2)
 // (src/field.cl:17-32 with FORCE_CONSTANT folded into force_constant).
 // 20 flop per evaluation by the SURVEY 8d convention: 3 FADD, 3 FFMA, MUFU.RSQ (2), 3 FMUL, 3 FFMA.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace nbody {
 
 constexpr int kLeafWarps = 4;
 constexpr int kLeafTile = 256;  // source particles per tile; two tiles (8 KB) per warp
+constexpr int kLeafChunk = 8;   // node ids per work ticket
+#ifndef NBODY_LEAF_MIN_CTAS
+#define NBODY_LEAF_MIN_CTAS 5
+#endif
+constexpr int kLeafMinCtas = NBODY_LEAF_MIN_CTAS;  // resident CTAs per SM the register allocation is held to
 
 __device__ __forceinline__ void leaf_cp_async16(void* smem, const void* gmem) {
 	const unsigned sa = (unsigned) __cvta_generic_to_shared(smem);
@@ -42,7 +49,7 @@ __device__ __forceinline__ void p2p_interact(const float4& s, float tx, float ty
 }
 
 struct LeafArgs {
-	const Ctrl* c;
+	Ctrl* c;
 	const float4* posq;      // sorted positions of this step (sources and targets)
 	const float4* velm_in;   // sorted velocities
 	float4* posq_out;        // new state
@@ -58,190 +65,242 @@ struct LeafArgs {
 	float eps2, G, dt;
 	int integrator, no_integrate;
 	int rank;                     // this rank's slice of the tree-ordered particle array: [c->part[rank], c->part[rank+1])
-	uint32_t batch_entries;       // source leaves staged per tile (batch_entries * quota <= kLeafTile)
+	uint32_t cost_ovh;            // warp layout choice: issue slots per source step that do not scale with the targets per lane (LDS, loop)
+	uint32_t max_tpl;             // most targets per lane the layout may use (1, 2 or 4)
 	unsigned long long* stat_inter;
 	unsigned long long* stat_leaves;
 };
 
-// Every lane walks its slice of the tile (sources sl, sl+S, ...) for one target, or two when TWO.
-template <bool SOFT, bool TWO>
-__device__ __forceinline__ void tile_compute(const float4* buf, uint32_t fill, unsigned sl, unsigned S, const float4& ta, const float4& tb,
-                                             float eps2, float (&acc)[6]) {
+// Every lane walks its slice of the tile (sources sl, sl+S, ...) for TPL targets held in registers:
+// one LDS.128 and one loop step feed TPL interactions. U sources are in flight per iteration.
+template <bool SOFT, int TPL, int U>
+__device__ __forceinline__ void tile_compute(const float4* buf, uint32_t fill, unsigned sl, unsigned S, const float (&tx)[4], const float (&ty)[4],
+                                             const float (&tz)[4], float eps2, float (&ax)[4], float (&ay)[4], float (&az)[4]) {
 	__syncwarp();
 	uint32_t j = sl;
-	for (; j + 3 * S < fill; j += 4 * S) {
-		const float4 s0 = buf[j], s1 = buf[j + S], s2 = buf[j + 2 * S], s3 = buf[j + 3 * S];
-		p2p_interact<SOFT>(s0, ta.x, ta.y, ta.z, eps2, acc[0], acc[1], acc[2]);
-		if (TWO) p2p_interact<SOFT>(s0, tb.x, tb.y, tb.z, eps2, acc[3], acc[4], acc[5]);
-		p2p_interact<SOFT>(s1, ta.x, ta.y, ta.z, eps2, acc[0], acc[1], acc[2]);
-		if (TWO) p2p_interact<SOFT>(s1, tb.x, tb.y, tb.z, eps2, acc[3], acc[4], acc[5]);
-		p2p_interact<SOFT>(s2, ta.x, ta.y, ta.z, eps2, acc[0], acc[1], acc[2]);
-		if (TWO) p2p_interact<SOFT>(s2, tb.x, tb.y, tb.z, eps2, acc[3], acc[4], acc[5]);
-		p2p_interact<SOFT>(s3, ta.x, ta.y, ta.z, eps2, acc[0], acc[1], acc[2]);
-		if (TWO) p2p_interact<SOFT>(s3, tb.x, tb.y, tb.z, eps2, acc[3], acc[4], acc[5]);
+	for (; j + (U - 1) * S < fill; j += U * S) {
+		float4 s[U];
+#pragma unroll
+		for (int u = 0; u < U; ++u) s[u] = buf[j + u * S];
+#pragma unroll
+		for (int u = 0; u < U; ++u) {
+#pragma unroll
+			for (int r = 0; r < TPL; ++r) p2p_interact<SOFT>(s[u], tx[r], ty[r], tz[r], eps2, ax[r], ay[r], az[r]);
+		}
 	}
 	for (; j < fill; j += S) {
 		const float4 s0 = buf[j];
-		p2p_interact<SOFT>(s0, ta.x, ta.y, ta.z, eps2, acc[0], acc[1], acc[2]);
-		if (TWO) p2p_interact<SOFT>(s0, tb.x, tb.y, tb.z, eps2, acc[3], acc[4], acc[5]);
+#pragma unroll
+		for (int r = 0; r < TPL; ++r) p2p_interact<SOFT>(s0, tx[r], ty[r], tz[r], eps2, ax[r], ay[r], az[r]);
 	}
 	__syncwarp();
 }
 
-// One warp per target leaf. Its source list is a chain of segments of {first particle, count} entries;
-// batches of `batch_entries` source leaves are expanded into a shared-memory tile with cp.async while the
-// previous tile is being evaluated (two tiles per warp), and the entries of the batch after that are already
-// in registers — so neither the list walk nor the particle fetch sits on the critical path.
+template <bool SOFT>
+__device__ __forceinline__ void tile_dispatch(unsigned tpl, const float4* buf, uint32_t fill, unsigned sl, unsigned S, const float (&tx)[4],
+                                              const float (&ty)[4], const float (&tz)[4], float eps2, float (&ax)[4], float (&ay)[4], float (&az)[4]) {
+	if (tpl == 4u) tile_compute<SOFT, 4, 2>(buf, fill, sl, S, tx, ty, tz, eps2, ax, ay, az);
+	else if (tpl == 2u) tile_compute<SOFT, 2, 4>(buf, fill, sl, S, tx, ty, tz, eps2, ax, ay, az);
+	else tile_compute<SOFT, 1, 4>(buf, fill, sl, S, tx, ty, tz, eps2, ax, ay, az);
+}
+
+// One warp per target leaf; leaves are handed out kLeafChunk node ids at a time by an atomic ticket, so the grid is
+// exactly the resident set and no warp idles while another still has a queue. The leaf's source list is a chain of
+// segments of {first particle, count} entries. A batch is the longest run of entries (<= 32, one per lane) whose
+// particles fit one 256-particle tile; it is expanded with fully used 16-byte cp.async rows (the flat index -> entry
+// map is a bitmap of the entries' end positions, built with warp OR-reductions) while the previous tile is being
+// evaluated (two tiles per warp), and the entries of the batch after that are already in registers — so neither the
+// list walk nor the particle fetch sits on the critical path.
 template <int P, bool SOFT>
-__global__ void __launch_bounds__(kLeafWarps * 32) k_leaf(const LeafArgs a) {
+__global__ void __launch_bounds__(kLeafWarps * 32, kLeafMinCtas) k_leaf(const LeafArgs a) {
 	using E = Expansion<P>;
 	constexpr int STRIDE = coef_stride(P);
+	constexpr uint32_t END = 0xffffffffu;
 	__shared__ float4 sbuf[kLeafWarps][2][kLeafTile];
 	const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
 	if (a.c->status) return;  // a pool overflowed: the host grows it and re-runs the step; leave the state untouched
 	const uint32_t n_nodes = a.c->n_nodes;
 	const uint32_t own_first = a.c->part[a.rank], own_end = a.c->part[a.rank + 1];
-	const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-	const uint32_t EB = a.batch_entries, quota = kLeafTile / EB;
+	const unsigned le_mask = (2u << lane) - 1u;  // bits 0..lane
 	unsigned long long inter = 0, leaves = 0;
-	for (uint32_t node = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; node < n_nodes; node += warps) {
-		const uint2 nf = a.info[node];
-		if (nf.x != 0u || nf.y == 0u) continue;  // internal or empty
-		const uint32_t b = a.nbegin[node];
-		if (b < own_first || b >= own_end) continue;  // another rank's leaf
-		++leaves;
-		const uint32_t nt = nf.y;
-		const float4 g = a.geom[node];
-		for (uint32_t t0 = 0; t0 < nt; t0 += 32) {
-			const uint32_t ntc = min(32u, nt - t0);
-			// Warp layout: T target lanes x S source slices, one or two targets per lane, whichever wastes fewer
-			// lanes: T = ntc (or ceil(ntc/2) with two targets per lane), S = floor(32 / T); lanes >= T*S stay idle.
-			const unsigned T1 = ntc, S1 = 32u / T1, T2 = (ntc + 1u) / 2u, S2 = 32u / T2;
-			// estimated issue slots per useful interaction: 17 / (ntc*S1/32) with one target per lane, 15 / (ntc*S2/64) with
-			// two (one LDS.128 and one loop step feed two interactions): two targets per lane when 544*S2 > 960*S1
-			const bool two = 544u * S2 > 960u * S1;
-			const unsigned T = two ? T2 : T1, S = two ? S2 : S1;
-			const unsigned sl_raw = lane / T, t = lane - sl_raw * T;
-			const bool lane_on = lane < T * S;
-			const unsigned sl = lane_on ? sl_raw : (unsigned) kLeafTile;  // idle lanes: an empty slice
-			const bool has_a = lane_on && t < ntc, has_b = two && lane_on && t + T < ntc;
-			float4 tp = make_float4(0.f, 0.f, 0.f, 0.f), tq = tp;
-			if (has_a) tp = a.posq[b + t0 + t];
-			if (has_b) tq = a.posq[b + t0 + t + T];
-			float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-			unsigned long long nsrc = 0;
-			// ---- cursor over the segment chain ----
-			uint32_t si = a.p2p_head[node], e0 = 0;
-			Segment sg; sg.off = 0; sg.cnt = 0; sg.next = 0xffffffffu;
-			auto fetch = [&](uint2& ent) -> bool {  // next batch of <= EB entries, lane l holds entry l; warp-uniform result
-				while (e0 >= sg.cnt) {
-					if (si == 0xffffffffu) return false;
-					sg = a.seg[si]; si = sg.next; e0 = 0;
-				}
-				ent = make_uint2(0u, 0u);
-				if (lane < EB && e0 + lane < sg.cnt) ent = a.p2p[sg.off + e0 + lane];
-				e0 += EB;
-				return true;
-			};
-			auto stage = [&](const uint2& ent, float4* tile, uint32_t& fill, unsigned& big) {  // issue the tile fill of one batch
-				const bool bigl = ent.y > quota;  // an over-full source leaf (only at max depth): streamed separately
-				const uint32_t v = bigl ? 0u : ent.y;
-				uint32_t inc = v;
+	for (;;) {
+		uint32_t chunk = 0;
+		if (lane == 0) chunk = atomicAdd(&a.c->work_ticket[3], (uint32_t) kLeafChunk);
+		chunk = __shfl_sync(0xffffffffu, chunk, 0);
+		if (chunk >= n_nodes) break;
+		uint2 nf_l = make_uint2(1u, 0u);
+		uint32_t b_l = 0;
+		if (lane < (unsigned) kLeafChunk && chunk + lane < n_nodes) { nf_l = a.info[chunk + lane]; b_l = a.nbegin[chunk + lane]; }
+		// childless, non-empty, and inside this rank's slice
+		unsigned todo = __ballot_sync(0xffffffffu, nf_l.x == 0u && nf_l.y != 0u && b_l >= own_first && b_l < own_end);
+		while (todo) {
+			const int kk = __ffs(todo) - 1;
+			todo &= todo - 1u;
+			const uint32_t node = chunk + kk;
+			const uint32_t nt = __shfl_sync(0xffffffffu, nf_l.y, kk), b = __shfl_sync(0xffffffffu, b_l, kk);
+			++leaves;
+			const float4 g = a.geom[node];
+			for (uint32_t t0 = 0; t0 < nt; t0 += 32) {
+				const uint32_t ntc = min(32u, nt - t0);
+				// Warp layout: T target lanes x S source slices with TPL targets per lane (T = ceil(ntc/TPL), S = floor(32/T),
+				// lanes >= T*S idle). One source step costs (cost_ovh + 13 TPL) issue slots and yields S*ntc useful interactions.
+				unsigned TPL = 1u, T = ntc, S = 32u / ntc;
+				{
+					uint32_t best = ((a.cost_ovh + 13u) << 12) / (S * ntc);
 #pragma unroll
-				for (int d = 1; d < 32; d <<= 1) {
-					const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d);
-					if (lane >= (unsigned) d) inc += u;
-				}
-				fill = __shfl_sync(0xffffffffu, inc, 31);
-				big = __ballot_sync(0xffffffffu, bigl);
-				const uint32_t dst = inc - v, maxc = __reduce_max_sync(0xffffffffu, v);
-				for (uint32_t k = 0; k < maxc; ++k)
-					if (k < v) leaf_cp_async16(tile + dst + k, a.posq + ent.x + k);
-				leaf_cp_async_commit();
-			};
-			uint2 ent_cur = make_uint2(0u, 0u), ent_nxt = make_uint2(0u, 0u);
-			uint32_t fill_cur = 0;
-			unsigned big_cur = 0;
-			int cur = 0;
-			bool has_cur = fetch(ent_cur);
-			if (has_cur) stage(ent_cur, sbuf[w][0], fill_cur, big_cur);
-			bool has_nxt = has_cur && fetch(ent_nxt);
-			while (has_cur) {
-				uint32_t fill_nxt = 0;
-				unsigned big_nxt = 0;
-				if (has_nxt) stage(ent_nxt, sbuf[w][cur ^ 1], fill_nxt, big_nxt);
-				else leaf_cp_async_commit();  // empty group keeps the wait_group arithmetic uniform
-				uint2 ent_nn = make_uint2(0u, 0u);
-				const bool has_nn = has_nxt && fetch(ent_nn);  // entries of the batch after next: in flight during the math
-				leaf_cp_async_wait1();
-				if (two) tile_compute<SOFT, true>(sbuf[w][cur], fill_cur, sl, S, tp, tq, a.eps2, acc);
-				else tile_compute<SOFT, false>(sbuf[w][cur], fill_cur, sl, S, tp, tq, a.eps2, acc);
-				nsrc += fill_cur;
-				while (big_cur) {  // stream an over-full source leaf through the tile that has just been consumed
-					const int first = __ffs(big_cur) - 1;
-					const uint32_t fb = __shfl_sync(0xffffffffu, ent_cur.x, first), fc = __shfl_sync(0xffffffffu, ent_cur.y, first);
-					for (uint32_t q0 = 0; q0 < fc; q0 += kLeafTile) {
-						const uint32_t m = min((uint32_t) kLeafTile, fc - q0);
-						for (uint32_t q = lane; q < m; q += 32) sbuf[w][cur][q] = a.posq[fb + q0 + q];
-						if (two) tile_compute<SOFT, true>(sbuf[w][cur], m, sl, S, tp, tq, a.eps2, acc);
-						else tile_compute<SOFT, false>(sbuf[w][cur], m, sl, S, tp, tq, a.eps2, acc);
+					for (unsigned tp = 2u; tp <= 4u; tp <<= 1) {
+						if (tp > a.max_tpl) break;
+						const unsigned Tt = (ntc + tp - 1u) / tp, St = 32u / Tt;
+						const uint32_t cost = ((a.cost_ovh + 13u * tp) << 12) / (St * ntc);
+						if (cost < best) { best = cost; TPL = tp; T = Tt; S = St; }
 					}
-					nsrc += fc;
-					big_cur &= big_cur - 1;
 				}
-				ent_cur = ent_nxt; fill_cur = fill_nxt; big_cur = big_nxt; has_cur = has_nxt;
-				ent_nxt = ent_nn; has_nxt = has_nn;
-				cur ^= 1;
-			}
-			leaf_cp_async_wait0();
-			// sum over the S slices into the lanes of slice 0 (lane t collects lanes t + s*T)
+				const unsigned sl_raw = lane / T, t = lane - sl_raw * T;
+				const bool lane_on = lane < T * S;
+				const unsigned sl = lane_on ? sl_raw : (unsigned) kLeafTile;  // idle lanes: an empty slice
+				float tx[4], ty[4], tz[4], ax[4], ay[4], az[4];
 #pragma unroll
-			for (int q = 0; q < 6; ++q) {
-				if (q >= 3 && !two) break;
-				float v = acc[q];
-				if ((T & (T - 1u)) == 0u) {  // T*S == 32: butterfly
-					for (unsigned d = T; d < 32u; d <<= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-				} else {
-					const float mine = lane_on ? v : 0.f;
-					float sum = mine;
-					for (unsigned sidx = 1; sidx < S; ++sidx) sum += __shfl_sync(0xffffffffu, mine, (lane + sidx * T) & 31u);
-					v = sum;
+				for (int r = 0; r < 4; ++r) {
+					tx[r] = ty[r] = tz[r] = ax[r] = ay[r] = az[r] = 0.f;
+					if ((unsigned) r < TPL && lane_on && t + r * T < ntc) {
+						const float4 p = a.posq[b + t0 + t + r * T];
+						tx[r] = p.x; ty[r] = p.y; tz[r] = p.z;
+					}
 				}
-				acc[q] = v;
-			}
-			if (lane == 0) inter += nsrc * ntc;
-			if (lane_on && sl_raw == 0) {
-				// far field: L2P of this leaf's local expansion, then the integrator — for each target of the lane
-				float l[E::NC];
-				const float4* L4 = reinterpret_cast<const float4*>(a.L + (size_t) node * STRIDE);
+				unsigned long long nsrc = 0;
+				// ---- cursor over the segment chain ----
+				uint32_t si = a.p2p_head[node], e0 = 0;
+				Segment sg; sg.off = 0; sg.cnt = 0; sg.next = END;
+				auto fetch = [&](uint2& ent) -> bool {  // the (up to) 32 entries at the cursor, lane l holds entry l; warp-uniform result
+					while (e0 >= sg.cnt) {
+						if (si == END) return false;
+						sg = a.seg[si]; si = sg.next; e0 = 0;
+					}
+					ent = make_uint2(0u, 0u);
+					if (e0 + lane < sg.cnt) ent = a.p2p[sg.off + e0 + lane];
+					return true;
+				};
+				// Consume the leading entries of `ent` that fit one tile and issue its fill. An over-full source leaf
+				// (more than a tile; only at max depth) forms a batch of its own and is streamed by the consumer.
+				auto stage = [&](const uint2& ent, float4* tile, uint32_t& fill, uint2& big) {
+					const uint32_t nvalid = min(32u, sg.cnt - e0);
+					const unsigned bigm = __ballot_sync(0xffffffffu, lane < nvalid && ent.y > (uint32_t) kLeafTile);
+					fill = 0; big = make_uint2(0u, 0u);
+					if (bigm & 1u) {
+						big = make_uint2(__shfl_sync(0xffffffffu, ent.x, 0), __shfl_sync(0xffffffffu, ent.y, 0));
+						e0 += 1u;
+						leaf_cp_async_commit();
+						return;
+					}
+					const uint32_t nlim = bigm ? (uint32_t) (__ffs(bigm) - 1) : nvalid;
+					uint32_t v = lane < nlim ? ent.y : 0u;
+					uint32_t inc = v;
 #pragma unroll
-				for (int q = 0; q < (E::NC + 3) / 4; ++q) {
-					const float4 v = L4[q];
-					l[4 * q] = v.x;
-					if (4 * q + 1 < E::NC) l[4 * q + 1] = v.y;
-					if (4 * q + 2 < E::NC) l[4 * q + 2] = v.z;
-					if (4 * q + 3 < E::NC) l[4 * q + 3] = v.w;
+					for (int d = 1; d < 32; d <<= 1) {
+						const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d);
+						if (lane >= (unsigned) d) inc += u;
+					}
+					const bool fits = lane < nlim && inc <= (uint32_t) kLeafTile;  // a prefix of the lanes: inc is monotone
+					const uint32_t nfit = __popc(__ballot_sync(0xffffffffu, fits));  // >= 1
+					fill = __shfl_sync(0xffffffffu, inc, (nfit - 1u) & 31u);
+					e0 += nfit;
+					const uint32_t src0 = ent.x - (inc - v);  // particle index of flat slot f inside entry l: src0 + f
+					uint32_t pc = 0;
+#pragma unroll
+					for (int i = 0; i < kLeafTile / 32; ++i) {
+						if (32u * i >= fill) break;
+						// bit p of the bitmap: some entry ends at flat position p; entry of slot f = number of ends <= f
+						const unsigned word = __reduce_or_sync(0xffffffffu, (fits && (inc >> 5) == (uint32_t) i) ? 1u << (inc & 31u) : 0u);
+						const uint32_t f = 32u * i + lane;
+						const uint32_t e = pc + __popc(word & le_mask);
+						const uint32_t s0 = __shfl_sync(0xffffffffu, src0, e & 31u);
+						if (f < fill) leaf_cp_async16(tile + f, a.posq + (s0 + f));
+						pc += __popc(word);
+					}
+					leaf_cp_async_commit();
+				};
+				uint2 ent_cur = make_uint2(0u, 0u), ent_nxt = make_uint2(0u, 0u), big_cur = make_uint2(0u, 0u);
+				uint32_t fill_cur = 0;
+				int cur = 0;
+				bool has_cur = fetch(ent_cur);
+				if (has_cur) stage(ent_cur, sbuf[w][0], fill_cur, big_cur);
+				bool has_nxt = has_cur && fetch(ent_nxt);
+				while (has_cur) {
+					uint32_t fill_nxt = 0;
+					uint2 big_nxt = make_uint2(0u, 0u);
+					if (has_nxt) stage(ent_nxt, sbuf[w][cur ^ 1], fill_nxt, big_nxt);
+					else leaf_cp_async_commit();  // empty group keeps the wait_group arithmetic uniform
+					uint2 ent_nn = make_uint2(0u, 0u);
+					const bool has_nn = has_nxt && fetch(ent_nn);  // entries of the batch after next: in flight during the math
+					leaf_cp_async_wait1();
+					tile_dispatch<SOFT>(TPL, sbuf[w][cur], fill_cur, sl, S, tx, ty, tz, a.eps2, ax, ay, az);
+					nsrc += fill_cur;
+					if (big_cur.y) {  // stream an over-full source leaf through the tile that has just been consumed
+						for (uint32_t q0 = 0; q0 < big_cur.y; q0 += kLeafTile) {
+							const uint32_t m = min((uint32_t) kLeafTile, big_cur.y - q0);
+							for (uint32_t q = lane; q < m; q += 32) sbuf[w][cur][q] = a.posq[big_cur.x + q0 + q];
+							tile_dispatch<SOFT>(TPL, sbuf[w][cur], m, sl, S, tx, ty, tz, a.eps2, ax, ay, az);
+						}
+						nsrc += big_cur.y;
+					}
+					ent_nxt = ent_nn; fill_cur = fill_nxt; big_cur = big_nxt; has_cur = has_nxt; has_nxt = has_nn;
+					cur ^= 1;
 				}
+				leaf_cp_async_wait0();
+				// sum over the S slices into the lanes of slice 0 (lane t collects lanes t + s*T)
+#pragma unroll
+				for (int r = 0; r < 4; ++r) {
+					if ((unsigned) r >= TPL) break;
+#pragma unroll
+					for (int q = 0; q < 3; ++q) {
+						float v = q == 0 ? ax[r] : q == 1 ? ay[r] : az[r];
+						if ((T & (T - 1u)) == 0u) {  // T*S == 32: butterfly
+							for (unsigned d = T; d < 32u; d <<= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+						} else {
+							const float mine = lane_on ? v : 0.f;
+							float sum = mine;
+							for (unsigned sidx = 1; sidx < S; ++sidx) sum += __shfl_sync(0xffffffffu, mine, (lane + sidx * T) & 31u);
+							v = sum;
+						}
+						if (q == 0) ax[r] = v; else if (q == 1) ay[r] = v; else az[r] = v;
+					}
+				}
+				if (lane == 0) inter += nsrc * ntc;
+				if (lane_on && sl_raw == 0) {
+					// far field: L2P of this leaf's local expansion, then the integrator — for each target of the lane
+					float l[E::NC];
+					const float4* L4 = reinterpret_cast<const float4*>(a.L + (size_t) node * STRIDE);
+#pragma unroll
+					for (int q = 0; q < (E::NC + 3) / 4; ++q) {
+						const float4 v = L4[q];
+						l[4 * q] = v.x;
+						if (4 * q + 1 < E::NC) l[4 * q + 1] = v.y;
+						if (4 * q + 2 < E::NC) l[4 * q + 2] = v.z;
+						if (4 * q + 3 < E::NC) l[4 * q + 3] = v.w;
+					}
 #pragma unroll 1
-				for (int r = 0; r < 2; ++r) {
-					if (r == 0 ? !has_a : !has_b) continue;
-					const float4 tt = r == 0 ? tp : tq;
-					const float px = r == 0 ? acc[0] : acc[3], py = r == 0 ? acc[1] : acc[4], pz = r == 0 ? acc[2] : acc[5];
-					float fx, fy, fz;
-					E::l2p(l, tt.x - g.x, tt.y - g.y, tt.z - g.z, fx, fy, fz);
-					const uint32_t i = b + t0 + t + (r ? T : 0u);
-					const float4 vm = a.velm_in[i];
-					const float sc = a.G * tt.w / vm.w;  // a = G q/m * field (src/force.cl:4-10, src/open_cl_simulation.cpp:602-604)
-					const float axx = sc * (px + fx), ayy = sc * (py + fy), azz = sc * (pz + fz);
-					a.acc[i] = make_float4(axx, ayy, azz, 0.f);
-					if (!a.no_integrate) {
-						const float vx = fmaf(axx, a.dt, vm.x), vy = fmaf(ayy, a.dt, vm.y), vz = fmaf(azz, a.dt, vm.z);
-						const bool kd = a.integrator == NBODY_KICK_DRIFT;
-						a.posq_out[i] = make_float4(fmaf(kd ? vx : vm.x, a.dt, tt.x), fmaf(kd ? vy : vm.y, a.dt, tt.y), fmaf(kd ? vz : vm.z, a.dt, tt.z), tt.w);
-						a.velm_out[i] = make_float4(vx, vy, vz, vm.w);
-					} else {
-						a.posq_out[i] = tt;
-						a.velm_out[i] = vm;
+					for (unsigned r = 0; r < TPL; ++r) {
+						if (t + r * T >= ntc) break;
+						const uint32_t i = b + t0 + t + r * T;
+						const float4 tt = a.posq[i];
+						const float px = r == 0 ? ax[0] : r == 1 ? ax[1] : r == 2 ? ax[2] : ax[3];
+						const float py = r == 0 ? ay[0] : r == 1 ? ay[1] : r == 2 ? ay[2] : ay[3];
+						const float pz = r == 0 ? az[0] : r == 1 ? az[1] : r == 2 ? az[2] : az[3];
+						float fx, fy, fz;
+						E::l2p(l, tt.x - g.x, tt.y - g.y, tt.z - g.z, fx, fy, fz);
+						const float4 vm = a.velm_in[i];
+						const float sc = a.G * tt.w / vm.w;  // a = G q/m * field (src/force.cl:4-10, src/open_cl_simulation.cpp:602-604)
+						const float axx = sc * (px + fx), ayy = sc * (py + fy), azz = sc * (pz + fz);
+						a.acc[i] = make_float4(axx, ayy, azz, 0.f);
+						if (!a.no_integrate) {
+							const float vx = fmaf(axx, a.dt, vm.x), vy = fmaf(ayy, a.dt, vm.y), vz = fmaf(azz, a.dt, vm.z);
+							const bool kd = a.integrator == NBODY_KICK_DRIFT;
+							a.posq_out[i] = make_float4(fmaf(kd ? vx : vm.x, a.dt, tt.x), fmaf(kd ? vy : vm.y, a.dt, tt.y), fmaf(kd ? vz : vm.z, a.dt, tt.z), tt.w);
+							a.velm_out[i] = make_float4(vx, vy, vz, vm.w);
+						} else {
+							a.posq_out[i] = tt;
+							a.velm_out[i] = vm;
+						}
 					}
 				}
 			}
@@ -250,28 +309,41 @@ __global__ void __launch_bounds__(kLeafWarps * 32) k_leaf(const LeafArgs a) {
 	if (lane == 0 && leaves) { atomicAdd(a.stat_inter, inter); atomicAdd(a.stat_leaves, leaves); }
 }
 
+struct LeafTuning { uint32_t cost_ovh, max_tpl, ctas_per_sm; };
+static LeafTuning leaf_tuning() {  // developer knobs (environment), read once
+	static const LeafTuning t = [] {
+		LeafTuning v{4u, 4u, 5u};
+		if (const char* e = getenv("NBODY_LEAF_OVH")) v.cost_ovh = (uint32_t) atoi(e);
+		if (const char* e = getenv("NBODY_LEAF_MAX_TPL")) v.max_tpl = (uint32_t) atoi(e);
+		if (const char* e = getenv("NBODY_LEAF_CTAS")) v.ctas_per_sm = (uint32_t) atoi(e);
+		if (v.max_tpl != 1u && v.max_tpl != 2u) v.max_tpl = 4u;
+		if (v.ctas_per_sm < 1u || v.ctas_per_sm > 16u) v.ctas_per_sm = 5u;
+		return v;
+	}();
+	return t;
+}
+
 template <int P>
-static void leaf_t(Sim& s, const LeafArgs& a) {
-	if (s.cfg.softening > 0.0f) k_leaf<P, true><<<kNumSM * 7, kLeafWarps * 32, 0, s.stream>>>(a);
-	else k_leaf<P, false><<<kNumSM * 7, kLeafWarps * 32, 0, s.stream>>>(a);
+static void leaf_t(Sim& s, const LeafArgs& a, unsigned grid) {
+	if (s.cfg.softening > 0.0f) k_leaf<P, true><<<grid, kLeafWarps * 32, 0, s.stream>>>(a);
+	else k_leaf<P, false><<<grid, kLeafWarps * 32, 0, s.stream>>>(a);
 }
 
 void launch_leaf(Sim& s) {
+	const LeafTuning tune = leaf_tuning();
 	LeafArgs a{};
 	a.c = s.ctrl; a.posq = s.posq[1]; a.velm_in = s.velm[1]; a.posq_out = s.posq[0]; a.velm_out = s.velm[0]; a.acc = s.acc;
 	a.geom = s.geom; a.info = s.info; a.nbegin = s.nbegin; a.p2p_head = s.p2p_head; a.seg = s.pools.seg; a.p2p = s.pools.p2p; a.L = s.L;
 	a.eps2 = s.cfg.softening * s.cfg.softening; a.G = s.cfg.force_constant; a.dt = s.cfg.time_step;
 	a.integrator = (int) s.cfg.integrator; a.no_integrate = (s.cfg.flags & NBODY_FLAG_NO_INTEGRATE) ? 1 : 0;
 	a.rank = s.rank;
-	{  // batch_entries * leaf_capacity <= kLeafTile, at most one entry per lane
-		uint32_t eb = kLeafTile / (s.cfg.leaf_capacity ? s.cfg.leaf_capacity : 1u);
-		a.batch_entries = eb < 1u ? 1u : (eb > 32u ? 32u : eb);
-	}
+	a.cost_ovh = tune.cost_ovh; a.max_tpl = tune.max_tpl;
 	a.stat_inter = &s.ctrl->stat_p2p_inter; a.stat_leaves = &s.ctrl->stat_leaves;
+	const unsigned grid = kNumSM * tune.ctas_per_sm;
 	switch (s.cfg.order) {
-		case 2: leaf_t<2>(s, a); break;
-		case 3: leaf_t<3>(s, a); break;
-		default: leaf_t<4>(s, a); break;
+		case 2: leaf_t<2>(s, a, grid); break;
+		case 3: leaf_t<3>(s, a, grid); break;
+		default: leaf_t<4>(s, a, grid); break;
 	}
 }
 

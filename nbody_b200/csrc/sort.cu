@@ -4,7 +4,8 @@
 // __match_any_sync (equal digits inside a warp-row keep lane order, rows keep row order, warps and
 // tiles keep index order), so the permutation is identical to a stable CPU sort (the oracle's
 // std::stable_sort): ties between equal keys keep their previous order.
-// HBM traffic per pass: 8 B (histogram read) + 12 B read + 12 B write per element.
+// HBM traffic per pass: 8 B (histogram read) + 12 B read + 12 B write per element; the scatter sorts each tile by
+// digit in shared memory first, so its global writes are contiguous runs.
 #include "common.cuh"
 
 namespace nbody {
@@ -93,37 +94,61 @@ __global__ void __launch_bounds__(256) k_scan_apply(uint32_t n, uint32_t* data, 
 }
 
 // ---- stable scatter ----
-__global__ void __launch_bounds__(kSortThreads) k_sort_scatter(uint64_t n, const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+// The tile is first sorted by digit inside shared memory (rank = elements of the same digit that precede it in the
+// tile), then written out slot by slot: consecutive threads hold consecutive slots of one digit run, so the global
+// writes are contiguous runs (16 elements = 128 B of keys on average) instead of one sector per lane.
+struct ScatterSmem {
+	uint64_t keys[kSortTile];
+	uint32_t vals[kSortTile];
+	uint32_t whist[kSortWarps][256];  // per warp: running count per digit, then exclusive base inside the tile
+	uint32_t gdelta[256];             // global position of tile slot s holding digit d: gdelta[d] + s
+	uint32_t ws[8];
+};
+
+__global__ void __launch_bounds__(kSortThreads, 3) k_sort_scatter(uint64_t n, const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                                                                uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int shift,
                                                                uint32_t nblocks, const uint32_t* __restrict__ offsets) {
-	__shared__ uint32_t whist[kSortWarps][256];  // per warp: running count per digit, then exclusive base inside the tile
-	__shared__ uint32_t gbase[256];
+	extern __shared__ __align__(16) unsigned char sort_smem_raw[];
+	ScatterSmem& S = *reinterpret_cast<ScatterSmem*>(sort_smem_raw);
 	const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
-	for (int k = threadIdx.x; k < kSortWarps * 256; k += kSortThreads) (&whist[0][0])[k] = 0;
-	gbase[threadIdx.x] = offsets[(size_t) threadIdx.x * nblocks + blockIdx.x];
+	for (int k = threadIdx.x; k < kSortWarps * 256; k += kSortThreads) (&S.whist[0][0])[k] = 0;
+	const uint32_t gb = offsets[(size_t) threadIdx.x * nblocks + blockIdx.x];
 	__syncthreads();
 	// warp w owns the contiguous range [w*512, (w+1)*512) of the tile, visited row by row (32 consecutive elements per row)
-	const uint64_t wbase = (uint64_t) blockIdx.x * kSortTile + (uint64_t) w * (32 * kSortItems);
+	const uint64_t tbase = (uint64_t) blockIdx.x * kSortTile;
+	const uint64_t wbase = tbase + (uint64_t) w * (32 * kSortItems);
 	uint64_t key[kSortItems];
-	uint32_t rank[kSortItems];
+	uint32_t rank2[kSortItems / 2];  // two 16-bit ranks per register (a rank is < 4096)
+	// all key loads first (independent requests in flight), then the ranking loop, which is serial by nature
+#pragma unroll
+	for (int j = 0; j < kSortItems; ++j) {
+		const uint64_t i = wbase + 32 * j + lane;
+		key[j] = i < n ? keys_in[i] : ~0ull;
+	}
 #pragma unroll
 	for (int j = 0; j < kSortItems; ++j) {
 		const uint64_t i = wbase + 32 * j + lane;
 		const bool ok = i < n;
-		key[j] = ok ? keys_in[i] : ~0ull;
 		const uint32_t d = (uint32_t) (key[j] >> shift) & 255u;
 		const unsigned peers = __match_any_sync(0xffffffffu, ok ? d : 256u + lane);  // out-of-range lanes match nobody
-		const uint32_t before = whist[w][d];
-		rank[j] = before + __popc(peers & ((1u << lane) - 1u));
+		const uint32_t before = S.whist[w][d];
+		const uint32_t r = before + __popc(peers & ((1u << lane) - 1u));
+		if (j & 1) rank2[j >> 1] |= r << 16; else rank2[j >> 1] = r;
 		__syncwarp();
-		if (ok && (peers >> lane) == 1u) whist[w][d] = before + __popc(peers);  // the highest peer lane updates the count
+		if (ok && (peers >> lane) == 1u) S.whist[w][d] = before + __popc(peers);  // the highest peer lane updates the count
 		__syncwarp();
 	}
 	__syncthreads();
-	{  // exclusive prefix over the warps, per digit (thread = digit)
+	{  // thread = digit: exclusive prefix over the warps, then over the digits of the tile
 		uint32_t run = 0;
 #pragma unroll
-		for (int ww = 0; ww < kSortWarps; ++ww) { const uint32_t c = whist[ww][threadIdx.x]; whist[ww][threadIdx.x] = run; run += c; }
+		for (int ww = 0; ww < kSortWarps; ++ww) run += S.whist[ww][threadIdx.x];
+		uint32_t total;
+		const uint32_t ex = block_scan_256(run, S.ws, total);
+		run = ex;
+#pragma unroll
+		for (int ww = 0; ww < kSortWarps; ++ww) { const uint32_t c = S.whist[ww][threadIdx.x]; S.whist[ww][threadIdx.x] = run; run += c; }
+		S.gdelta[threadIdx.x] = gb - ex;
 	}
 	__syncthreads();
 #pragma unroll
@@ -131,9 +156,21 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_scatter(uint64_t n, const
 		const uint64_t i = wbase + 32 * j + lane;
 		if (i < n) {
 			const uint32_t d = (uint32_t) (key[j] >> shift) & 255u;
-			const uint32_t pos = gbase[d] + whist[w][d] + rank[j];
-			keys_out[pos] = key[j];
-			vals_out[pos] = vals_in[i];
+			const uint32_t slot = S.whist[w][d] + ((j & 1) ? rank2[j >> 1] >> 16 : rank2[j >> 1] & 0xffffu);
+			S.keys[slot] = key[j];
+			S.vals[slot] = vals_in[i];
+		}
+	}
+	__syncthreads();
+	const uint32_t nv = (uint32_t) (n - tbase < (uint64_t) kSortTile ? n - tbase : (uint64_t) kSortTile);
+#pragma unroll
+	for (int j = 0; j < kSortItems; ++j) {
+		const uint32_t slot = j * kSortThreads + threadIdx.x;
+		if (slot < nv) {
+			const uint64_t k = S.keys[slot];
+			const uint32_t pos = S.gdelta[(uint32_t) (k >> shift) & 255u] + slot;
+			keys_out[pos] = k;
+			vals_out[pos] = S.vals[slot];
 		}
 	}
 }
@@ -155,13 +192,14 @@ void launch_own_sort(Sim& s) {
 	uint32_t* sums = hist + hist_n;
 	uint64_t* kin = s.keys[0]; uint64_t* kout = s.keys[1];
 	uint32_t* vin = s.idx[0]; uint32_t* vout = s.idx[1];
+	cudaFuncSetAttribute(k_sort_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(ScatterSmem));
 	for (int pass = 0; pass < 8; ++pass) {
 		const int shift = 8 * pass;
 		k_sort_hist<<<nblocks, kSortThreads, 0, s.stream>>>(n, kin, shift, nblocks, hist);
 		k_scan_sums<<<nsums, 256, 0, s.stream>>>(hist_n, hist, sums);
 		k_scan_top<<<1, 256, 0, s.stream>>>(nsums, sums);
 		k_scan_apply<<<nsums, 256, 0, s.stream>>>(hist_n, hist, sums);
-		k_sort_scatter<<<nblocks, kSortThreads, 0, s.stream>>>(n, kin, vin, kout, vout, shift, nblocks, hist);
+		k_sort_scatter<<<nblocks, kSortThreads, sizeof(ScatterSmem), s.stream>>>(n, kin, vin, kout, vout, shift, nblocks, hist);
 		uint64_t* tk = kin; kin = kout; kout = tk;
 		uint32_t* tv = vin; vin = vout; vout = tv;
 	}
