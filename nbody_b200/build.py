@@ -6,13 +6,16 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "build")
-LIB = os.path.join(HERE, "libnbody_cuda.so")
+# developer variants: NBODY_BUILD_TAG=g12 NBODY_BUILD_DEFS="-DNBODY_LEAF_G=12" builds libnbody_cuda_g12.so next to the product
+# library (objects under build_g12/); load it with NBODY_CUDA_LIB=<path>.
+TAG = os.environ.get("NBODY_BUILD_TAG", "")
+OBJ = os.path.join(HERE, "build" + ("_" + TAG if TAG else ""))
+LIB = os.path.join(HERE, "libnbody_cuda" + ("_" + TAG if TAG else "") + ".so")
 SOURCES = ["api.cu", "tree.cu", "sort.cu", "upsweep.cu", "traverse.cu", "m2l.cu", "leaf.cu", "comm.cu"]
 HEADERS = ["common.cuh", "expansion.cuh", os.path.join("..", "..", "include", "nbody_cuda.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
-         "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+         "--expt-relaxed-constexpr", "-Xptxas", "-v"] + os.environ.get("NBODY_BUILD_DEFS", "").split()
 
 
 def _stale(target, deps):

@@ -149,4 +149,18 @@ int direct_field_device(const float4* src, uint64_t n_src, const float4* tgt, ui
 // device helpers shared by several translation units
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
 
+// Sum each of 32 values over the 32 lanes of the warp: every halving step hands the partner lane the half of
+// the values it is responsible for, so 31 shuffles do the work of 160. On return v[0] of lane l holds the total of value l.
+__device__ __forceinline__ void transpose_reduce32(float (&v)[32], unsigned lane) {
+#pragma unroll
+	for (int h = 16; h >= 1; h >>= 1) {  // partner = lane ^ h: lanes with that bit set keep the upper h values
+		const bool up = (lane & (unsigned) h) != 0u;
+#pragma unroll
+		for (int i = 0; i < h; ++i) {
+			const float send = up ? v[i] : v[i + h], keep = up ? v[i + h] : v[i];
+			v[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+		}
+	}
+}
+
 }  // namespace nbody

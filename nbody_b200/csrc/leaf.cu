@@ -1,9 +1,11 @@
-// Stage 5: near field. One warp per target leaf: the leaf's P2P source list is
-// expanded into a per-warp shared-memory tile of source particles (x,y,z,q) and the
-// warp evaluates T targets x S source slices (T*S = 32, T = leaf population rounded
-// up to a power of two) so that small leaves still fill the warp. The epilogue adds
-// the far field (L2P) and applies the integrator, so accelerations never make a
-// round trip through a per-interaction buffer.
+// Stage 5: near field. One warp per block of <= kLeafG targets of one leaf: the leaf's P2P
+// source list is expanded into a per-warp shared-memory tile of source particles (x,y,z,q);
+// every lane owns one source of a 32-source row and applies it to all targets of the block
+// (target coordinates are broadcast from shared memory, the 3 x G partial accelerations live
+// in registers), so all 32 lanes do useful work whatever the leaf population is. One
+// transposing shuffle reduction per block, then the epilogue adds the far field (L2P) and
+// applies the integrator, so accelerations never make a round trip through a per-interaction
+// buffer.
 //
 // Replaces src/field.cl:49-148 (8x8 work-group per leaf interaction writing one
 // 16-byte slot per (leaf, partner leaf, interaction)), src/force.cl:21-81 (slot
@@ -21,10 +23,20 @@ namespace nbody {
 constexpr int kLeafWarps = 4;
 constexpr int kLeafTile = 256;  // source particles per tile; two tiles (8 KB) per warp
 constexpr int kLeafChunk = 8;   // node ids per work ticket
+#ifndef NBODY_LEAF_G
+#define NBODY_LEAF_G 16
+#endif
+constexpr int kLeafG = NBODY_LEAF_G;  // most targets per block (3 accumulators each, in registers)
+#ifndef NBODY_LEAF_ROWS
+#define NBODY_LEAF_ROWS 2
+#endif
+constexpr int kLeafRows = NBODY_LEAF_ROWS;  // 32-source rows in flight per lane (independent dependency chains per target)
+constexpr uint32_t kLeafPad = 32u * kLeafRows;  // tiles are padded with zero-charge sources to a multiple of this
 #ifndef NBODY_LEAF_MIN_CTAS
-#define NBODY_LEAF_MIN_CTAS 5
+#define NBODY_LEAF_MIN_CTAS 4
 #endif
 constexpr int kLeafMinCtas = NBODY_LEAF_MIN_CTAS;  // resident CTAs per SM the register allocation is held to
+static_assert(kLeafG >= 1 && kLeafG <= 16, "the transposing reduction handles up to 16 targets per block");
 
 __device__ __forceinline__ void leaf_cp_async16(void* smem, const void* gmem) {
 	const unsigned sa = (unsigned) __cvta_generic_to_shared(smem);
@@ -65,64 +77,78 @@ struct LeafArgs {
 	float eps2, G, dt;
 	int integrator, no_integrate;
 	int rank;                     // this rank's slice of the tree-ordered particle array: [c->part[rank], c->part[rank+1])
-	uint32_t cost_ovh;            // warp layout choice: issue slots per source step that do not scale with the targets per lane (LDS, loop)
-	uint32_t max_tpl;             // most targets per lane the layout may use (1, 2 or 4)
 	unsigned long long* stat_inter;
 	unsigned long long* stat_leaves;
 };
 
-// Every lane walks its slice of the tile (sources sl, sl+S, ...) for TPL targets held in registers:
-// one LDS.128 and one loop step feed TPL interactions. U sources are in flight per iteration.
-template <bool SOFT, int TPL, int U>
-__device__ __forceinline__ void tile_compute(const float4* buf, uint32_t fill, unsigned sl, unsigned S, const float (&tx)[4], const float (&ty)[4],
-                                             const float (&tz)[4], float eps2, float (&ax)[4], float (&ay)[4], float (&az)[4]) {
+// One tile against the G targets of the block: lane = one source of each of kLeafRows rows, the targets are applied
+// by falling through a switch (entry point = G), so there is ONE copy of the interaction code whatever G is —
+// per-G unrolled loops were tried and lost to instruction-cache misses (warps of one SM work on different G).
+// The tile is padded with zero-charge sources up to a whole group of rows.
+template <bool SOFT>
+__device__ __forceinline__ void tile_rows(unsigned G, const float4* __restrict__ buf, uint32_t nrows, unsigned lane, const float4* __restrict__ tgt,
+                                          float eps2, float (&ax)[16], float (&ay)[16], float (&az)[16]) {
 	__syncwarp();
-	uint32_t j = sl;
-	for (; j + (U - 1) * S < fill; j += U * S) {
-		float4 s[U];
+#pragma unroll 1
+	for (uint32_t r = 0; r < nrows; r += kLeafRows) {
+		float4 s[kLeafRows];
 #pragma unroll
-		for (int u = 0; u < U; ++u) s[u] = buf[j + u * S];
+		for (int u = 0; u < kLeafRows; ++u) s[u] = buf[(r + u) * 32u + lane];
+		float4 t = tgt[G - 1u];  // the coordinates of the next target are fetched one block ahead of their use
+#define NB_LEAF_T(k)                                                                                        \
+	case k + 1:                                                                                                \
+		if (k < kLeafG) {                                                                                        \
+			const float4 tn = tgt[k > 0 ? k - 1 : 0];                                                              \
+			_Pragma("unroll") for (int u = 0; u < kLeafRows; ++u) p2p_interact<SOFT>(s[u], t.x, t.y, t.z, eps2, ax[k], ay[k], az[k]); \
+			t = tn;                                                                                                \
+		}
+		switch (G) {
+			NB_LEAF_T(15) NB_LEAF_T(14) NB_LEAF_T(13) NB_LEAF_T(12) NB_LEAF_T(11) NB_LEAF_T(10) NB_LEAF_T(9) NB_LEAF_T(8)
+			NB_LEAF_T(7) NB_LEAF_T(6) NB_LEAF_T(5) NB_LEAF_T(4) NB_LEAF_T(3) NB_LEAF_T(2) NB_LEAF_T(1) NB_LEAF_T(0)
+			default: break;
+		}
+#undef NB_LEAF_T
+	}
+	__syncwarp();
+}
+
+// Sum v[k] over the 32 lanes for 16 values at once: each halving step exchanges the half of the values the
+// partner lane is responsible for, so 16 shuffles do the work of 80. On return v[0] of lanes 2k and 2k+1 holds
+// the total of value k.
+__device__ __forceinline__ void transpose_reduce16(float (&v)[16], unsigned lane) {
 #pragma unroll
-		for (int u = 0; u < U; ++u) {
+	for (int h = 8; h >= 1; h >>= 1) {  // partner = lane ^ (2h): lanes with that bit set keep the upper h values
+		const bool up = (lane & (2u * h)) != 0u;
 #pragma unroll
-			for (int r = 0; r < TPL; ++r) p2p_interact<SOFT>(s[u], tx[r], ty[r], tz[r], eps2, ax[r], ay[r], az[r]);
+		for (int i = 0; i < h; ++i) {
+			const float send = up ? v[i] : v[i + h], keep = up ? v[i + h] : v[i];
+			v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2 * h);
 		}
 	}
-	for (; j < fill; j += S) {
-		const float4 s0 = buf[j];
-#pragma unroll
-		for (int r = 0; r < TPL; ++r) p2p_interact<SOFT>(s0, tx[r], ty[r], tz[r], eps2, ax[r], ay[r], az[r]);
-	}
-	__syncwarp();
+	v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
-template <bool SOFT>
-__device__ __forceinline__ void tile_dispatch(unsigned tpl, const float4* buf, uint32_t fill, unsigned sl, unsigned S, const float (&tx)[4],
-                                              const float (&ty)[4], const float (&tz)[4], float eps2, float (&ax)[4], float (&ay)[4], float (&az)[4]) {
-	if (tpl == 4u) tile_compute<SOFT, 4, 2>(buf, fill, sl, S, tx, ty, tz, eps2, ax, ay, az);
-	else if (tpl == 2u) tile_compute<SOFT, 2, 4>(buf, fill, sl, S, tx, ty, tz, eps2, ax, ay, az);
-	else tile_compute<SOFT, 1, 4>(buf, fill, sl, S, tx, ty, tz, eps2, ax, ay, az);
-}
-
-// One warp per target leaf; leaves are handed out kLeafChunk node ids at a time by an atomic ticket, so the grid is
-// exactly the resident set and no warp idles while another still has a queue. The leaf's source list is a chain of
-// segments of {first particle, count} entries. A batch is the longest run of entries (<= 32, one per lane) whose
-// particles fit one 256-particle tile; it is expanded with fully used 16-byte cp.async rows (the flat index -> entry
-// map is a bitmap of the entries' end positions, built with warp OR-reductions) while the previous tile is being
-// evaluated (two tiles per warp), and the entries of the batch after that are already in registers — so neither the
-// list walk nor the particle fetch sits on the critical path.
+// Leaves are handed out kLeafChunk node ids at a time by an atomic ticket, so the grid is exactly the resident set.
+// A leaf's source list is a chain of segments of {first particle, count} entries. The sources stream through two
+// 256-particle tiles per warp: the flat particle range of up to 32 entries (one per lane) is cut at exactly one
+// tile — an entry may straddle two tiles, `skip` remembers how much of the first entry is already consumed — and
+// copied with fully used 16-byte cp.async rows (the flat slot -> entry map is a bitmap of the entries' end
+// positions, built with warp OR-reductions) while the previous tile is being evaluated; the entries of the batch
+// after that are already in registers, so neither the list walk nor the particle fetch sits on the critical path.
 template <int P, bool SOFT>
 __global__ void __launch_bounds__(kLeafWarps * 32, kLeafMinCtas) k_leaf(const LeafArgs a) {
 	using E = Expansion<P>;
 	constexpr int STRIDE = coef_stride(P);
 	constexpr uint32_t END = 0xffffffffu;
 	__shared__ float4 sbuf[kLeafWarps][2][kLeafTile];
+	__shared__ float4 stgt[kLeafWarps][16];
 	const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
 	if (a.c->status) return;  // a pool overflowed: the host grows it and re-runs the step; leave the state untouched
 	const uint32_t n_nodes = a.c->n_nodes;
 	const uint32_t own_first = a.c->part[a.rank], own_end = a.c->part[a.rank + 1];
 	const unsigned le_mask = (2u << lane) - 1u;  // bits 0..lane
 	unsigned long long inter = 0, leaves = 0;
+#pragma unroll 1
 	for (;;) {
 		uint32_t chunk = 0;
 		if (lane == 0) chunk = atomicAdd(&a.c->work_ticket[3], (uint32_t) kLeafChunk);
@@ -133,6 +159,7 @@ __global__ void __launch_bounds__(kLeafWarps * 32, kLeafMinCtas) k_leaf(const Le
 		if (lane < (unsigned) kLeafChunk && chunk + lane < n_nodes) { nf_l = a.info[chunk + lane]; b_l = a.nbegin[chunk + lane]; }
 		// childless, non-empty, and inside this rank's slice
 		unsigned todo = __ballot_sync(0xffffffffu, nf_l.x == 0u && nf_l.y != 0u && b_l >= own_first && b_l < own_end);
+#pragma unroll 1
 		while (todo) {
 			const int kk = __ffs(todo) - 1;
 			todo &= todo - 1u;
@@ -140,36 +167,18 @@ __global__ void __launch_bounds__(kLeafWarps * 32, kLeafMinCtas) k_leaf(const Le
 			const uint32_t nt = __shfl_sync(0xffffffffu, nf_l.y, kk), b = __shfl_sync(0xffffffffu, b_l, kk);
 			++leaves;
 			const float4 g = a.geom[node];
-			for (uint32_t t0 = 0; t0 < nt; t0 += 32) {
-				const uint32_t ntc = min(32u, nt - t0);
-				// Warp layout: T target lanes x S source slices with TPL targets per lane (T = ceil(ntc/TPL), S = floor(32/T),
-				// lanes >= T*S idle). One source step costs (cost_ovh + 13 TPL) issue slots and yields S*ntc useful interactions.
-				unsigned TPL = 1u, T = ntc, S = 32u / ntc;
-				{
-					uint32_t best = ((a.cost_ovh + 13u) << 12) / (S * ntc);
+			const uint32_t nblk = (nt + kLeafG - 1) / kLeafG, gmax = (nt + nblk - 1) / nblk;  // even blocks of <= kLeafG targets
+#pragma unroll 1
+			for (uint32_t t0 = 0; t0 < nt; t0 += gmax) {
+				const unsigned G = min(gmax, nt - t0);
+				__syncwarp();
+				if (lane < G) stgt[w][lane] = a.posq[b + t0 + lane];
+				float ax[16], ay[16], az[16];
 #pragma unroll
-					for (unsigned tp = 2u; tp <= 4u; tp <<= 1) {
-						if (tp > a.max_tpl) break;
-						const unsigned Tt = (ntc + tp - 1u) / tp, St = 32u / Tt;
-						const uint32_t cost = ((a.cost_ovh + 13u * tp) << 12) / (St * ntc);
-						if (cost < best) { best = cost; TPL = tp; T = Tt; S = St; }
-					}
-				}
-				const unsigned sl_raw = lane / T, t = lane - sl_raw * T;
-				const bool lane_on = lane < T * S;
-				const unsigned sl = lane_on ? sl_raw : (unsigned) kLeafTile;  // idle lanes: an empty slice
-				float tx[4], ty[4], tz[4], ax[4], ay[4], az[4];
-#pragma unroll
-				for (int r = 0; r < 4; ++r) {
-					tx[r] = ty[r] = tz[r] = ax[r] = ay[r] = az[r] = 0.f;
-					if ((unsigned) r < TPL && lane_on && t + r * T < ntc) {
-						const float4 p = a.posq[b + t0 + t + r * T];
-						tx[r] = p.x; ty[r] = p.y; tz[r] = p.z;
-					}
-				}
+				for (int k = 0; k < 16; ++k) ax[k] = ay[k] = az[k] = 0.f;
 				unsigned long long nsrc = 0;
-				// ---- cursor over the segment chain ----
-				uint32_t si = a.p2p_head[node], e0 = 0;
+				// ---- cursor over the segment chain: entry e0 of segment sg, of which `skip` particles are consumed ----
+				uint32_t si = a.p2p_head[node], e0 = 0, skip = 0;
 				Segment sg; sg.off = 0; sg.cnt = 0; sg.next = END;
 				auto fetch = [&](uint2& ent) -> bool {  // the (up to) 32 entries at the cursor, lane l holds entry l; warp-uniform result
 					while (e0 >= sg.cnt) {
@@ -180,94 +189,68 @@ __global__ void __launch_bounds__(kLeafWarps * 32, kLeafMinCtas) k_leaf(const Le
 					if (e0 + lane < sg.cnt) ent = a.p2p[sg.off + e0 + lane];
 					return true;
 				};
-				// Consume the leading entries of `ent` that fit one tile and issue its fill. An over-full source leaf
-				// (more than a tile; only at max depth) forms a batch of its own and is streamed by the consumer.
-				auto stage = [&](const uint2& ent, float4* tile, uint32_t& fill, uint2& big) {
+				// Cut one tile off the flat particle range of `ent`, issue its fill and advance the cursor.
+				auto stage = [&](const uint2& ent, float4* tile, uint32_t& fill) {
 					const uint32_t nvalid = min(32u, sg.cnt - e0);
-					const unsigned bigm = __ballot_sync(0xffffffffu, lane < nvalid && ent.y > (uint32_t) kLeafTile);
-					fill = 0; big = make_uint2(0u, 0u);
-					if (bigm & 1u) {
-						big = make_uint2(__shfl_sync(0xffffffffu, ent.x, 0), __shfl_sync(0xffffffffu, ent.y, 0));
-						e0 += 1u;
-						leaf_cp_async_commit();
-						return;
-					}
-					const uint32_t nlim = bigm ? (uint32_t) (__ffs(bigm) - 1) : nvalid;
-					uint32_t v = lane < nlim ? ent.y : 0u;
+					const uint32_t sk = lane == 0u ? skip : 0u;
+					const uint32_t v = lane < nvalid ? ent.y - sk : 0u;
 					uint32_t inc = v;
 #pragma unroll
 					for (int d = 1; d < 32; d <<= 1) {
 						const uint32_t u = __shfl_up_sync(0xffffffffu, inc, d);
 						if (lane >= (unsigned) d) inc += u;
 					}
-					const bool fits = lane < nlim && inc <= (uint32_t) kLeafTile;  // a prefix of the lanes: inc is monotone
-					const uint32_t nfit = __popc(__ballot_sync(0xffffffffu, fits));  // >= 1
-					fill = __shfl_sync(0xffffffffu, inc, (nfit - 1u) & 31u);
-					e0 += nfit;
-					const uint32_t src0 = ent.x - (inc - v);  // particle index of flat slot f inside entry l: src0 + f
+					const bool full = lane < nvalid && inc <= (uint32_t) kLeafTile;  // entries that end inside the tile: a prefix of the lanes
+					const uint32_t nfull = __popc(__ballot_sync(0xffffffffu, full));
+					const uint32_t avail = __shfl_sync(0xffffffffu, inc, nvalid - 1u);
+					const uint32_t used = __shfl_sync(0xffffffffu, inc, (nfull - 1u) & 31u);  // particles of the whole entries (if any)
+					fill = min(avail, (uint32_t) kLeafTile);
+					if (nfull < nvalid) skip = (nfull ? 0u : skip) + (fill - (nfull ? used : 0u));  // entry nfull straddles the tile end
+					else skip = 0u;
+					e0 += nfull;
+					const uint32_t src0 = ent.x + sk - (inc - v);  // particle index of flat slot f inside entry l: src0 + f
 					uint32_t pc = 0;
 #pragma unroll
 					for (int i = 0; i < kLeafTile / 32; ++i) {
-						if (32u * i >= fill) break;
+						if (32u * i >= (fill + kLeafPad - 1u) / kLeafPad * kLeafPad) break;
 						// bit p of the bitmap: some entry ends at flat position p; entry of slot f = number of ends <= f
-						const unsigned word = __reduce_or_sync(0xffffffffu, (fits && (inc >> 5) == (uint32_t) i) ? 1u << (inc & 31u) : 0u);
+						const unsigned word = __reduce_or_sync(0xffffffffu, (full && (inc >> 5) == (uint32_t) i) ? 1u << (inc & 31u) : 0u);
 						const uint32_t f = 32u * i + lane;
 						const uint32_t e = pc + __popc(word & le_mask);
 						const uint32_t s0 = __shfl_sync(0xffffffffu, src0, e & 31u);
 						if (f < fill) leaf_cp_async16(tile + f, a.posq + (s0 + f));
+						else if (f < (fill + kLeafPad - 1u) / kLeafPad * kLeafPad) tile[f] = make_float4(0.f, 0.f, 0.f, 0.f);  // pad to whole row groups: zero charge
 						pc += __popc(word);
 					}
 					leaf_cp_async_commit();
 				};
-				uint2 ent_cur = make_uint2(0u, 0u), ent_nxt = make_uint2(0u, 0u), big_cur = make_uint2(0u, 0u);
+				uint2 ent_cur = make_uint2(0u, 0u), ent_nxt = make_uint2(0u, 0u);
 				uint32_t fill_cur = 0;
 				int cur = 0;
 				bool has_cur = fetch(ent_cur);
-				if (has_cur) stage(ent_cur, sbuf[w][0], fill_cur, big_cur);
+				if (has_cur) stage(ent_cur, sbuf[w][0], fill_cur);
 				bool has_nxt = has_cur && fetch(ent_nxt);
+#pragma unroll 1
 				while (has_cur) {
 					uint32_t fill_nxt = 0;
-					uint2 big_nxt = make_uint2(0u, 0u);
-					if (has_nxt) stage(ent_nxt, sbuf[w][cur ^ 1], fill_nxt, big_nxt);
+					if (has_nxt) stage(ent_nxt, sbuf[w][cur ^ 1], fill_nxt);
 					else leaf_cp_async_commit();  // empty group keeps the wait_group arithmetic uniform
 					uint2 ent_nn = make_uint2(0u, 0u);
 					const bool has_nn = has_nxt && fetch(ent_nn);  // entries of the batch after next: in flight during the math
 					leaf_cp_async_wait1();
-					tile_dispatch<SOFT>(TPL, sbuf[w][cur], fill_cur, sl, S, tx, ty, tz, a.eps2, ax, ay, az);
+					tile_rows<SOFT>(G, sbuf[w][cur], (fill_cur + 31u) >> 5, lane, stgt[w], a.eps2, ax, ay, az);
 					nsrc += fill_cur;
-					if (big_cur.y) {  // stream an over-full source leaf through the tile that has just been consumed
-						for (uint32_t q0 = 0; q0 < big_cur.y; q0 += kLeafTile) {
-							const uint32_t m = min((uint32_t) kLeafTile, big_cur.y - q0);
-							for (uint32_t q = lane; q < m; q += 32) sbuf[w][cur][q] = a.posq[big_cur.x + q0 + q];
-							tile_dispatch<SOFT>(TPL, sbuf[w][cur], m, sl, S, tx, ty, tz, a.eps2, ax, ay, az);
-						}
-						nsrc += big_cur.y;
-					}
-					ent_nxt = ent_nn; fill_cur = fill_nxt; big_cur = big_nxt; has_cur = has_nxt; has_nxt = has_nn;
+					ent_nxt = ent_nn; fill_cur = fill_nxt; has_cur = has_nxt; has_nxt = has_nn;
 					cur ^= 1;
 				}
 				leaf_cp_async_wait0();
-				// sum over the S slices into the lanes of slice 0 (lane t collects lanes t + s*T)
-#pragma unroll
-				for (int r = 0; r < 4; ++r) {
-					if ((unsigned) r >= TPL) break;
-#pragma unroll
-					for (int q = 0; q < 3; ++q) {
-						float v = q == 0 ? ax[r] : q == 1 ? ay[r] : az[r];
-						if ((T & (T - 1u)) == 0u) {  // T*S == 32: butterfly
-							for (unsigned d = T; d < 32u; d <<= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-						} else {
-							const float mine = lane_on ? v : 0.f;
-							float sum = mine;
-							for (unsigned sidx = 1; sidx < S; ++sidx) sum += __shfl_sync(0xffffffffu, mine, (lane + sidx * T) & 31u);
-							v = sum;
-						}
-						if (q == 0) ax[r] = v; else if (q == 1) ay[r] = v; else az[r] = v;
-					}
-				}
-				if (lane == 0) inter += nsrc * ntc;
-				if (lane_on && sl_raw == 0) {
-					// far field: L2P of this leaf's local expansion, then the integrator — for each target of the lane
+				transpose_reduce16(ax, lane);
+				transpose_reduce16(ay, lane);
+				transpose_reduce16(az, lane);
+				if (lane == 0) inter += nsrc * G;
+				const unsigned t = lane >> 1;
+				if ((lane & 1u) == 0u && t < G) {
+					// far field: L2P of this leaf's local expansion, then the integrator
 					float l[E::NC];
 					const float4* L4 = reinterpret_cast<const float4*>(a.L + (size_t) node * STRIDE);
 #pragma unroll
@@ -278,29 +261,22 @@ __global__ void __launch_bounds__(kLeafWarps * 32, kLeafMinCtas) k_leaf(const Le
 						if (4 * q + 2 < E::NC) l[4 * q + 2] = v.z;
 						if (4 * q + 3 < E::NC) l[4 * q + 3] = v.w;
 					}
-#pragma unroll 1
-					for (unsigned r = 0; r < TPL; ++r) {
-						if (t + r * T >= ntc) break;
-						const uint32_t i = b + t0 + t + r * T;
-						const float4 tt = a.posq[i];
-						const float px = r == 0 ? ax[0] : r == 1 ? ax[1] : r == 2 ? ax[2] : ax[3];
-						const float py = r == 0 ? ay[0] : r == 1 ? ay[1] : r == 2 ? ay[2] : ay[3];
-						const float pz = r == 0 ? az[0] : r == 1 ? az[1] : r == 2 ? az[2] : az[3];
-						float fx, fy, fz;
-						E::l2p(l, tt.x - g.x, tt.y - g.y, tt.z - g.z, fx, fy, fz);
-						const float4 vm = a.velm_in[i];
-						const float sc = a.G * tt.w / vm.w;  // a = G q/m * field (src/force.cl:4-10, src/open_cl_simulation.cpp:602-604)
-						const float axx = sc * (px + fx), ayy = sc * (py + fy), azz = sc * (pz + fz);
-						a.acc[i] = make_float4(axx, ayy, azz, 0.f);
-						if (!a.no_integrate) {
-							const float vx = fmaf(axx, a.dt, vm.x), vy = fmaf(ayy, a.dt, vm.y), vz = fmaf(azz, a.dt, vm.z);
-							const bool kd = a.integrator == NBODY_KICK_DRIFT;
-							a.posq_out[i] = make_float4(fmaf(kd ? vx : vm.x, a.dt, tt.x), fmaf(kd ? vy : vm.y, a.dt, tt.y), fmaf(kd ? vz : vm.z, a.dt, tt.z), tt.w);
-							a.velm_out[i] = make_float4(vx, vy, vz, vm.w);
-						} else {
-							a.posq_out[i] = tt;
-							a.velm_out[i] = vm;
-						}
+					const uint32_t i = b + t0 + t;
+					const float4 tt = stgt[w][t];
+					float fx, fy, fz;
+					E::l2p(l, tt.x - g.x, tt.y - g.y, tt.z - g.z, fx, fy, fz);
+					const float4 vm = a.velm_in[i];
+					const float sc = a.G * tt.w / vm.w;  // a = G q/m * field (src/force.cl:4-10, src/open_cl_simulation.cpp:602-604)
+					const float axx = sc * (ax[0] + fx), ayy = sc * (ay[0] + fy), azz = sc * (az[0] + fz);
+					a.acc[i] = make_float4(axx, ayy, azz, 0.f);
+					if (!a.no_integrate) {
+						const float vx = fmaf(axx, a.dt, vm.x), vy = fmaf(ayy, a.dt, vm.y), vz = fmaf(azz, a.dt, vm.z);
+						const bool kd = a.integrator == NBODY_KICK_DRIFT;
+						a.posq_out[i] = make_float4(fmaf(kd ? vx : vm.x, a.dt, tt.x), fmaf(kd ? vy : vm.y, a.dt, tt.y), fmaf(kd ? vz : vm.z, a.dt, tt.z), tt.w);
+						a.velm_out[i] = make_float4(vx, vy, vz, vm.w);
+					} else {
+						a.posq_out[i] = tt;
+						a.velm_out[i] = vm;
 					}
 				}
 			}
@@ -309,41 +285,30 @@ __global__ void __launch_bounds__(kLeafWarps * 32, kLeafMinCtas) k_leaf(const Le
 	if (lane == 0 && leaves) { atomicAdd(a.stat_inter, inter); atomicAdd(a.stat_leaves, leaves); }
 }
 
-struct LeafTuning { uint32_t cost_ovh, max_tpl, ctas_per_sm; };
-static LeafTuning leaf_tuning() {  // developer knobs (environment), read once
-	static const LeafTuning t = [] {
-		LeafTuning v{4u, 4u, 5u};
-		if (const char* e = getenv("NBODY_LEAF_OVH")) v.cost_ovh = (uint32_t) atoi(e);
-		if (const char* e = getenv("NBODY_LEAF_MAX_TPL")) v.max_tpl = (uint32_t) atoi(e);
-		if (const char* e = getenv("NBODY_LEAF_CTAS")) v.ctas_per_sm = (uint32_t) atoi(e);
-		if (v.max_tpl != 1u && v.max_tpl != 2u) v.max_tpl = 4u;
-		if (v.ctas_per_sm < 1u || v.ctas_per_sm > 16u) v.ctas_per_sm = 5u;
-		return v;
-	}();
-	return t;
-}
-
 template <int P>
-static void leaf_t(Sim& s, const LeafArgs& a, unsigned grid) {
-	if (s.cfg.softening > 0.0f) k_leaf<P, true><<<grid, kLeafWarps * 32, 0, s.stream>>>(a);
-	else k_leaf<P, false><<<grid, kLeafWarps * 32, 0, s.stream>>>(a);
+static void leaf_t(Sim& s, const LeafArgs& a) {
+	int ctas = kLeafMinCtas;
+	if (s.cfg.softening > 0.0f) {
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, k_leaf<P, true>, kLeafWarps * 32, 0);
+		k_leaf<P, true><<<kNumSM * (ctas > 0 ? ctas : 1), kLeafWarps * 32, 0, s.stream>>>(a);
+	} else {
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, k_leaf<P, false>, kLeafWarps * 32, 0);
+		k_leaf<P, false><<<kNumSM * (ctas > 0 ? ctas : 1), kLeafWarps * 32, 0, s.stream>>>(a);
+	}
 }
 
 void launch_leaf(Sim& s) {
-	const LeafTuning tune = leaf_tuning();
 	LeafArgs a{};
 	a.c = s.ctrl; a.posq = s.posq[1]; a.velm_in = s.velm[1]; a.posq_out = s.posq[0]; a.velm_out = s.velm[0]; a.acc = s.acc;
 	a.geom = s.geom; a.info = s.info; a.nbegin = s.nbegin; a.p2p_head = s.p2p_head; a.seg = s.pools.seg; a.p2p = s.pools.p2p; a.L = s.L;
 	a.eps2 = s.cfg.softening * s.cfg.softening; a.G = s.cfg.force_constant; a.dt = s.cfg.time_step;
 	a.integrator = (int) s.cfg.integrator; a.no_integrate = (s.cfg.flags & NBODY_FLAG_NO_INTEGRATE) ? 1 : 0;
 	a.rank = s.rank;
-	a.cost_ovh = tune.cost_ovh; a.max_tpl = tune.max_tpl;
 	a.stat_inter = &s.ctrl->stat_p2p_inter; a.stat_leaves = &s.ctrl->stat_leaves;
-	const unsigned grid = kNumSM * tune.ctas_per_sm;
 	switch (s.cfg.order) {
-		case 2: leaf_t<2>(s, a, grid); break;
-		case 3: leaf_t<3>(s, a, grid); break;
-		default: leaf_t<4>(s, a, grid); break;
+		case 2: leaf_t<2>(s, a); break;
+		case 3: leaf_t<3>(s, a); break;
+		default: leaf_t<4>(s, a); break;
 	}
 }
 

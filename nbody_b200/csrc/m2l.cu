@@ -164,15 +164,21 @@ k_m2l(Ctrl* __restrict__ c, const Group* __restrict__ items, uint32_t items_cap,
 			}
 			__syncwarp();
 			any = any || (cnt_h + cnt_l) != 0;
+			// The last 32-wide step of the order-P list would leave lanes idle: fill them with pairs taken from the tail of the
+			// order-(P-1) list (evaluating a pair at the higher order costs nothing there and only improves it).
+			const uint32_t take = min((32u - (cnt_h & 31u)) & 31u, cnt_l);
+			cnt_l -= take;
+			const uint32_t tot_h = cnt_h + take;
+			auto hi_slot = [&](uint32_t k) -> uint32_t { return k < cnt_h ? S.list_hi[w][k] : S.list_lo[w][cnt_l + (k - cnt_h)]; };
 			// order P pairs; the slot number and geometry of the next iteration are fetched before the math of this one
 			{
 				uint32_t k = lane;
 				uint32_t sc = 0; float4 gc = make_float4(0.f, 0.f, 0.f, 0.f);
-				if (k < cnt_h) { sc = s0 + S.list_hi[w][k]; gc = S.sgeom[cur][sc]; }
-				while (k < cnt_h) {
+				if (k < tot_h) { sc = s0 + hi_slot(k); gc = S.sgeom[cur][sc]; }
+				while (k < tot_h) {
 					const uint32_t kn = k + 32;
 					uint32_t sn = 0; float4 gn = gc;
-					if (kn < cnt_h) { sn = s0 + S.list_hi[w][kn]; gn = S.sgeom[cur][sn]; }
+					if (kn < tot_h) { sn = s0 + hi_slot(kn); gn = S.sgeom[cur][sn]; }
 					m2l_one<P, P>(Lacc, tg, gc, S.sM[cur] + sc * STRIDE, eps2);
 					k = kn; sc = sn; gc = gn;
 				}
@@ -203,13 +209,21 @@ k_m2l(Ctrl* __restrict__ c, const Group* __restrict__ items, uint32_t items_cap,
 			fetch(ch + 3, id_n, mk_n);
 		}
 		if (!any) continue;  // warp-uniform
-		// warp reduction, then lane a adds coefficient a (L[0], the potential term, is not carried)
+		// warp reduction (transposing: 31 shuffles for 32 coefficients), then lane a-1 adds coefficient a
+		// (L[0], the potential term, is not carried)
+		{
+			float v[32];
 #pragma unroll
-		for (int a = 1; a < E::NC; ++a) {
-			float v = Lacc[a];
+			for (int a = 0; a < 32; ++a) v[a] = a + 1 < E::NC ? Lacc[a + 1] : 0.0f;
+			transpose_reduce32(v, lane);
+			if (lane + 1u < (unsigned) E::NC) atomicAdd(L + (size_t) target * STRIDE + lane + 1u, v[0]);
 #pragma unroll
-			for (int d = 16; d >= 1; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-			if (lane == (unsigned) (a & 31)) atomicAdd(L + (size_t) target * STRIDE + a, v);
+			for (int a = 33; a < E::NC; ++a) {
+				float x = Lacc[a];
+#pragma unroll
+				for (int d = 16; d >= 1; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
+				if (lane == (unsigned) (a & 31)) atomicAdd(L + (size_t) target * STRIDE + a, x);
+			}
 		}
 	}
 }
