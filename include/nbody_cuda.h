@@ -60,7 +60,8 @@ enum {
 	NBODY_FLAG_KEEP_LISTS = 1u,   /* keep interaction lists after step() for nbody_cuda_get_lists */
 	NBODY_FLAG_NO_INTEGRATE = 2u, /* step() computes accelerations only (state is re-ordered, not advanced) */
 	NBODY_FLAG_DIRECT = 4u,       /* all-pairs direct sum instead of the FMM (validation / P2P microbenchmark) */
-	NBODY_FLAG_CUB_SORT = 8u      /* sort with CUB's DeviceRadixSort instead of the built-in radix sort (comparison only) */
+	NBODY_FLAG_CUB_SORT = 8u,     /* sort with CUB's DeviceRadixSort instead of the built-in radix sort (comparison only) */
+	NBODY_FLAG_STATIC_PARTITION = 16u /* multi-GPU: equal particle counts per rank every step instead of per-step load rebalancing */
 };
 
 typedef struct nbody_cuda_config {
@@ -97,7 +98,7 @@ typedef struct nbody_cuda_stats {
 	uint64_t device_bytes;     /* bytes currently allocated on the device */
 	/* device time of the last step, milliseconds (CUDA events on the compute stream) */
 	float ms_total, ms_sort, ms_tree, ms_upsweep, ms_traverse, ms_m2l, ms_l2l, ms_leaf, ms_comm;
-	float _pad;
+	float work_imbalance;      /* multi-GPU: max over ranks / mean over ranks - 1 of the owned-slice device time of the last step */
 } nbody_cuda_stats;
 
 typedef struct nbody_cuda_sim nbody_cuda_sim; /* opaque; single-threaded use */
@@ -172,6 +173,12 @@ int nbody_cuda_owned_range(nbody_cuda_sim* sim, uint64_t* first, uint64_t* count
  * counterparts of get_particles / set_particles. set_ is collective: every rank must call it. */
 int nbody_cuda_get_owned_particles(nbody_cuda_sim* sim, nbody_particle* out, uint64_t capacity);
 int nbody_cuda_set_owned_particles(nbody_cuda_sim* sim, const nbody_particle* particles, uint64_t n);
+/* Per-step load rebalancing, the host-side rule on its own (no device needed): from last step's slice boundaries
+ * (world + 1 entries, first 0, last n) and each rank's device time for its slice, the wanted boundaries of the next
+ * step (world + 1 entries; before they are snapped to leaf boundaries). damping in (0,1]: fraction of the correction
+ * applied per step (the library uses 0.5); <= 0 returns the input boundaries. step() applies this internally unless
+ * NBODY_FLAG_STATIC_PARTITION is set. */
+int nbody_cuda_rebalance(int world, const uint32_t* boundaries, const float* work_ms, float damping, uint32_t* out);
 
 const char* nbody_cuda_last_error(void);
 

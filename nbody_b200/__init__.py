@@ -18,14 +18,14 @@ LIB_PATH = os.environ.get("NBODY_CUDA_LIB") or os.path.join(_HERE, "libnbody_cud
 PARTICLE_FLOATS = 12  # 48-byte AoS record: position[4], velocity[4], mass, charge, pad[2]
 
 KICK_DRIFT, EXPLICIT_EULER = 0, 1
-FLAG_KEEP_LISTS, FLAG_NO_INTEGRATE, FLAG_DIRECT, FLAG_CUB_SORT = 1, 2, 4, 8
+FLAG_KEEP_LISTS, FLAG_NO_INTEGRATE, FLAG_DIRECT, FLAG_CUB_SORT, FLAG_STATIC_PARTITION = 1, 2, 4, 8, 16
 
 EXPORTED_SYMBOLS = [
     "nbody_cuda_default_config", "nbody_cuda_create", "nbody_cuda_destroy", "nbody_cuda_set_particles", "nbody_cuda_step",
     "nbody_cuda_num_particles", "nbody_cuda_get_particles", "nbody_cuda_get_permutation", "nbody_cuda_get_accelerations",
     "nbody_cuda_get_keys", "nbody_cuda_get_tree", "nbody_cuda_get_lists", "nbody_cuda_get_expansions", "nbody_cuda_get_stats",
     "nbody_cuda_direct_field", "nbody_cuda_comm_unique_id", "nbody_cuda_create_distributed", "nbody_cuda_owned_range",
-    "nbody_cuda_get_owned_particles", "nbody_cuda_set_owned_particles",
+    "nbody_cuda_get_owned_particles", "nbody_cuda_set_owned_particles", "nbody_cuda_rebalance",
     "nbody_cuda_last_error",
 ]
 
@@ -41,7 +41,7 @@ class Stats(C.Structure):
     _fields_ = [(k, C.c_uint64) for k in ("n_particles", "n_nodes", "n_leaves", "n_levels", "m2l_entries", "m2l_interactions",
                                           "m2l_interactions_low", "p2p_entries", "p2p_interactions", "near_entries", "retries", "device_bytes")] + \
                [(k, C.c_float) for k in ("ms_total", "ms_sort", "ms_tree", "ms_upsweep", "ms_traverse", "ms_m2l", "ms_l2l",
-                                         "ms_leaf", "ms_comm", "_pad")]
+                                         "ms_leaf", "ms_comm", "work_imbalance")]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if not k.startswith("_")}

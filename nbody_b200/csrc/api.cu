@@ -11,7 +11,8 @@ namespace nbody {
 static thread_local std::string g_error;
 void set_error(const std::string& msg) { g_error = msg; }
 size_t sort_temp_bytes(uint64_t n);
-int comm_step_exchange(Sim& s);                     // comm.cu
+int comm_step_exchange(Sim& s, float own_ms);       // comm.cu
+float comm_work_imbalance(const Sim& s);            // comm.cu
 void comm_destroy(Sim& s);                          // comm.cu
 int comm_partition(Sim& s);                         // comm.cu
 int comm_exchange_aos(Sim& s);                      // comm.cu
@@ -150,7 +151,9 @@ int run_pipeline(Sim& s) {
 	if (s.comm && s.ctrl_host->status == 0) {
 		// distributed: the slice boundaries were computed on the device; now that the host has them, exchange the slices
 		comm_adopt_partition(s);
-		if ((rc = comm_step_exchange(s))) return rc;
+		float own_ms = 0.0f;  // traversal .. leaf kernel: the stages this rank runs for its own slice only
+		NB_CUDA_CHECK(cudaEventElapsedTime(&own_ms, s.ev[3], s.ev[7]));
+		if ((rc = comm_step_exchange(s, own_ms))) return rc;
 		NB_CUDA_CHECK(cudaEventRecord(s.ev[8], st));
 		NB_CUDA_CHECK(cudaStreamSynchronize(st));
 	} else {
@@ -362,6 +365,7 @@ int nbody_cuda_step(nbody_cuda_sim* sim, float* time_out) {
 	auto ms = [&](int a, int b) { float v = 0; cudaEventElapsedTime(&v, s->ev[a], s->ev[b]); return v; };
 	t.ms_sort = ms(0, 1); t.ms_tree = ms(1, 2); t.ms_upsweep = ms(2, 3); t.ms_traverse = ms(3, 4); t.ms_m2l = ms(4, 5); t.ms_l2l = ms(5, 6);
 	t.ms_leaf = ms(6, 7); t.ms_comm = ms(7, 8); t.ms_total = ms(0, 8);
+	t.work_imbalance = comm_work_imbalance(*s);
 	if (s->cfg.flags & NBODY_FLAG_DIRECT) t.p2p_interactions = s->n * (s->n - 1);
 	if (time_out) *time_out = s->time;
 	return NBODY_OK;

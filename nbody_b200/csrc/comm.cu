@@ -17,6 +17,7 @@
 #include <cstring>
 #include <vector>
 
+#include "balance.h"
 #include "common.cuh"
 
 namespace nbody {
@@ -65,8 +66,13 @@ void destroy_for_comm(Sim* s);
 struct Comm {
 	ncclComm_t comm = nullptr;
 	int rank = 0, world = 1;
-	uint32_t* part_host = nullptr;  // pinned, world + 1
+	uint32_t* part_host = nullptr;  // pinned, world + 1: boundaries of the last step
+	float* work_host = nullptr;     // pinned, world: per-rank device time of the owned-slice stages of the last step
+	float* work_dev = nullptr;      // device, world
+	bool have_work = false;         // work_host describes the partition in part_host
 };
+
+struct PartitionTargets { uint32_t t[17]; };
 
 #define NB_NCCL_CHECK(expr)                                                                  \
 	do {                                                                                        \
@@ -77,13 +83,14 @@ struct Comm {
 		}                                                                                         \
 	} while (0)
 
-// Boundary r = r*N/world, moved down to the first particle of the leaf that contains it.
-__global__ void k_partition(Ctrl* c, int world, uint32_t n, const uint2* __restrict__ info, const uint32_t* __restrict__ nbegin) {
+// Boundary r = the wanted position, moved down to the first particle of the leaf that contains it.
+__global__ void k_partition(Ctrl* c, int world, uint32_t n, const PartitionTargets want, const uint2* __restrict__ info,
+                            const uint32_t* __restrict__ nbegin) {
 	const int r = threadIdx.x;
 	if (r > world) return;
-	uint32_t p = (uint32_t) ((uint64_t) n * r / world);
+	uint32_t p = want.t[r] < n ? want.t[r] : n;
 	if (r == 0) p = 0;
-	if (r == world) { c->part[r] = n; return; }
+	if (r == world || p >= n) { c->part[r] = n; return; }
 	uint32_t node = 0;
 	for (;;) {
 		const uint2 nf = info[node];
@@ -99,9 +106,17 @@ __global__ void k_partition(Ctrl* c, int world, uint32_t n, const uint2* __restr
 }
 
 // Enqueues the partition kernel; the kernels of the step read the boundaries from the control block on the device.
+// First step (or NBODY_FLAG_STATIC_PARTITION): equal particle counts. Afterwards: the boundaries follow the measured
+// per-rank work of the previous step (balance.h).
 int comm_partition(Sim& s) {
 	Comm& cm = *s.comm;
-	k_partition<<<1, 32, 0, s.stream>>>(s.ctrl, cm.world, (uint32_t) s.n, s.info, s.nbegin);
+	PartitionTargets want{};
+	if (cm.have_work && !(s.cfg.flags & NBODY_FLAG_STATIC_PARTITION)) {
+		rebalance_boundaries(cm.world, cm.part_host, cm.work_host, 0.5f, want.t);
+	} else {
+		for (int r = 0; r <= cm.world; ++r) want.t[r] = (uint32_t) ((uint64_t) s.n * r / cm.world);
+	}
+	k_partition<<<1, 32, 0, s.stream>>>(s.ctrl, cm.world, (uint32_t) s.n, want, s.info, s.nbegin);
 	return NBODY_OK;
 }
 
@@ -129,12 +144,28 @@ static int exchange(Sim& s, void* buf, size_t elem_bytes) {
 
 int comm_exchange_aos(Sim& s) { return exchange(s, s.aos_dev, sizeof(nbody_particle)); }
 
-int comm_step_exchange(Sim& s) {
+// `own_ms`: device time this rank spent on the stages it runs for its own slice only (the input of the next
+// step's rebalancing); all-gathered next to the slices, on the host after the step's final synchronisation.
+int comm_step_exchange(Sim& s, float own_ms) {
+	Comm& cm = *s.comm;
 	int rc;
 	if ((rc = exchange(s, s.posq[0], sizeof(float4)))) return rc;
 	if ((rc = exchange(s, s.velm[0], sizeof(float4)))) return rc;
 	s.acc_partial = true;  // accelerations stay rank-local until somebody asks for them (comm_exchange_acc)
+	cm.work_host[cm.rank] = own_ms;
+	NB_CUDA_CHECK(cudaMemcpyAsync(cm.work_dev + cm.rank, cm.work_host + cm.rank, sizeof(float), cudaMemcpyHostToDevice, s.stream));
+	NB_NCCL_CHECK(g_nccl.AllGather(cm.work_dev + cm.rank, cm.work_dev, 1, ncclFloat, cm.comm, s.stream));
+	NB_CUDA_CHECK(cudaMemcpyAsync(cm.work_host, cm.work_dev, sizeof(float) * cm.world, cudaMemcpyDeviceToHost, s.stream));
+	cm.have_work = true;  // valid once the caller has synchronised the stream
 	return NBODY_OK;
+}
+
+// max over ranks / mean over ranks - 1 of the last step's owned-slice work (0 on a single GPU or before the first step)
+float comm_work_imbalance(const Sim& s) {
+	if (!s.comm || !s.comm->have_work) return 0.0f;
+	float mx = 0.0f, sum = 0.0f;
+	for (int r = 0; r < s.comm->world; ++r) { mx = s.comm->work_host[r] > mx ? s.comm->work_host[r] : mx; sum += s.comm->work_host[r]; }
+	return sum > 0.0f ? mx * s.comm->world / sum - 1.0f : 0.0f;
 }
 
 int comm_exchange_acc(Sim& s) {
@@ -149,6 +180,8 @@ void comm_destroy(Sim& s) {
 	if (!s.comm) return;
 	if (s.comm->comm) g_nccl.CommDestroy(s.comm->comm);
 	if (s.comm->part_host) cudaFreeHost(s.comm->part_host);
+	if (s.comm->work_host) cudaFreeHost(s.comm->work_host);
+	if (s.comm->work_dev) cudaFree(s.comm->work_dev);
 	delete s.comm;
 	s.comm = nullptr;
 }
@@ -158,6 +191,12 @@ void comm_destroy(Sim& s) {
 using namespace nbody;
 
 extern "C" {
+
+int nbody_cuda_rebalance(int world, const uint32_t* boundaries, const float* work_ms, float damping, uint32_t* out) {
+	if (!boundaries || !work_ms || !out || world < 1 || world > 16) { set_error("bad argument"); return NBODY_ERR_INVALID; }
+	rebalance_boundaries(world, boundaries, work_ms, damping, out);
+	return NBODY_OK;
+}
 
 int nbody_cuda_comm_unique_id(uint8_t* id) {
 	if (!id) { set_error("NULL argument"); return NBODY_ERR_INVALID; }
@@ -185,7 +224,9 @@ int nbody_cuda_create_distributed(const nbody_cuda_config* cfg, const nbody_part
 	Comm& cm = *s->comm;
 	cm.rank = rank; cm.world = world;
 	s->rank = rank;
-	if (cudaMallocHost((void**) &cm.part_host, sizeof(uint32_t) * (world + 1)) != cudaSuccess) { set_error("pinned allocation failed"); return fail(NBODY_ERR_CUDA); }
+	if (cudaMallocHost((void**) &cm.part_host, sizeof(uint32_t) * (world + 1)) != cudaSuccess ||
+	    cudaMallocHost((void**) &cm.work_host, sizeof(float) * world) != cudaSuccess ||
+	    cudaMalloc((void**) &cm.work_dev, sizeof(float) * world) != cudaSuccess) { set_error("allocation of the partition tables failed"); return fail(NBODY_ERR_CUDA); }
 	ncclUniqueId u;
 	std::memcpy(&u, id, 128);
 	ncclResult_t nr = g_nccl.CommInitRank(&cm.comm, world, u, rank);

@@ -212,16 +212,17 @@ __global__ void __launch_bounds__(kLeafWarps * 32, kLeafMinCtas) k_leaf(const Le
 					uint32_t pc = 0;
 #pragma unroll
 					for (int i = 0; i < kLeafTile / 32; ++i) {
-						if (32u * i >= (fill + kLeafPad - 1u) / kLeafPad * kLeafPad) break;
+						if (32u * i >= fill) break;
 						// bit p of the bitmap: some entry ends at flat position p; entry of slot f = number of ends <= f
 						const unsigned word = __reduce_or_sync(0xffffffffu, (full && (inc >> 5) == (uint32_t) i) ? 1u << (inc & 31u) : 0u);
 						const uint32_t f = 32u * i + lane;
 						const uint32_t e = pc + __popc(word & le_mask);
 						const uint32_t s0 = __shfl_sync(0xffffffffu, src0, e & 31u);
 						if (f < fill) leaf_cp_async16(tile + f, a.posq + (s0 + f));
-						else if (f < (fill + kLeafPad - 1u) / kLeafPad * kLeafPad) tile[f] = make_float4(0.f, 0.f, 0.f, 0.f);  // pad to whole row groups: zero charge
 						pc += __popc(word);
 					}
+					// pad to whole row groups with zero-charge sources (only the last tile of a segment is short)
+					for (uint32_t f = fill + lane; f < (fill + kLeafPad - 1u) / kLeafPad * kLeafPad; f += 32u) tile[f] = make_float4(0.f, 0.f, 0.f, 0.f);
 					leaf_cp_async_commit();
 				};
 				uint2 ent_cur = make_uint2(0u, 0u), ent_nxt = make_uint2(0u, 0u);

@@ -7,8 +7,9 @@
 //
 // M2L kernel: one CTA per work item = 8 sibling targets (one warp each) sharing one
 // candidate list. Candidate geometry + multipoles are staged in shared memory once
-// per CTA in chunks of 128 (coalesced float4 loads of 16-byte-aligned records; the
-// record stride of 36/20/12 floats makes the per-lane LDS.128 reads conflict-free),
+// per CTA in chunks of 256 (coalesced 16-byte copies; only the multipole orders 0..P-1 a
+// field-only M2L reads are staged: 20/12/4 floats per candidate, a stride that keeps the
+// per-lane LDS.128 reads of consecutive slots conflict-free),
 // so a multipole is read from L2 once per 8 targets. Each lane owns one candidate at
 // a time and keeps its own partial local expansion in registers; one shuffle
 // reduction per target at the end, then RED.ADD into L. FP32-FMA bound: per
@@ -59,8 +60,8 @@ __device__ __forceinline__ void m2l_two(float (&Lacc)[Expansion<P>::NC], const f
 template <int P, int NT>
 struct M2LShared {
 	static constexpr int CH = NT == 8 ? 256 : 32;   // candidate slots per chunk = threads per CTA
-	static constexpr int STRIDE = coef_stride(P);
-	float sM[2][CH * STRIDE];
+	static constexpr int MS = coef_stride(P - 1);  // a field-only M2L reads multipole orders 0..P-1 only (|n| >= 1, |n|+|m| <= P)
+	float sM[2][CH * MS];
 	float4 sgeom[2][CH];
 	uint32_t sid[3][CH];                     // ids / masks of chunk k live in ring slot k % 3 (published two chunks ahead)
 	uint8_t smask[3][CH], smask_lo[3][CH];
@@ -85,7 +86,8 @@ k_m2l(Ctrl* __restrict__ c, const Group* __restrict__ items, uint32_t items_cap,
 	using SH = M2LShared<P, NT>;
 	constexpr int CH = SH::CH;
 	constexpr int STRIDE = coef_stride(P);
-	constexpr int S4 = STRIDE / 4;
+	constexpr int S4 = STRIDE / 4;          // 16-byte pieces per multipole record in global memory
+	constexpr int MS = SH::MS, MS4 = MS / 4;  // floats / pieces staged per candidate
 	constexpr int PL = P > 2 ? P - 1 : P;  // the low evaluation order
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	SH& S = *reinterpret_cast<SH*>(smem_raw);
@@ -121,8 +123,8 @@ k_m2l(Ctrl* __restrict__ c, const Group* __restrict__ items, uint32_t items_cap,
 			const uint32_t* ids = S.sid[chunk % 3];
 			float4* dst = reinterpret_cast<float4*>(S.sM[buf]);
 #pragma unroll
-			for (int r = 0; r < S4; ++r) {
-				const uint32_t piece = tid + r * CH, slot = piece / S4, j = piece - slot * S4;
+			for (int r = 0; r < MS4; ++r) {
+				const uint32_t piece = tid + r * CH, slot = piece / MS4, j = piece - slot * MS4;
 				if (slot < ns) cp_async16(dst + piece, M4 + (size_t) ids[slot] * S4 + j);
 			}
 			if (tid < ns) cp_async16(&S.sgeom[buf][tid], geom + ids[tid]);
@@ -179,7 +181,7 @@ k_m2l(Ctrl* __restrict__ c, const Group* __restrict__ items, uint32_t items_cap,
 					const uint32_t kn = k + 32;
 					uint32_t sn = 0; float4 gn = gc;
 					if (kn < tot_h) { sn = s0 + hi_slot(kn); gn = S.sgeom[cur][sn]; }
-					m2l_one<P, P>(Lacc, tg, gc, S.sM[cur] + sc * STRIDE, eps2);
+					m2l_one<P, P>(Lacc, tg, gc, S.sM[cur] + sc * MS, eps2);
 					k = kn; sc = sn; gc = gn;
 				}
 			}
@@ -195,13 +197,13 @@ k_m2l(Ctrl* __restrict__ c, const Group* __restrict__ items, uint32_t items_cap,
 						san = s0 + S.list_lo[w][base + 64 + lane]; sbn = s0 + S.list_lo[w][base + 96 + lane];
 						gan = S.sgeom[cur][san]; gbn = S.sgeom[cur][sbn];
 					}
-					m2l_two<P, PL>(Lacc, tg, ga, S.sM[cur] + sa * STRIDE, gb, S.sM[cur] + sb * STRIDE, eps2);
+					m2l_two<P, PL>(Lacc, tg, ga, S.sM[cur] + sa * MS, gb, S.sM[cur] + sb * MS, eps2);
 					sa = san; sb = sbn; ga = gan; gb = gbn;
 				}
 			}
 			for (uint32_t k = base + lane; k < cnt_l; k += 32) {
 				const uint32_t s = s0 + S.list_lo[w][k];
-				m2l_one<P, PL>(Lacc, tg, S.sgeom[cur][s], S.sM[cur] + s * STRIDE, eps2);
+				m2l_one<P, PL>(Lacc, tg, S.sgeom[cur][s], S.sM[cur] + s * MS, eps2);
 			}
 			// ids of chunk ch+2 become visible at the next barrier (ring slot (ch+2)%3 was last read for chunk ch-1,
 			// which every warp finished before this iteration's barrier); the registers then prefetch chunk ch+3

@@ -49,6 +49,6 @@ def test_two_gpu_step_matches_single_gpu():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs (run tools/mg_check.py under torchrun on a multi-GPU box)")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-                        "--master-port", "29655", os.path.join(ROOT, "tools", "mg_check.py"), "200000", "2"],
+                        "--master-port", "29655", os.path.join(ROOT, "tools", "mg_check.py"), "200000", "4"],
                        capture_output=True, text=True, timeout=300)
     assert "MG_CHECK PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

@@ -182,7 +182,7 @@ def test_edge_cases():
     P = workloads.uniform_cube(300)
     P[:40, 0:3] = (0.3, 0.3, 0.3)
     for md in (21, 6):
-        sim = make_sim(P, max_depth=md)
+        sim = make_sim(P, max_depth=md, low_order_tau=0.0)  # every pair at order P: the device must equal the FP64 FMM
         sim.step()
         o = sorted_system(P, max_depth=md)
         assert np.array_equal(sim.keys(), o["keys"])
@@ -193,7 +193,7 @@ def test_edge_cases():
         assert np.array_equal(packed(m2l), directed(m2l_o)) and np.array_equal(packed(p2p), directed(p2p_o))
         gd = oracle.direct_field(o["posq"], None, 0.01)
         scale = (o["P"][:, 9] / o["P"][:, 8])[:, None]
-        g_fmm = o["tree"].fmm_field(o["posq"], 4, 0.01, low_order_tau=float(sim.config.low_order_tau))
+        g_fmm = o["tree"].fmm_field(o["posq"], 4, 0.01, low_order_tau=0.0)
         assert rms_rel(sim.accelerations(), g_fmm * scale) < 2e-6      # identical to the FP64 FMM over the same lists
         assert rms_rel(sim.accelerations(), gd * scale) < 6e-3         # a 300-body system with a 40-body point clump
         sim.close()
@@ -211,17 +211,17 @@ def test_edge_cases():
     assert np.array_equal(packed(m2l), directed(m2l_o)) and np.array_equal(packed(p2p), directed(p2p_o))
     assert np.all(np.isfinite(sim.accelerations()))
     sim.close()
-    # a leaf far beyond the P2P tile size (600 coincident particles) exercises the streaming path
+    # a leaf far beyond the P2P tile size (600 coincident particles): one source entry straddles several tiles
     P = workloads.uniform_cube(2000)
     P[:600, 0:3] = (0.7, 0.2, 0.4)
-    sim = make_sim(P)
+    sim = make_sim(P, low_order_tau=0.0)
     sim.step()
     o = sorted_system(P)
     gd = oracle.direct_field(o["posq"], None, 0.01)
     scale = (o["P"][:, 9] / o["P"][:, 8])[:, None]
     o["tree"].traverse(0.5)
-    g_fmm = o["tree"].fmm_field(o["posq"], 4, 0.01, low_order_tau=float(sim.config.low_order_tau))
-    assert rms_rel(sim.accelerations(), g_fmm * scale) < 2e-6          # streaming path == FP64 FMM over the same lists
+    g_fmm = o["tree"].fmm_field(o["posq"], 4, 0.01, low_order_tau=0.0)
+    assert rms_rel(sim.accelerations(), g_fmm * scale) < 2e-6          # straddling entries == FP64 FMM over the same lists
     assert rms_rel(sim.accelerations(), gd * scale) < 6e-3             # 30 % of the mass in one point: the method's own error
     sim.close()
 

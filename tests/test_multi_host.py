@@ -82,3 +82,44 @@ def test_cpp_wrapper_compiles_and_fails_loudly_without_gpu(tmp_path):
         pytest.skip("a GPU is present: covered by the gpu tests")
     r = subprocess.run([exe, "--n", "64", "--steps", "1", "--quiet", "--csv", "none"], capture_output=True, text=True)
     assert r.returncode == 1 and "no CPU fallback" in r.stderr
+
+
+def test_rebalance_rule():
+    """Per-step load rebalancing, host side (nbody_b200/csrc/balance.h through the C ABI; no device involved)."""
+    import ctypes as C
+    import nbody_b200
+    if not os.path.exists(nbody_b200.LIB_PATH):
+        nbody_b200.build_library()
+    L = C.CDLL(nbody_b200.LIB_PATH)
+
+    def rebalance(part, work, damping):
+        world = len(work)
+        out = (C.c_uint32 * (world + 1))()
+        rc = L.nbody_cuda_rebalance(world, (C.c_uint32 * (world + 1))(*part), (C.c_float * world)(*work), C.c_float(damping), out)
+        assert rc == 0
+        return list(out)
+
+    n = 1 << 20
+    even = [n * r // 4 for r in range(5)]
+    assert rebalance(even, [10.0, 10.0, 10.0, 10.0], 0.5) == even              # balanced: nothing moves
+    assert rebalance(even, [10.0, 0.0, 10.0, 10.0], 0.5) == even               # unusable timing: keep the partition
+    assert rebalance(even, [10.0, 12.0, 9.0, 11.0], 0.0) == even               # damping 0: keep the partition
+    slow0 = rebalance(even, [20.0, 10.0, 10.0, 10.0], 1.0)                     # rank 0 is twice as slow: its slice shrinks
+    assert slow0[0] == 0 and slow0[4] == n and slow0 == sorted(slow0)
+    assert abs(slow0[1] - n * 0.25 * (12.5 / 20.0)) <= 1                        # 12.5 of its 20 units of work stay
+    assert abs(slow0[2] - (n // 4 + n * 0.25 * 0.5)) <= 1                       # total 50: the second cut is 5 units into rank 1
+    half = rebalance(even, [20.0, 10.0, 10.0, 10.0], 0.5)
+    assert abs(half[1] - (even[1] + slow0[1]) / 2) <= 1                         # damping: half of the correction per step
+    # iterating the rule on a fixed cost density converges to equal work (cost 4 per particle in the first quarter, 1 elsewhere)
+    def work_of(part):
+        cum = lambda x: 4.0 * min(x, n // 4) + max(0, x - n // 4)
+        return [cum(part[r + 1]) - cum(part[r]) for r in range(4)]
+    part = even
+    for _ in range(12):
+        part = rebalance(part, work_of(part), 0.5)
+    w = work_of(part)
+    assert max(w) / (sum(w) / 4) - 1.0 < 0.01
+    # degenerate inputs
+    assert rebalance([0, 7], [3.0], 0.5) == [0, 7]
+    two = rebalance([0, 0, 100], [1.0, 9.0], 1.0)                              # an empty slice that reported time receives work
+    assert two[0] == 0 and two[2] == 100 and 0 < two[1] <= 100

@@ -12,16 +12,20 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 200000
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+kind = sys.argv[3] if len(sys.argv) > 3 else "plummer"
 lo, hi = n * rank // world, n * (rank + 1) // world
-P = workloads.plummer(hi - lo, start=lo, n_total=n)
+P = workloads.plummer(hi - lo, start=lo, n_total=n) if kind == "plummer" else workloads.GENERATORS[kind](n)[lo:hi]
 uid = [nbody_b200.comm_unique_id() if rank == 0 else None]
 dist.broadcast_object_list(uid, src=0)
 sim = nbody_b200.CudaSimulation([1, 1, 1], P, 1e-3, device=local,
                                 _distributed={"unique_id": uid[0], "n_global": n, "global_offset": lo, "rank": rank, "world": world})
 ranges = []
 t0 = time.time()
-for _ in range(steps):
+for k in range(steps):
     sim.step()
+    st_k = sim.stats()
+    if rank == 0:
+        print(f"step {k}: owned {sim.owned_range()} work imbalance {st_k['work_imbalance']:.3f} ms_total {st_k['ms_total']:.2f}", flush=True)
 torch.cuda.synchronize()
 dt = time.time() - t0
 out = sim.particles()
@@ -33,7 +37,7 @@ if rank == 0:
     print("owned ranges:", [(a, b) for a, b, *_ in allr], "ms_total per rank:", [round(x[2], 2) for x in allr], flush=True)
     cover = sorted((a, a + b) for a, b, *_ in allr)
     ok &= cover[0][0] == 0 and cover[-1][1] == n and all(cover[i][1] == cover[i + 1][0] for i in range(world - 1))
-    ref = nbody_b200.CudaSimulation([1, 1, 1], workloads.plummer(n), 1e-3, device=local)
+    ref = nbody_b200.CudaSimulation([1, 1, 1], workloads.GENERATORS[kind](n), 1e-3, device=local)
     for _ in range(steps):
         ref.step()
     r = ref.particles()
