@@ -8,10 +8,12 @@ A "step" is one Simulation::step() on the metric's configuration: a Plummer sphe
 of N = 16M particles (BASELINE.json configs[2]), at the reference's physics constants
 (MAC 0.5, softening 0.01). The octree node capacity — hard-coded to 8 in the reference
 with a "should be adjustable" FIXME (src/open_cl_simulation.cpp:41-47) — is a tuning
-parameter here: the headline runs at 32, and the same workload at the reference's 8 is
+parameter here: the headline runs at 48, and the same workload at the reference's 8 is
 measured in the same run and reported under "reference_capacity". One JSON line on
 stdout (rank 0).
-  value     whole-job particle-steps/s, state resident in HBM
+  value     whole-job particle-steps/s, state resident in HBM: N * K / wall time of K blocking step() calls between
+            barrier + synchronize pairs, max over ranks; device_ms_per_step is the same interval seen by CUDA events
+            on the solver's own stream (max over ranks) and must agree with ms_per_step
   e2e       the same through the C ABI with HOST buffers: set_particles (H2D) +
             step + get_particles (D2H) inside the timed region
   roofline  dominant kernel vs the FP32 FMA peak (this path is FP32-pipe bound by
@@ -48,8 +50,8 @@ def measured_peaks():
 
 def measured_traffic(kernel, args):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full
-    capture of exactly this workload (profiles/r01h_traffic.json); None for any other workload."""
-    p = os.path.join(ROOT, "profiles", "r01h_traffic.json")
+    capture of exactly this workload (profiles/r01k_traffic.json); None for any other workload."""
+    p = os.path.join(ROOT, "profiles", "r01k_traffic.json")
     try:
         with open(p) as f:
             d = json.load(f)
@@ -170,8 +172,8 @@ def main():
     ap.add_argument("--workload", default="plummer", choices=["plummer", "uniform", "two_galaxies"])
     ap.add_argument("--n", type=int, default=1 << 24)
     ap.add_argument("--order", type=int, default=4)
-    ap.add_argument("--leaf-capacity", type=int, default=32,
-                    help="octree node capacity; the reference hard-codes 8 with a FIXME (src/open_cl_simulation.cpp:41-47), 32 is the B200 tuning")
+    ap.add_argument("--leaf-capacity", type=int, default=48,
+                    help="octree node capacity; the reference hard-codes 8 with a FIXME (src/open_cl_simulation.cpp:41-47), 48 is the B200 tuning")
     ap.add_argument("--no-reference-capacity", action="store_true", help="skip the additional measurement at the reference's capacity 8")
     ap.add_argument("--dt", type=float, default=1e-3)
     ap.add_argument("--cpu-sample", type=int, default=16384)
@@ -243,10 +245,12 @@ def main():
                     cnts[key] = v
         barrier()
         dt = time.perf_counter() - t0
+        dev_ms = sums.get("ms_total", 0.0)  # CUDA events on the solver's stream, first launch to last of every step
         if world > 1:
-            tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            tt = torch.tensor([dt, dev_ms], device="cuda", dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            dt = float(tt.item())
+            dt, dev_ms = float(tt[0].item()), float(tt[1].item())
+        cnts["device_ms_per_step"] = dev_ms / k
         return dt, {key: v / k for key, v in sums.items()}, cnts
 
     sim = make_sim(args.leaf_capacity)
@@ -296,7 +300,7 @@ def main():
         sim8 = make_sim(8)
         dt8, st8, c8 = timed_steps(sim8, 3, min(args.steps, 3))
         sim8.close()
-        ref_cap = {"leaf_capacity": 8, "value": n * min(args.steps, 3) / dt8, "unit": UNIT, "ms_per_step": 1e3 * dt8 / min(args.steps, 3),
+        ref_cap = {"leaf_capacity": 8, "value": n * min(args.steps, 3) / dt8, "unit": UNIT, "ms_per_step": 1e3 * dt8 / min(args.steps, 3), "device_ms_per_step": c8.pop("device_ms_per_step", None),
                    "stage_ms": st8, "m2l_interactions": c8.get("m2l_interactions"), "p2p_interactions": c8.get("p2p_interactions")}
     p2p_micro = None
     if rank == 0:
@@ -331,7 +335,7 @@ def main():
         }
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
-            "ms_per_step": 1e3 * elapsed / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "ms_per_step": 1e3 * elapsed / K, "device_ms_per_step": counts.pop("device_ms_per_step", None), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": f"{args.workload} sphere N={n}" if args.workload == "plummer" else f"{args.workload} N={n}",
                        "order": args.order, "leaf_capacity": args.leaf_capacity, "mac_ratio": 0.5, "softening": 0.01,

@@ -28,7 +28,7 @@ constexpr int kLeafChunk = 8;   // node ids per work ticket
 #endif
 constexpr int kLeafG = NBODY_LEAF_G;  // most targets per block (3 accumulators each, in registers)
 #ifndef NBODY_LEAF_ROWS
-#define NBODY_LEAF_ROWS 2
+#define NBODY_LEAF_ROWS 4
 #endif
 constexpr int kLeafRows = NBODY_LEAF_ROWS;  // 32-source rows in flight per lane (independent dependency chains per target)
 constexpr uint32_t kLeafPad = 32u * kLeafRows;  // tiles are padded with zero-charge sources to a multiple of this
