@@ -60,6 +60,14 @@ public:
 		_log << "Creating the CUDA simulation (" << particles.size() << " particles).\n";
 		check(nbody_cuda_create(&cfg, reinterpret_cast<const nbody_particle*>(particles.data()), particles.size(), &_sim));
 	}
+	// Continue a run from a checkpoint written by saveCheckpoint() (the reference cannot resume: its particles.csv drops
+	// velocities, masses and charges, src/main.cpp:88-95). `config` (optional) replaces the stored configuration.
+	CudaSimulation(const std::string& checkpointPath, std::ostream& log, const nbody_cuda_config* config = nullptr)
+	    : _log(log), _time(0.0f) {
+		_log << "Restoring the CUDA simulation from " << checkpointPath << ".\n";
+		check(nbody_cuda_checkpoint_load(checkpointPath.c_str(), config, &_sim));
+		check(nbody_cuda_get_time(_sim, &_time, nullptr));
+	}
 	CudaSimulation(const CudaSimulation&) = delete;
 	CudaSimulation& operator=(const CudaSimulation&) = delete;
 	~CudaSimulation() override { nbody_cuda_destroy(_sim); }
@@ -85,6 +93,23 @@ public:
 		std::vector<std::uint32_t> p(nbody_cuda_num_particles(_sim));
 		check(nbody_cuda_get_permutation(_sim, p.data(), p.size()));
 		return p;
+	}
+
+	void saveCheckpoint(const std::string& path) const { check(nbody_cuda_checkpoint_save(_sim, path.c_str())); }
+
+	// Variable time step (the reference's TODO:2): with nbody_cuda_config::time_step_eta > 0 the library picks every
+	// step from the largest acceleration of the step before; setTimeStep() lets the caller drive it instead.
+	void setTimeStep(Scalar dt) { check(nbody_cuda_set_time_step(_sim, dt)); }
+	Scalar timeStep() const {
+		Scalar dt = 0.0f;
+		check(nbody_cuda_get_time_step(_sim, &dt, nullptr, nullptr));
+		return dt;
+	}
+	Scalar time() const { return _time; }
+	std::uint64_t stepsDone() const {
+		std::uint64_t k = 0;
+		check(nbody_cuda_get_time(_sim, nullptr, &k));
+		return k;
 	}
 
 	nbody_cuda_stats stats() const {

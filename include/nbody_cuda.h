@@ -81,7 +81,15 @@ typedef struct nbody_cuda_config {
 	float low_order_tau;    /* adaptive-order M2L: accepted pairs with 0.75 (dimA+dimB)^2 / d^2 < tau are evaluated at
 	                           order P-1 (same lists, less work; 0 = always order P). default 0.13: RMS error 4.4e-4 on
 	                           the Plummer model against 2.1e-4 at full order (tools/explore notes in DESIGN.md) */
-	uint32_t _reserved[6];
+	/* Variable time step (the reference's TODO:2-3 "variable timestep"; it ships fixed steps only, src/main.cpp:69).
+	 * time_step_eta = 0 (default): every step uses time_step, like the reference. > 0: step n uses dt_n, with
+	 * dt_0 = time_step and dt_{n+1} = clamp(eta * sqrt(len / max_i |a_i|), time_step_min, time_step_max), the maximum
+	 * taken over the accelerations step n computed; len = softening, or bounds[0] * 2^-max_depth when softening is 0.
+	 * time_step_max = 0 means time_step; time_step_min = 0 means no lower bound. */
+	float time_step_eta;
+	float time_step_min;
+	float time_step_max;
+	uint32_t _reserved[3];
 } nbody_cuda_config;
 
 /* per-step statistics (tracing/metrics hook) */
@@ -150,6 +158,58 @@ int nbody_cuda_get_lists(nbody_cuda_sim* sim, uint64_t* n_m2l, uint32_t* m2l_pai
 int nbody_cuda_get_expansions(nbody_cuda_sim* sim, float* multipoles, float* locals, uint64_t capacity_floats);
 
 int nbody_cuda_get_stats(nbody_cuda_sim* sim, nbody_cuda_stats* stats);
+
+/* ---- variable time step -------------------------------- */
+/* Override the time step the NEXT step() uses (caller-driven variable steps; with time_step_eta > 0 the library
+ * replaces it again after that step). dt must be finite and > 0. Distributed: every rank must pass the same value. */
+int nbody_cuda_set_time_step(nbody_cuda_sim* sim, float dt);
+/* *next_dt = the step the next step() will take; *last_dt = the one the last step() took (0 before the first);
+ * *acc_max = max_i |a_i| of the last step (0 unless time_step_eta > 0). Any pointer may be NULL. */
+int nbody_cuda_get_time_step(nbody_cuda_sim* sim, float* next_dt, float* last_dt, float* acc_max);
+/* The rule on its own (host arithmetic, no device needed): the step that follows a step whose largest acceleration
+ * was acc_max under configuration cfg. Returns cfg->time_step when time_step_eta <= 0 or acc_max is not finite and > 0. */
+float nbody_cuda_next_time_step(const nbody_cuda_config* cfg, float acc_max);
+
+/* ---- checkpoint / restart ------------------------------- */
+/* The reference's only output is particles.csv, which drops velocities, masses and charges (src/main.cpp:88-95), so a
+ * run cannot be resumed from it. A checkpoint file holds the full state: configuration, simulation time (the FP32
+ * accumulator step() returns), step count, the time step the next step() will use, the 48-byte particle records in the
+ * order particles() returns them and the permutation nbody_cuda_get_permutation returns. Layout: nbody_checkpoint_header,
+ * n * 48 bytes, n * 4 bytes; little-endian; `checksum` = sum over i of (w_i + 0x9E3779B97F4A7C15) * (2 i + 1) mod 2^64, w_i the
+ * 64-bit words of the particle array followed by those of the permutation (zero-padded to a whole word). Resuming reproduces the
+ * uninterrupted run bit for bit with NBODY_FLAG_DIRECT; the FMM path sums its interaction lists in an order that depends
+ * on kernel timing, so there (as between any two runs of it) the states agree to FP32 round-off, not bitwise. */
+#define NBODY_CHECKPOINT_MAGIC 0x31504b435944424eull /* the bytes "NBDYCKP1" */
+#define NBODY_CHECKPOINT_VERSION 1u
+typedef struct nbody_checkpoint_header {
+	uint64_t magic;
+	uint32_t version;
+	uint32_t header_bytes;      /* sizeof(nbody_checkpoint_header) */
+	uint64_t n_particles;
+	uint64_t steps_done;
+	float time;                 /* simulation time */
+	float next_time_step;       /* the dt the next step() takes */
+	float last_time_step;
+	float last_acc_max;
+	uint64_t checksum;
+	nbody_cuda_config config;
+} nbody_checkpoint_header;
+
+/* Write the state of `sim` to `path` (blocking). Distributed: the state is replicated, every rank may call it (each with
+ * its own path); it is a collective only in that every rank must have finished the same step. */
+int nbody_cuda_checkpoint_save(nbody_cuda_sim* sim, const char* path);
+/* Host-only (no device needed): read and validate the header of a checkpoint file. */
+int nbody_cuda_checkpoint_info(const char* path, nbody_checkpoint_header* header);
+/* Host-only: read the payload; verifies the checksum. Either pointer may be NULL. capacity in particles. */
+int nbody_cuda_checkpoint_read(const char* path, nbody_particle* particles, uint32_t* orig_index, uint64_t capacity);
+/* Host-only: write a checkpoint from host arrays (orig_index NULL = identity); fills magic, version, sizes, checksum. */
+int nbody_cuda_checkpoint_write(const char* path, const nbody_checkpoint_header* header, const nbody_particle* particles,
+                                const uint32_t* orig_index);
+/* Construct a simulation that continues where the checkpoint stopped. cfg NULL = the configuration stored in the
+ * file (on the current device); otherwise cfg replaces it (bounds, order, capacity ... may change between runs). */
+int nbody_cuda_checkpoint_load(const char* path, const nbody_cuda_config* cfg, nbody_cuda_sim** out);
+/* Simulation time and number of steps taken (what a checkpoint stores). */
+int nbody_cuda_get_time(nbody_cuda_sim* sim, float* time, uint64_t* steps_done);
 
 /* All-pairs softened field of `n_src` sources (x,y,z,q) on `n_tgt` targets (x,y,z,*)
  * with the tiled P2P kernel; host buffers in, field (not yet scaled by G q/m) out.

@@ -26,15 +26,27 @@ EXPORTED_SYMBOLS = [
     "nbody_cuda_get_keys", "nbody_cuda_get_tree", "nbody_cuda_get_lists", "nbody_cuda_get_expansions", "nbody_cuda_get_stats",
     "nbody_cuda_direct_field", "nbody_cuda_comm_unique_id", "nbody_cuda_create_distributed", "nbody_cuda_owned_range",
     "nbody_cuda_get_owned_particles", "nbody_cuda_set_owned_particles", "nbody_cuda_rebalance",
+    "nbody_cuda_set_time_step", "nbody_cuda_get_time_step", "nbody_cuda_next_time_step", "nbody_cuda_get_time",
+    "nbody_cuda_checkpoint_save", "nbody_cuda_checkpoint_info", "nbody_cuda_checkpoint_read", "nbody_cuda_checkpoint_write",
+    "nbody_cuda_checkpoint_load",
     "nbody_cuda_last_error",
 ]
+CHECKPOINT_MAGIC = 0x31504B435944424E  # the bytes "NBDYCKP1"
 
 
 class Config(C.Structure):
     _fields_ = [("abi_version", C.c_uint32), ("bounds", C.c_float * 4), ("time_step", C.c_float), ("force_constant", C.c_float),
                 ("softening", C.c_float), ("mac_ratio", C.c_float), ("leaf_capacity", C.c_uint32), ("max_depth", C.c_uint32),
                 ("order", C.c_uint32), ("integrator", C.c_uint32), ("flags", C.c_uint32), ("device", C.c_int32),
-                ("pool_scale", C.c_float), ("low_order_tau", C.c_float), ("_reserved", C.c_uint32 * 6)]
+                ("pool_scale", C.c_float), ("low_order_tau", C.c_float), ("time_step_eta", C.c_float), ("time_step_min", C.c_float),
+                ("time_step_max", C.c_float), ("_reserved", C.c_uint32 * 3)]
+
+
+class CheckpointHeader(C.Structure):
+    """nbody_checkpoint_header (include/nbody_cuda.h): followed in the file by n*48 bytes of particles and n*4 of permutation."""
+    _fields_ = [("magic", C.c_uint64), ("version", C.c_uint32), ("header_bytes", C.c_uint32), ("n_particles", C.c_uint64),
+                ("steps_done", C.c_uint64), ("time", C.c_float), ("next_time_step", C.c_float), ("last_time_step", C.c_float),
+                ("last_acc_max", C.c_float), ("checksum", C.c_uint64), ("config", Config)]
 
 
 class Stats(C.Structure):
@@ -92,6 +104,16 @@ def load_library():
     L.nbody_cuda_owned_range.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
     L.nbody_cuda_get_owned_particles.argtypes = [vp, vp, u64]
     L.nbody_cuda_set_owned_particles.argtypes = [vp, vp, u64]
+    L.nbody_cuda_set_time_step.argtypes = [vp, C.c_float]
+    L.nbody_cuda_get_time_step.argtypes = [vp] + [C.POINTER(C.c_float)] * 3
+    L.nbody_cuda_next_time_step.argtypes = [C.POINTER(Config), C.c_float]
+    L.nbody_cuda_next_time_step.restype = C.c_float
+    L.nbody_cuda_get_time.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(u64)]
+    L.nbody_cuda_checkpoint_save.argtypes = [vp, C.c_char_p]
+    L.nbody_cuda_checkpoint_info.argtypes = [C.c_char_p, C.POINTER(CheckpointHeader)]
+    L.nbody_cuda_checkpoint_read.argtypes = [C.c_char_p, vp, vp, u64]
+    L.nbody_cuda_checkpoint_write.argtypes = [C.c_char_p, C.POINTER(CheckpointHeader), vp, vp]
+    L.nbody_cuda_checkpoint_load.argtypes = [C.c_char_p, C.POINTER(Config), C.POINTER(vp)]
     L.nbody_cuda_last_error.restype = C.c_char_p
     _lib = L
     return L
@@ -129,9 +151,27 @@ class CudaSimulation:
 
     particles: float32 [N, 12] boundary records (see nbody_b200.workloads)."""
 
-    def __init__(self, bounds, particles, time_step, log=None, *, _distributed=None, **config):
+    def __init__(self, bounds, particles, time_step, log=None, *, _distributed=None, _checkpoint=None, **config):
         self._h = C.c_void_p()
         self._lib = load_library()
+        if _checkpoint is not None:  # see from_checkpoint()
+            self._log = log
+            hdr = checkpoint_info(_checkpoint)
+            if config or bounds is not None or time_step is not None:
+                base = {k: getattr(hdr.config, k) for k, _ in Config._fields_ if k not in ("_reserved", "bounds", "abi_version")}
+                base["device"] = -1
+                base.update(config)
+                if time_step is not None:
+                    base["time_step"] = time_step
+                b = list(bounds) + [0.0] * (4 - len(bounds)) if bounds is not None else list(hdr.config.bounds)
+                self.config = default_config(bounds=b, **base)
+                cfgp = C.byref(self.config)
+            else:
+                self.config, cfgp = hdr.config, None
+            _check(self._lib.nbody_cuda_checkpoint_load(os.fsencode(_checkpoint), cfgp, C.byref(self._h)))
+            self.n = int(self._lib.nbody_cuda_num_particles(self._h))
+            self.time = self.sim_time()[0]
+            return
         particles = np.ascontiguousarray(particles, np.float32)
         if particles.ndim != 2 or particles.shape[1] != PARTICLE_FLOATS:
             raise ValueError("particles must be float32 [N, 12]")
@@ -165,6 +205,29 @@ class CudaSimulation:
             out = np.empty((self.n, PARTICLE_FLOATS), np.float32)
         _check(self._lib.nbody_cuda_get_particles(self._h, _ptr(out), out.shape[0]))
         return out
+
+    # --- variable time step and checkpoints -------------------
+    @classmethod
+    def from_checkpoint(cls, path, log=None, *, bounds=None, time_step=None, **config):
+        """Continue the run stored in `path` (save_checkpoint). Without overrides the stored configuration is used."""
+        return cls(bounds, None, time_step, log, _checkpoint=path, **config)
+
+    def save_checkpoint(self, path):
+        _check(self._lib.nbody_cuda_checkpoint_save(self._h, os.fsencode(path)))
+
+    def set_time_step(self, dt):
+        _check(self._lib.nbody_cuda_set_time_step(self._h, dt))
+
+    def time_step(self):
+        """{'next': dt of the next step(), 'last': dt of the last one, 'acc_max': max |a| of the last step (eta > 0)}"""
+        a, b, c = C.c_float(), C.c_float(), C.c_float()
+        _check(self._lib.nbody_cuda_get_time_step(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"next": a.value, "last": b.value, "acc_max": c.value}
+
+    def sim_time(self):
+        t, k = C.c_float(), C.c_uint64()
+        _check(self._lib.nbody_cuda_get_time(self._h, C.byref(t), C.byref(k)))
+        return t.value, k.value
 
     # --- extras --------------------------------------------------------------------
     def set_particles(self, particles):
@@ -267,6 +330,43 @@ def direct_field(src_posq, tgt_pos4, softening=0.01, device=-1, repeats=1):
     _check(L.nbody_cuda_direct_field(device, _ptr(src), src.shape[0], _ptr(tgt), tgt.shape[0], softening, _ptr(out), C.byref(ms),
                                      repeats))
     return out, ms.value
+
+
+def next_time_step(acc_max, **config):
+    """The variable-time-step rule on its own (host arithmetic): nbody_cuda_next_time_step."""
+    cfg = config.pop("config", None) or default_config(**config)
+    return float(load_library().nbody_cuda_next_time_step(C.byref(cfg), acc_max))
+
+
+def checkpoint_info(path):
+    hdr = CheckpointHeader()
+    _check(load_library().nbody_cuda_checkpoint_info(os.fsencode(path), C.byref(hdr)))
+    return hdr
+
+
+def checkpoint_read(path):
+    """(header, particles float32 [n,12], orig_index uint32 [n]) of a checkpoint file; host only, checksum verified."""
+    hdr = checkpoint_info(path)
+    n = int(hdr.n_particles)
+    P = np.empty((n, PARTICLE_FLOATS), np.float32)
+    orig = np.empty(n, np.uint32)
+    _check(load_library().nbody_cuda_checkpoint_read(os.fsencode(path), _ptr(P), _ptr(orig), n))
+    return hdr, P, orig
+
+
+def checkpoint_write(path, particles, orig_index=None, *, time=0.0, steps_done=0, next_time_step=None, config=None):
+    """Write a checkpoint from host arrays (host only): the way to start a run from an arbitrary saved state."""
+    P = np.ascontiguousarray(particles, np.float32)
+    if P.ndim != 2 or P.shape[1] != PARTICLE_FLOATS:
+        raise ValueError("particles must be float32 [N, 12]")
+    hdr = CheckpointHeader()
+    hdr.config = config if config is not None else default_config()
+    hdr.n_particles, hdr.steps_done, hdr.time = P.shape[0], steps_done, time
+    hdr.next_time_step = hdr.config.time_step if next_time_step is None else next_time_step
+    o = None if orig_index is None else np.ascontiguousarray(orig_index, np.uint32)
+    if o is not None and o.shape != (P.shape[0],):
+        raise ValueError("orig_index must be uint32 [N]")
+    _check(load_library().nbody_cuda_checkpoint_write(os.fsencode(path), C.byref(hdr), _ptr(P), _ptr(o)))
 
 
 def comm_unique_id():

@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 TAG = os.environ.get("NBODY_BUILD_TAG", "")
 OBJ = os.path.join(HERE, "build" + ("_" + TAG if TAG else ""))
 LIB = os.path.join(HERE, "libnbody_cuda" + ("_" + TAG if TAG else "") + ".so")
-SOURCES = ["api.cu", "tree.cu", "sort.cu", "upsweep.cu", "traverse.cu", "m2l.cu", "leaf.cu", "comm.cu"]
+SOURCES = ["api.cu", "tree.cu", "sort.cu", "upsweep.cu", "traverse.cu", "m2l.cu", "leaf.cu", "comm.cu", "checkpoint.cu"]
 HEADERS = ["common.cuh", "expansion.cuh", os.path.join("..", "..", "include", "nbody_cuda.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",

@@ -1,6 +1,7 @@
 // C ABI of the solver (include/nbody_cuda.h): device memory arena, step orchestration,
 // readback, parity exports. No CPU fallback: every entry point needs a CUDA device.
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <vector>
 
@@ -17,6 +18,8 @@ void comm_destroy(Sim& s);                          // comm.cu
 int comm_partition(Sim& s);                         // comm.cu
 int comm_exchange_aos(Sim& s);                      // comm.cu
 int comm_exchange_acc(Sim& s);                      // comm.cu
+int comm_all_max(Sim& s, float* value);             // comm.cu
+float next_time_step(const nbody_cuda_config& cfg, float acc_max);  // checkpoint.cu
 void comm_adopt_partition(Sim& s);                  // comm.cu
 
 namespace {
@@ -116,6 +119,12 @@ int validate(const nbody_cuda_config* cfg, uint64_t n) {
 	if (!(cfg->softening >= 0) || !(cfg->mac_ratio > 0)) { set_error("softening must be >= 0 and mac_ratio > 0"); return NBODY_ERR_INVALID; }
 	if (cfg->integrator > 1) { set_error("unknown integrator"); return NBODY_ERR_INVALID; }
 	if (!(cfg->low_order_tau >= 0)) { set_error("low_order_tau must be >= 0"); return NBODY_ERR_INVALID; }
+	if (!(cfg->time_step_eta >= 0) || !(cfg->time_step_min >= 0) || !(cfg->time_step_max >= 0) ||
+	    (cfg->time_step_max > 0 && cfg->time_step_min > cfg->time_step_max)) {
+		set_error("time_step_eta/min/max must be >= 0 and min <= max");
+		return NBODY_ERR_INVALID;
+	}
+	if (cfg->time_step_eta > 0 && !(cfg->time_step > 0)) { set_error("the variable time step needs time_step > 0"); return NBODY_ERR_INVALID; }
 	return NBODY_OK;
 }
 
@@ -144,6 +153,7 @@ int run_pipeline(Sim& s) {
 		for (int k = 3; k <= 6; ++k) NB_CUDA_CHECK(cudaEventRecord(s.ev[k], st));
 		launch_direct(s);
 	}
+	if (s.cfg.time_step_eta > 0.0f) launch_acc_max(s);
 	NB_CUDA_CHECK(cudaEventRecord(s.ev[7], st));
 	NB_CUDA_CHECK(cudaMemcpyAsync(s.ctrl_host, s.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
 	NB_CUDA_CHECK(cudaStreamSynchronize(st));  // the one synchronisation of a step
@@ -201,6 +211,7 @@ int create_common(const nbody_cuda_config* cfg, uint64_t n, Sim** out) {
 	}
 	Sim* s = new Sim;
 	s->cfg = *cfg;
+	s->dt = cfg->time_step;
 	if (s->cfg.pool_scale <= 0) s->cfg.pool_scale = 1.0f;
 	if (cfg->device >= 0) s->device = cfg->device; else cudaGetDevice(&s->device);
 	auto fail = [&](int code) { free_all(s); return code; };
@@ -352,8 +363,19 @@ int nbody_cuda_step(nbody_cuda_sim* sim, float* time_out) {
 		++s->stats.retries;
 	}
 	std::swap(s->orig[0], s->orig[1]);
-	s->time += s->cfg.time_step;  // FP32 accumulation like src/open_cl_simulation.cpp:103
+	s->time += s->dt;  // FP32 accumulation like src/open_cl_simulation.cpp:103
 	++s->steps_done;
+	s->dt_last = s->dt;
+	if (s->cfg.time_step_eta > 0.0f) {
+		// variable time step: this step's largest acceleration sets the next step (rule in nbody_cuda_next_time_step)
+		float a2;
+		std::memcpy(&a2, &s->ctrl_host->acc_max2_bits, sizeof(float));
+		if (s->comm) { int rc = comm_all_max(*s, &a2); if (rc) return rc; }
+		s->acc_max = std::sqrt(a2);
+		s->dt = next_time_step(s->cfg, s->acc_max);
+	} else {
+		s->dt = s->dt_last;  // fixed step: cfg.time_step, or what nbody_cuda_set_time_step installed
+	}
 	s->lists_valid = !(s->cfg.flags & NBODY_FLAG_DIRECT);
 	// statistics
 	const Ctrl& c = *s->ctrl_host;

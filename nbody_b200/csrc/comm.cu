@@ -70,6 +70,8 @@ struct Comm {
 	float* work_host = nullptr;     // pinned, world: per-rank device time of the owned-slice stages of the last step
 	float* work_dev = nullptr;      // device, world
 	bool have_work = false;         // work_host describes the partition in part_host
+	float* red_host = nullptr;      // pinned, world: scratch of comm_all_max
+	float* red_dev = nullptr;       // device, world
 };
 
 struct PartitionTargets { uint32_t t[17]; };
@@ -168,6 +170,22 @@ float comm_work_imbalance(const Sim& s) {
 	return sum > 0.0f ? mx * s.comm->world / sum - 1.0f : 0.0f;
 }
 
+// Maximum of one float over the ranks (variable time step: the largest acceleration of the step). An all-gather of
+// `world` floats and a host-side maximum, so that every rank derives the next step from identical bits. NaN on any
+// rank gives NaN everywhere.
+int comm_all_max(Sim& s, float* value) {
+	Comm& cm = *s.comm;
+	cm.red_host[cm.rank] = *value;
+	NB_CUDA_CHECK(cudaMemcpyAsync(cm.red_dev + cm.rank, cm.red_host + cm.rank, sizeof(float), cudaMemcpyHostToDevice, s.stream));
+	NB_NCCL_CHECK(g_nccl.AllGather(cm.red_dev + cm.rank, cm.red_dev, 1, ncclFloat, cm.comm, s.stream));
+	NB_CUDA_CHECK(cudaMemcpyAsync(cm.red_host, cm.red_dev, sizeof(float) * cm.world, cudaMemcpyDeviceToHost, s.stream));
+	NB_CUDA_CHECK(cudaStreamSynchronize(s.stream));
+	float m = cm.red_host[0];
+	for (int r = 1; r < cm.world; ++r) m = (cm.red_host[r] > m || cm.red_host[r] != cm.red_host[r]) ? cm.red_host[r] : m;
+	*value = m;
+	return NBODY_OK;
+}
+
 int comm_exchange_acc(Sim& s) {
 	if (!s.acc_partial) return NBODY_OK;
 	int rc = exchange(s, s.acc, sizeof(float4));
@@ -182,6 +200,8 @@ void comm_destroy(Sim& s) {
 	if (s.comm->part_host) cudaFreeHost(s.comm->part_host);
 	if (s.comm->work_host) cudaFreeHost(s.comm->work_host);
 	if (s.comm->work_dev) cudaFree(s.comm->work_dev);
+	if (s.comm->red_host) cudaFreeHost(s.comm->red_host);
+	if (s.comm->red_dev) cudaFree(s.comm->red_dev);
 	delete s.comm;
 	s.comm = nullptr;
 }
@@ -226,7 +246,9 @@ int nbody_cuda_create_distributed(const nbody_cuda_config* cfg, const nbody_part
 	s->rank = rank;
 	if (cudaMallocHost((void**) &cm.part_host, sizeof(uint32_t) * (world + 1)) != cudaSuccess ||
 	    cudaMallocHost((void**) &cm.work_host, sizeof(float) * world) != cudaSuccess ||
-	    cudaMalloc((void**) &cm.work_dev, sizeof(float) * world) != cudaSuccess) { set_error("allocation of the partition tables failed"); return fail(NBODY_ERR_CUDA); }
+	    cudaMalloc((void**) &cm.work_dev, sizeof(float) * world) != cudaSuccess ||
+	    cudaMallocHost((void**) &cm.red_host, sizeof(float) * world) != cudaSuccess ||
+	    cudaMalloc((void**) &cm.red_dev, sizeof(float) * world) != cudaSuccess) { set_error("allocation of the partition tables failed"); return fail(NBODY_ERR_CUDA); }
 	ncclUniqueId u;
 	std::memcpy(&u, id, 128);
 	ncclResult_t nr = g_nccl.CommInitRank(&cm.comm, world, u, rank);

@@ -52,6 +52,7 @@ struct Ctrl {
 	unsigned long long stat_m2l_inter, stat_m2l_low, stat_p2p_entries, stat_p2p_inter, stat_near, stat_leaves;
 	uint32_t work_ticket[4];             // dynamic work distribution of the persistent kernels
 	uint32_t part[17];                   // distributed: rank r owns particles [part[r], part[r+1]) of the tree-ordered array
+	uint32_t acc_max2_bits;              // variable time step: bits of max |a|^2 over this rank's slice (k_acc_max; non-negative floats order like uints)
 };
 
 struct Pools {
@@ -79,7 +80,11 @@ struct Sim {
 	cudaStream_t stream = nullptr;
 	uint64_t n = 0;
 	float time = 0.0f;
-	uint64_t steps_done = 0;
+	uint64_t steps_done = 0;  // steps taken by this object (0 = no tree, lists or accelerations yet)
+	uint64_t steps_base = 0;  // steps taken before the checkpoint this object was loaded from
+	float dt = 0.0f;          // the step the next step() takes (cfg.time_step unless the variable time step or the caller changed it)
+	float dt_last = 0.0f;     // the step the last step() took
+	float acc_max = 0.0f;     // max |a| of the last step (time_step_eta > 0 only)
 	int nc_stride = 0;  // floats per multipole/local record
 
 	// particle state, SoA of two float4 planes; [0] = state (order of the last step), [1] = sorted scratch of the current step
@@ -144,6 +149,7 @@ void launch_m2l(Sim& s);                                                        
 void launch_l2l(Sim& s);                                                               // stage 4b: L2L downsweep
 void launch_leaf(Sim& s);                                                              // stage 5: P2P + L2P + integrator
 void launch_direct(Sim& s);                                                            // all-pairs P2P + integrator (validation)
+void launch_acc_max(Sim& s);                                                           // variable time step: max |a|^2 of the owned slice -> Ctrl
 int direct_field_device(const float4* src, uint64_t n_src, const float4* tgt, uint64_t n_tgt, float eps2, float4* out, cudaStream_t st);
 
 // device helpers shared by several translation units

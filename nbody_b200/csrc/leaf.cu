@@ -302,7 +302,7 @@ void launch_leaf(Sim& s) {
 	LeafArgs a{};
 	a.c = s.ctrl; a.posq = s.posq[1]; a.velm_in = s.velm[1]; a.posq_out = s.posq[0]; a.velm_out = s.velm[0]; a.acc = s.acc;
 	a.geom = s.geom; a.info = s.info; a.nbegin = s.nbegin; a.p2p_head = s.p2p_head; a.seg = s.pools.seg; a.p2p = s.pools.p2p; a.L = s.L;
-	a.eps2 = s.cfg.softening * s.cfg.softening; a.G = s.cfg.force_constant; a.dt = s.cfg.time_step;
+	a.eps2 = s.cfg.softening * s.cfg.softening; a.G = s.cfg.force_constant; a.dt = s.dt;
 	a.integrator = (int) s.cfg.integrator; a.no_integrate = (s.cfg.flags & NBODY_FLAG_NO_INTEGRATE) ? 1 : 0;
 	a.rank = s.rank;
 	a.stat_inter = &s.ctrl->stat_p2p_inter; a.stat_leaves = &s.ctrl->stat_leaves;
@@ -397,8 +397,37 @@ void launch_direct(Sim& s) {
 	direct_field_device(s.posq[1], s.n, s.posq[1], s.n, eps2, field, s.stream);
 	const uint64_t want = (s.n + 255) / 256;
 	k_direct_finish<<<(unsigned) (want > kNumSM * 16 ? kNumSM * 16 : (want ? want : 1)), 256, 0, s.stream>>>(
-	    s.n, field, s.posq[1], s.velm[1], s.posq[0], s.velm[0], s.acc, s.cfg.force_constant, s.cfg.time_step, (int) s.cfg.integrator,
+	    s.n, field, s.posq[1], s.velm[1], s.posq[0], s.velm[0], s.acc, s.cfg.force_constant, s.dt, (int) s.cfg.integrator,
 	    (s.cfg.flags & NBODY_FLAG_NO_INTEGRATE) ? 1 : 0);
 }
+
+// Variable time step (nbody_cuda_config::time_step_eta > 0): max |a|^2 over this rank's slice of `acc`, 16 B per particle
+// read once (HBM-bound, ~0.05 ms at 2^24). Launched only when the feature is on, so the fixed-step path is unchanged.
+// |a|^2 >= 0, so the float ordering equals the ordering of the bit patterns and one atomicMax per block suffices; a NaN
+// (bits above +inf) wins the maximum and is rejected by the host rule.
+__global__ void __launch_bounds__(256) k_acc_max(Ctrl* c, int rank, const float4* __restrict__ acc) {
+	if (c->status) return;
+	const uint32_t first = c->part[rank], end = c->part[rank + 1];
+	float m = 0.0f;
+	bool bad = false;
+	for (uint64_t i = (uint64_t) first + blockIdx.x * blockDim.x + threadIdx.x; i < end; i += (uint64_t) gridDim.x * blockDim.x) {
+		const float4 a = acc[i];
+		const float a2 = fmaf(a.z, a.z, fmaf(a.y, a.y, a.x * a.x));
+		bad |= !(a2 == a2);
+		m = fmaxf(m, a2);  // fmaxf drops NaN operands: `bad` carries them
+	}
+	uint32_t bits = bad ? 0x7fc00000u : __float_as_uint(m);
+	bits = __reduce_max_sync(0xffffffffu, bits);
+	__shared__ uint32_t sm[8];
+	if ((threadIdx.x & 31u) == 0u) sm[threadIdx.x >> 5] = bits;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		uint32_t b = sm[0];
+		for (int k = 1; k < 8; ++k) b = sm[k] > b ? sm[k] : b;
+		if (b) atomicMax(&c->acc_max2_bits, b);
+	}
+}
+
+void launch_acc_max(Sim& s) { k_acc_max<<<kNumSM * 4, 256, 0, s.stream>>>(s.ctrl, s.rank, s.acc); }
 
 }  // namespace nbody

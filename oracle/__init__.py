@@ -60,6 +60,10 @@ def lib():
         L.orc_naive_step_as_written.restype = C.c_float
         L.orc_direct_step.argtypes = [C.c_uint64, f32p, C.c_float, C.c_float, C.c_float, C.c_uint32, C.c_int, C.c_int]
         L.orc_direct_step.restype = C.c_float
+        L.orc_next_time_step.argtypes = [C.c_float] * 6
+        L.orc_next_time_step.restype = C.c_float
+        L.orc_direct_step_adaptive.argtypes = [C.c_uint64, f32p] + [C.c_float] * 7 + [C.c_uint32, C.c_int, C.c_int, f32p, f32p]
+        L.orc_direct_step_adaptive.restype = C.c_float
         _LIB = L
     return _LIB
 
@@ -181,6 +185,21 @@ def direct_step(particles12, G=1.0, eps=0.01, dt=1e-3, steps=1, integrator=0, th
     P = np.ascontiguousarray(particles12, np.float32).copy()
     t = lib().orc_direct_step(P.shape[0], P, G, eps, dt, steps, integrator, threads or os.cpu_count() or 1)
     return P, t
+
+
+def next_time_step(eta, length, acc_max, dt0, dt_min=0.0, dt_max=0.0):
+    return float(lib().orc_next_time_step(eta, length, acc_max, dt0, dt_min, dt_max))
+
+
+def direct_step_adaptive(particles12, G=1.0, eps=0.01, dt0=1e-3, eta=0.1, dt_min=0.0, dt_max=0.0, steps=1, integrator=0, length=None,
+                         threads=None):
+    """Variable-step FP64 direct-sum run: returns (particles, final time, dt per step, max |a| per step)."""
+    P = np.ascontiguousarray(particles12, np.float32).copy()
+    dts = np.zeros(steps, np.float32)
+    amax = np.zeros(steps, np.float32)
+    t = lib().orc_direct_step_adaptive(P.shape[0], P, G, eps, eps if length is None else length, dt0, eta, dt_min, dt_max, steps,
+                                       integrator, threads or os.cpu_count() or 1, dts, amax)
+    return P, t, dts, amax
 
 
 def ref_naive_run(particles12, force_constant, dt, steps=1):
