@@ -127,7 +127,7 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def reference_arm(args, rank):
+def reference_arm(args, rank, emit):
     """--impl reference: the unmodified reference CPU path (naive_simulation.cpp via oracle/_ref;
     the oracle port if the reference was never compiled) on a bounded sample of the same workload."""
     if rank != 0:
@@ -160,7 +160,7 @@ def reference_arm(args, rank):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -186,9 +186,17 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE line, the JSON: anything a library prints there (NCCL's version banner under torchrun)
+    # goes to stderr instead; the line itself is written to the saved descriptor at the end
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
 
     if args.impl == "reference":
-        reference_arm(args, rank)
+        reference_arm(args, rank, emit)
         return
 
     import torch
@@ -353,7 +361,7 @@ def main():
             line["per_rank_ms"] = {"columns": ["traverse", "m2l", "leaf", "comm"], "rows": rank_ms}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args)
-        print(json.dumps(line), flush=True)
+        emit(line)
     sim.close()
     if world > 1:
         dist.destroy_process_group()

@@ -39,7 +39,7 @@ def test_cpp_driver_checkpoint_restart_and_variable_step(tmp_path, driver_exe):
     def rows(path):
         return np.array([[float(v) for v in line.split(",")] for line in open(path).read().strip().splitlines()])
     whole, parts, ckp = str(tmp_path / "whole.csv"), str(tmp_path / "parts.csv"), str(tmp_path / "run.ckp")
-    common = ["--n", "8000", "--csv-max", "8000", "--quiet", "--eta", "0.02"]
+    common = ["--n", "8000", "--csv-max", "8000", "--quiet", "--eta", "0.005"]  # max |a| of this cube is ~4: eta sqrt(eps/|a|) = 2.5e-4 < dt
     for args in (["--steps", "4", "--csv", whole], ["--steps", "2", "--csv", parts, "--checkpoint", ckp],
                  ["--steps", "2", "--csv", parts, "--restart", ckp]):
         r = subprocess.run([driver_exe] + common + args, capture_output=True, text=True, timeout=120)
@@ -48,7 +48,7 @@ def test_cpp_driver_checkpoint_restart_and_variable_step(tmp_path, driver_exe):
     a, b = rows(whole), rows(parts)
     assert a.shape == b.shape == (4, 1 + 3 * 8000)
     assert np.all(np.diff(a[:, 0]) > 0) and np.diff(a[:, 0])[1:].max() < 1e-3      # the variable step took over after step 1
-    np.testing.assert_allclose(b[:, 0], a[:, 0], rtol=1e-5)                          # the restarted run continues the same clock
+    np.testing.assert_allclose(b[:, 0], a[:, 0], rtol=3e-5)                          # the restarted run continues the same clock
     # same particles at the same places (tree order may differ where round-off flips two neighbouring keys: compare as sets)
     for s in range(4):
         pa, pb = np.sort(a[s, 1:].reshape(-1, 3), axis=0), np.sort(b[s, 1:].reshape(-1, 3), axis=0)
@@ -80,3 +80,8 @@ def test_two_gpu_step_matches_single_gpu():
                         "--master-port", "29655", os.path.join(ROOT, "tools", "mg_check.py"), "200000", "4"],
                        capture_output=True, text=True, timeout=300)
     assert "MG_CHECK PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    # the variable time step across ranks: every rank derives the same step sequence as the single-GPU run
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29656", os.path.join(ROOT, "tools", "mg_check.py"), "100000", "4", "plummer", "0.05"],
+                       capture_output=True, text=True, timeout=300)
+    assert "MG_CHECK PASS" in r.stdout and "time steps agree: True" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

@@ -40,7 +40,7 @@ def test_variable_time_step_follows_the_oracle(flags, tol_dt, tol_x):
     acc = np.float32(0)
     for d in got_dt:
         acc = np.float32(acc + np.float32(d))
-    assert np.float32(t) == acc and abs(t - tref) < 1e-6   # FP32 accumulation of the steps actually taken
+    assert np.float32(t) == acc and abs(t - tref) < steps * 1e-3 * tol_dt + 1e-7   # FP32 accumulation of the steps actually taken
     assert sim.sim_time() == (pytest.approx(t), steps)
     assert np.abs(by_identity(sim)[:, 0:3] - Pref[:, 0:3]).max() < tol_x
     # max |a| reported == max over the accelerations the caller can read
