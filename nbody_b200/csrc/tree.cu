@@ -173,18 +173,22 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* w
 }
 
 // Pass A of level `l`: count the nodes that split in each tile; the last block to finish
-// turns the tile counts into exclusive offsets and publishes the size of level l+1.
+// turns the tile counts into exclusive offsets (a block-wide scan) and publishes the size of level l+1.
+// A level without nodes (below the deepest one) costs one launch that only clears the split count.
 __global__ void __launch_bounds__(256) k_level_count(Ctrl* c, int l, uint32_t cap, uint32_t max_depth, uint32_t max_nodes,
                                                       const uint2* __restrict__ info, uint32_t* scan_sums) {
 	__shared__ uint32_t warp_sums[32];
 	__shared__ bool last;
 	const uint32_t lo = c->level_off[l], hi = c->level_off[l + 1];
 	const uint32_t nl = hi - lo;
+	if (nl == 0 || (uint32_t) l >= max_depth) {  // uniform over the grid: nothing can split here
+		if (blockIdx.x == 0 && threadIdx.x == 0) scan_sums[gridDim.x] = 0;
+		return;
+	}
 	const uint32_t tile = (nl + gridDim.x - 1) / gridDim.x;
 	const uint32_t t0 = lo + blockIdx.x * tile, t1 = min(hi, t0 + tile);
 	uint32_t cnt = 0;
-	if ((uint32_t) l < max_depth)
-		for (uint32_t i = t0 + threadIdx.x; i < t1; i += blockDim.x) cnt += info[i].y > cap ? 1u : 0u;
+	for (uint32_t i = t0 + threadIdx.x; i < t1; i += blockDim.x) cnt += info[i].y > cap ? 1u : 0u;
 	uint32_t total;
 	block_exclusive_scan(cnt, warp_sums, total);
 	if (threadIdx.x == 0) {
@@ -193,10 +197,27 @@ __global__ void __launch_bounds__(256) k_level_count(Ctrl* c, int l, uint32_t ca
 		last = atomicAdd(&c->scan_ticket, 1u) == gridDim.x - 1;
 	}
 	__syncthreads();
-	if (last && threadIdx.x == 0) {
-		__threadfence();
-		uint32_t run = 0;
-		for (uint32_t b = 0; b < gridDim.x; ++b) { const uint32_t v = ((volatile uint32_t*) scan_sums)[b]; scan_sums[b] = run; run += v; }
+	if (!last) return;
+	__threadfence();
+	// exclusive scan of the gridDim.x tile counts by the whole block: thread t owns counts [t*per, (t+1)*per)
+	constexpr uint32_t kPerMax = (kScanBlocks + 255) / 256;
+	const uint32_t per = (gridDim.x + blockDim.x - 1) / blockDim.x;
+	uint32_t v[kPerMax], mine = 0;
+#pragma unroll
+	for (uint32_t k = 0; k < kPerMax; ++k) {
+		const uint32_t b = threadIdx.x * per + k;
+		v[k] = (k < per && b < gridDim.x) ? ((volatile uint32_t*) scan_sums)[b] : 0u;
+		mine += v[k];
+	}
+	uint32_t run;
+	uint32_t ex = block_exclusive_scan(mine, warp_sums, run);
+#pragma unroll
+	for (uint32_t k = 0; k < kPerMax; ++k) {
+		const uint32_t b = threadIdx.x * per + k;
+		if (k < per && b < gridDim.x) scan_sums[b] = ex;
+		ex += v[k];
+	}
+	if (threadIdx.x == 0) {
 		uint32_t next = hi + 8u * run;
 		if (next > max_nodes || next < hi) { atomicOr(&c->status, kOvfNodes); run = 0; next = hi; }
 		scan_sums[gridDim.x] = run;
@@ -209,6 +230,11 @@ __global__ void __launch_bounds__(256) k_level_count(Ctrl* c, int l, uint32_t ca
 
 // Pass B of level `l`: every splitting node gets its 8 children at level_off[l+1] + 8*rank,
 // rank = its position among the splitting nodes of the level (deterministic, Morton order).
+// Eight lanes per node, lane k = child k: the seven child boundaries are found by seven concurrent binary
+// searches in the sorted keys (one thread searching them one after the other made every level cost 60-90 us of
+// dependent-load latency, even the top ones with a handful of nodes) and the eight child records are written by
+// eight consecutive lanes.
+constexpr int kSplitNodes = 256 / 8;  // nodes per block iteration
 __global__ void __launch_bounds__(256) k_level_split(Ctrl* c, int l, uint32_t cap, uint32_t max_depth, float bx, float by, float bz,
                                                       const uint64_t* __restrict__ keys, float4* geom, uint2* info, uint32_t* nbegin,
                                                       uint32_t* nparent, uint64_t* nkey, uint32_t* p2p_head,
@@ -223,43 +249,45 @@ __global__ void __launch_bounds__(256) k_level_split(Ctrl* c, int l, uint32_t ca
 	const int shift = 3 * (kMaxDepth - 1 - l);
 	const float sc = __int_as_float((127 - (l + 1)) << 23);  // 2^-(l+1), exact
 	const float dx = __fmul_rn(bx, sc), dy = __fmul_rn(by, sc), dz = __fmul_rn(bz, sc);
-	for (uint32_t base = t0; base < t1; base += blockDim.x) {  // uniform trip count inside the block
-		const uint32_t i = base + threadIdx.x;
+	const uint32_t k = threadIdx.x & 7u, slot = threadIdx.x >> 3;
+	for (uint32_t base = t0; base < t1; base += kSplitNodes) {  // uniform trip count inside the block
+		const uint32_t i = base + slot;
 		uint2 nf = make_uint2(0u, 0u);
 		if (i < t1) nf = info[i];
 		const bool split = i < t1 && nf.y > cap;
 		uint32_t total;
-		const uint32_t rank = block_exclusive_scan(split ? 1u : 0u, warp_sums, total);
+		uint32_t rank = block_exclusive_scan(split && k == 0u ? 1u : 0u, warp_sums, total);
+		rank = __shfl_sync(0xffffffffu, rank, (threadIdx.x & 31u) & ~7u);  // the node's lane 0 holds its rank
+		uint32_t b = 0, e = 0, end_k = 0;
+		uint64_t pk = 0;
+		if (split) {
+			b = nbegin[i]; e = b + nf.y; pk = nkey[i];
+			// first particle whose digit at this level exceeds k
+			end_k = e;
+			if (k < 7u) {
+				const uint64_t bound = pk | (uint64_t) (k + 1u) << shift;
+				uint32_t a = b, z = e;
+				while (a < z) { const uint32_t m = a + ((z - a) >> 1); if (keys[m] < bound) a = m + 1; else z = m; }
+				end_k = a;
+			}
+		}
+		uint32_t prev = __shfl_up_sync(0xffffffffu, end_k, 1);  // child k starts where child k-1 ends
+		if (k == 0u) prev = b;
 		if (split) {
 			const uint32_t cb = hi + 8u * (running + rank);
-			const uint32_t b = nbegin[i], e = b + nf.y;
-			const uint64_t pk = nkey[i];
-			info[i] = make_uint2(cb, nf.y);
-			uint32_t prev = b;
+			if (k == 0u) info[i] = make_uint2(cb, nf.y);
 			const uint64_t pp = l == 0 ? 0ull : pk >> (shift + 3);  // parent's digits, last one in bits 0..2
 			const uint32_t pix = compact3(pp), piy = compact3(pp >> 1), piz = compact3(pp >> 2);
-#pragma unroll 1
-			for (uint32_t k = 0; k < 8; ++k) {
-				// first particle whose digit at this level exceeds k
-				uint32_t end_k = e;
-				if (k < 7) {
-					const uint64_t bound = pk | (uint64_t) (k + 1) << shift;
-					uint32_t a = prev, z = e;
-					while (a < z) { const uint32_t m = a + ((z - a) >> 1); if (keys[m] < bound) a = m + 1; else z = m; }
-					end_k = a;
-				}
-				const uint32_t cid = cb + k;
-				const uint32_t ix = pix << 1 | (k & 1u), iy = piy << 1 | (k >> 1 & 1u), iz = piz << 1 | (k >> 2 & 1u);
-				geom[cid] = make_float4(__fadd_rn(__fmul_rn((float) ix, dx), __fmul_rn(dx, 0.5f)),
-				                        __fadd_rn(__fmul_rn((float) iy, dy), __fmul_rn(dy, 0.5f)),
-				                        __fadd_rn(__fmul_rn((float) iz, dz), __fmul_rn(dz, 0.5f)), dx);
-				info[cid] = make_uint2(0u, end_k - prev);
-				nbegin[cid] = prev;
-				nparent[cid] = i;
-				nkey[cid] = pk | (uint64_t) k << shift;
-				p2p_head[cid] = 0xffffffffu;
-				prev = end_k;
-			}
+			const uint32_t cid = cb + k;
+			const uint32_t ix = pix << 1 | (k & 1u), iy = piy << 1 | (k >> 1 & 1u), iz = piz << 1 | (k >> 2 & 1u);
+			geom[cid] = make_float4(__fadd_rn(__fmul_rn((float) ix, dx), __fmul_rn(dx, 0.5f)),
+			                        __fadd_rn(__fmul_rn((float) iy, dy), __fmul_rn(dy, 0.5f)),
+			                        __fadd_rn(__fmul_rn((float) iz, dz), __fmul_rn(dz, 0.5f)), dx);
+			info[cid] = make_uint2(0u, end_k - prev);
+			nbegin[cid] = prev;
+			nparent[cid] = i;
+			nkey[cid] = pk | (uint64_t) k << shift;
+			p2p_head[cid] = 0xffffffffu;
 		}
 		running += total;
 	}
