@@ -181,6 +181,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pool-scale", type=float, default=1.0)
+    ap.add_argument("--flags", type=int, default=0, help="nbody_cuda_config.flags (e.g. 32 = NBODY_FLAG_NO_OVERLAP, for A/B runs)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -220,7 +221,7 @@ def main():
     Pn = host.numpy()
 
     def make_sim(capacity):
-        cfgkw = dict(order=args.order, leaf_capacity=capacity, device=local_rank, pool_scale=args.pool_scale,
+        cfgkw = dict(order=args.order, leaf_capacity=capacity, device=local_rank, pool_scale=args.pool_scale, flags=args.flags,
                      force_constant=workloads.force_constant(args.workload, n))
         if world == 1:
             return nbody_b200.CudaSimulation([1.0, 1.0, 1.0], Pn, args.dt, **cfgkw)
@@ -348,7 +349,7 @@ def main():
             "config": {"workload": f"{args.workload} sphere N={n}" if args.workload == "plummer" else f"{args.workload} N={n}",
                        "order": args.order, "leaf_capacity": args.leaf_capacity, "mac_ratio": 0.5, "softening": 0.01,
                        "integrator": "kick-drift", "l2_policy": "working set (>1 GB of lists and particle state per step) exceeds the 126 MB L2",
-                       "partition": "morton-range" if world > 1 else "single"},
+                       "partition": "morton-range" if world > 1 else "single", "flags": args.flags},
             "clocks": clocks, "e2e": e2e, "gpu_launches": K * launches_per_step(sim, world),
             "roofline": roof,
             "p2p_fp32_tflops": {"tree_p2p_kernel": p2p_tf, "tree_p2p_frac_of_peak": p2p_tf / peak,

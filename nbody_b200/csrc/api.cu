@@ -19,6 +19,7 @@ int comm_partition(Sim& s);                         // comm.cu
 int comm_exchange_aos(Sim& s);                      // comm.cu
 int comm_exchange_acc(Sim& s);                      // comm.cu
 int comm_all_max(Sim& s, float* value);             // comm.cu
+int comm_wait_velocities(Sim& s);                   // comm.cu
 float next_time_step(const nbody_cuda_config& cfg, float acc_max);  // checkpoint.cu
 void comm_adopt_partition(Sim& s);                  // comm.cu
 
@@ -147,10 +148,13 @@ int run_pipeline(Sim& s) {
 		launch_m2l(s);
 		NB_CUDA_CHECK(cudaEventRecord(s.ev[5], st));
 		launch_l2l(s);
+		if (s.comm) { if ((rc = comm_wait_velocities(s))) return rc; launch_gather_velocities(s); }
 		NB_CUDA_CHECK(cudaEventRecord(s.ev[6], st));
 		launch_leaf(s);
 	} else {
-		for (int k = 3; k <= 6; ++k) NB_CUDA_CHECK(cudaEventRecord(s.ev[k], st));
+		for (int k = 3; k <= 5; ++k) NB_CUDA_CHECK(cudaEventRecord(s.ev[k], st));
+		if (s.comm) { if ((rc = comm_wait_velocities(s))) return rc; launch_gather_velocities(s); }
+		NB_CUDA_CHECK(cudaEventRecord(s.ev[6], st));
 		launch_direct(s);
 	}
 	if (s.cfg.time_step_eta > 0.0f) launch_acc_max(s);
@@ -400,6 +404,7 @@ int nbody_cuda_get_particles(nbody_cuda_sim* sim, nbody_particle* out, uint64_t 
 	if (!s || !out) { set_error("NULL argument"); return NBODY_ERR_INVALID; }
 	if (capacity < s->n) { set_error("get_particles: output buffer too small"); return NBODY_ERR_INVALID; }
 	NB_CUDA_CHECK(cudaSetDevice(s->device));
+	if (s->comm) { int rc = comm_wait_velocities(*s); if (rc) return rc; }
 	launch_export(*s, s->aos_dev, s->n);
 	NB_CUDA_CHECK(cudaMemcpyAsync(out, s->aos_dev, s->n * sizeof(nbody_particle), cudaMemcpyDeviceToHost, s->stream));
 	NB_CUDA_CHECK(cudaStreamSynchronize(s->stream));
@@ -601,6 +606,7 @@ int nbody_cuda_get_owned_particles(nbody_cuda_sim* sim, nbody_particle* out, uin
 	if (!s || !out) { set_error("NULL argument"); return NBODY_ERR_INVALID; }
 	if (capacity < s->own_count) { set_error("get_owned_particles: output buffer too small"); return NBODY_ERR_INVALID; }
 	NB_CUDA_CHECK(cudaSetDevice(s->device));
+	if (s->comm) { int rc = comm_wait_velocities(*s); if (rc) return rc; }
 	launch_export(*s, s->aos_dev, s->n);
 	NB_CUDA_CHECK(cudaMemcpyAsync(out, s->aos_dev + s->own_first, s->own_count * sizeof(nbody_particle), cudaMemcpyDeviceToHost, s->stream));
 	NB_CUDA_CHECK(cudaStreamSynchronize(s->stream));
@@ -612,6 +618,7 @@ int nbody_cuda_set_owned_particles(nbody_cuda_sim* sim, const nbody_particle* pa
 	if (!s || !particles) { set_error("NULL argument"); return NBODY_ERR_INVALID; }
 	if (n != s->own_count) { set_error("set_owned_particles: count differs from the owned range"); return NBODY_ERR_INVALID; }
 	NB_CUDA_CHECK(cudaSetDevice(s->device));
+	if (s->comm) { int rc = comm_wait_velocities(*s); if (rc) return rc; }  // the import below overwrites the velocity plane
 	NB_CUDA_CHECK(cudaMemcpyAsync(s->aos_dev + s->own_first, particles, n * sizeof(nbody_particle), cudaMemcpyHostToDevice, s->stream));
 	if (s->comm) { int rc = comm_exchange_aos(*s); if (rc) return rc; }
 	// the permutation is kept: the caller hands back the particles it read with get_owned_particles

@@ -72,6 +72,10 @@ struct Comm {
 	bool have_work = false;         // work_host describes the partition in part_host
 	float* red_host = nullptr;      // pinned, world: scratch of comm_all_max
 	float* red_dev = nullptr;       // device, world
+	// velocities travel on a second stream: the other ranks need them only in the next step's leaf kernel
+	cudaStream_t vel_stream = nullptr;
+	cudaEvent_t ev_step = nullptr, ev_vel = nullptr;
+	bool vel_pending = false;       // a velocity exchange was issued that the compute stream has not been ordered after yet
 };
 
 struct PartitionTargets { uint32_t t[17]; };
@@ -131,14 +135,15 @@ void comm_adopt_partition(Sim& s) {
 	s.own_count = cm.part_host[cm.rank + 1] - cm.part_host[cm.rank];
 }
 
-static int exchange(Sim& s, void* buf, size_t elem_bytes) {
+static int exchange(Sim& s, void* buf, size_t elem_bytes, cudaStream_t st = nullptr) {
 	Comm& cm = *s.comm;
+	if (!st) st = s.stream;
 	NB_NCCL_CHECK(g_nccl.GroupStart());
 	for (int r = 0; r < cm.world; ++r) {
 		const size_t off = (size_t) cm.part_host[r] * elem_bytes, cnt = (size_t) (cm.part_host[r + 1] - cm.part_host[r]) * elem_bytes;
 		if (cnt == 0) continue;
 		char* p = static_cast<char*>(buf) + off;
-		NB_NCCL_CHECK(g_nccl.Broadcast(p, p, cnt, ncclChar, r, cm.comm, s.stream));
+		NB_NCCL_CHECK(g_nccl.Broadcast(p, p, cnt, ncclChar, r, cm.comm, st));
 	}
 	NB_NCCL_CHECK(g_nccl.GroupEnd());
 	return NBODY_OK;
@@ -151,14 +156,36 @@ int comm_exchange_aos(Sim& s) { return exchange(s, s.aos_dev, sizeof(nbody_parti
 int comm_step_exchange(Sim& s, float own_ms) {
 	Comm& cm = *s.comm;
 	int rc;
+	// positions first: every rank's next step starts with the keys of ALL particles
 	if ((rc = exchange(s, s.posq[0], sizeof(float4)))) return rc;
-	if ((rc = exchange(s, s.velm[0], sizeof(float4)))) return rc;
+	const bool overlap = !(s.cfg.flags & NBODY_FLAG_NO_OVERLAP);
+	if (!overlap && (rc = exchange(s, s.velm[0], sizeof(float4)))) return rc;
 	s.acc_partial = true;  // accelerations stay rank-local until somebody asks for them (comm_exchange_acc)
 	cm.work_host[cm.rank] = own_ms;
 	NB_CUDA_CHECK(cudaMemcpyAsync(cm.work_dev + cm.rank, cm.work_host + cm.rank, sizeof(float), cudaMemcpyHostToDevice, s.stream));
 	NB_NCCL_CHECK(g_nccl.AllGather(cm.work_dev + cm.rank, cm.work_dev, 1, ncclFloat, cm.comm, s.stream));
 	NB_CUDA_CHECK(cudaMemcpyAsync(cm.work_host, cm.work_dev, sizeof(float) * cm.world, cudaMemcpyDeviceToHost, s.stream));
 	cm.have_work = true;  // valid once the caller has synchronised the stream
+	if (overlap) {
+		// velocities: nobody reads another rank's velocities before the next step's leaf kernel (or an export), so their
+		// broadcasts run on a second stream behind this step's kernels and overlap the next step's sort, tree build,
+		// upsweep and traversal; the consumer orders itself after ev_vel (comm_wait_velocities).
+		NB_CUDA_CHECK(cudaEventRecord(cm.ev_step, s.stream));
+		NB_CUDA_CHECK(cudaStreamWaitEvent(cm.vel_stream, cm.ev_step, 0));
+		if ((rc = exchange(s, s.velm[0], sizeof(float4), cm.vel_stream))) return rc;
+		NB_CUDA_CHECK(cudaEventRecord(cm.ev_vel, cm.vel_stream));
+		cm.vel_pending = true;
+	}
+	return NBODY_OK;
+}
+
+// Orders the compute stream after the velocity exchange in flight, if any. Called before the first reader or writer of the
+// velocity plane after a step: the next step's velocity gather, an export, an import.
+int comm_wait_velocities(Sim& s) {
+	Comm& cm = *s.comm;
+	if (!cm.vel_pending) return NBODY_OK;
+	NB_CUDA_CHECK(cudaStreamWaitEvent(s.stream, cm.ev_vel, 0));
+	cm.vel_pending = false;
 	return NBODY_OK;
 }
 
@@ -196,6 +223,9 @@ int comm_exchange_acc(Sim& s) {
 
 void comm_destroy(Sim& s) {
 	if (!s.comm) return;
+	if (s.comm->vel_stream) { cudaStreamSynchronize(s.comm->vel_stream); cudaStreamDestroy(s.comm->vel_stream); }
+	if (s.comm->ev_step) cudaEventDestroy(s.comm->ev_step);
+	if (s.comm->ev_vel) cudaEventDestroy(s.comm->ev_vel);
 	if (s.comm->comm) g_nccl.CommDestroy(s.comm->comm);
 	if (s.comm->part_host) cudaFreeHost(s.comm->part_host);
 	if (s.comm->work_host) cudaFreeHost(s.comm->work_host);
@@ -248,7 +278,10 @@ int nbody_cuda_create_distributed(const nbody_cuda_config* cfg, const nbody_part
 	    cudaMallocHost((void**) &cm.work_host, sizeof(float) * world) != cudaSuccess ||
 	    cudaMalloc((void**) &cm.work_dev, sizeof(float) * world) != cudaSuccess ||
 	    cudaMallocHost((void**) &cm.red_host, sizeof(float) * world) != cudaSuccess ||
-	    cudaMalloc((void**) &cm.red_dev, sizeof(float) * world) != cudaSuccess) { set_error("allocation of the partition tables failed"); return fail(NBODY_ERR_CUDA); }
+	    cudaMalloc((void**) &cm.red_dev, sizeof(float) * world) != cudaSuccess ||
+	    cudaStreamCreateWithFlags(&cm.vel_stream, cudaStreamNonBlocking) != cudaSuccess ||
+	    cudaEventCreateWithFlags(&cm.ev_step, cudaEventDisableTiming) != cudaSuccess ||
+	    cudaEventCreateWithFlags(&cm.ev_vel, cudaEventDisableTiming) != cudaSuccess) { set_error("allocation of the partition tables failed"); return fail(NBODY_ERR_CUDA); }
 	ncclUniqueId u;
 	std::memcpy(&u, id, 128);
 	ncclResult_t nr = g_nccl.CommInitRank(&cm.comm, world, u, rank);

@@ -142,6 +142,7 @@ void set_error(const std::string& msg);
 void launch_import(Sim& s, const nbody_particle* aos_dev, uint64_t n);                 // AoS48 -> SoA state
 void launch_export(Sim& s, nbody_particle* aos_dev, uint64_t n);                       // SoA state -> AoS48
 int launch_keys_sort_permute(Sim& s);                                                 // stage 1a: keys, radix sort, gather
+void launch_gather_velocities(Sim& s);                                                 // distributed: the velocity half of stage 1a's gather, delayed until the leaf kernel needs it
 void launch_tree_build(Sim& s);                                                        // stage 1b: linear octree, level-major
 void launch_upsweep(Sim& s);                                                           // stage 2: P2M + M2M
 void launch_traversal(Sim& s);                                                         // stage 3: dual-tree traversal -> lists

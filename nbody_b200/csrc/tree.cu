@@ -91,6 +91,24 @@ __global__ void k_gather(uint64_t n, const uint32_t* __restrict__ idx, const flo
 	}
 }
 
+// Distributed runs gather in two halves: positions (+ identity) right after the sort, velocities only before the leaf
+// kernel, because the other ranks' velocities of the previous step may still be travelling on the second stream (comm.cu).
+__global__ void k_gather_pos(uint64_t n, const uint32_t* __restrict__ idx, const float4* __restrict__ posq_in,
+                             const uint32_t* __restrict__ orig_in, float4* __restrict__ posq_out, uint32_t* __restrict__ orig_out) {
+	for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
+		const uint32_t j = idx[i];
+		posq_out[i] = posq_in[j];
+		orig_out[i] = orig_in[j];
+	}
+}
+__global__ void k_gather_vel(uint64_t n, const uint32_t* __restrict__ idx, const float4* __restrict__ velm_in, float4* __restrict__ velm_out) {
+	for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) velm_out[i] = velm_in[idx[i]];
+}
+void launch_gather_velocities(Sim& s) {
+	if (!s.comm) return;  // single GPU: k_gather already moved them
+	k_gather_vel<<<grid_for(s.n, 256), 256, 0, s.stream>>>(s.n, s.idx[0], s.velm[0], s.velm[1]);
+}
+
 size_t own_sort_temp_bytes(uint64_t n);  // sort.cu
 void launch_own_sort(Sim& s);            // sort.cu
 
@@ -119,7 +137,8 @@ int launch_keys_sort_permute(Sim& s) {
 	} else {
 		launch_own_sort(s);
 	}
-	k_gather<<<grid_for(n, 256), 256, 0, s.stream>>>(n, s.idx[0], s.posq[0], s.velm[0], s.orig[0], s.posq[1], s.velm[1], s.orig[1]);
+	if (s.comm) k_gather_pos<<<grid_for(n, 256), 256, 0, s.stream>>>(n, s.idx[0], s.posq[0], s.orig[0], s.posq[1], s.orig[1]);
+	else k_gather<<<grid_for(n, 256), 256, 0, s.stream>>>(n, s.idx[0], s.posq[0], s.velm[0], s.orig[0], s.posq[1], s.velm[1], s.orig[1]);
 	return NBODY_OK;
 }
 
