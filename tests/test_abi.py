@@ -78,3 +78,18 @@ def test_oracle_is_not_linked_into_the_product():
             if f.endswith((".py", ".cu", ".cuh")):
                 txt = open(os.path.join(root, f)).read()
                 assert "import oracle" not in txt and "liboracle" not in txt, f
+
+
+def test_plain_c99_client_compiles_and_runs(tmp_path):
+    """include/nbody_cuda.h is C, not C++: a -std=c99 -pedantic -Werror client links against the library and runs every
+    entry point that needs no device (examples/abi_host_check.c)."""
+    import subprocess
+    if not os.path.exists(nbody_b200.LIB_PATH):
+        nbody_b200.build_library()
+    exe = str(tmp_path / "abi_host_check")
+    libdir = os.path.dirname(nbody_b200.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "abi_host_check.c"), "-L" + libdir, "-lnbody_cuda", "-lm",
+                           "-Wl,-rpath," + libdir, "-o", exe])
+    r = subprocess.run([exe, str(tmp_path / "c.ckp")], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and "abi_host_check: ok" in r.stdout, r.stdout + r.stderr
