@@ -1,6 +1,6 @@
 """Single-GPU evidence at the particle counts of BASELINE configs 4 and 5: a few timed steps, then the accuracy of one force
 evaluation on the EVOLVED state against direct summation (GPU all-pairs kernel on a 65,536-target subsample, FP64 oracle on
-256 of them). Prints one JSON line per run.   python tools/scale_evidence.py KIND N CAPACITY [POOL_SCALE] [STEPS]"""
+256 of them). Prints one JSON line per run.   python tests/tools/scale_evidence.py KIND N CAPACITY [POOL_SCALE] [STEPS]"""
 import json, sys, time
 import numpy as np
 sys.path.insert(0, ".")
