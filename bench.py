@@ -369,10 +369,15 @@ def main():
 
 
 def launches_per_step(sim, world):
+    """Kernels of ours launched by one step() (matches the ncu launch lists under profiles/: 174 on one GPU at max_depth 21)."""
     d = int(sim.config.max_depth)
-    # keys, gather, tree init, per level (count, split), P2M, per level M2M, traversal init, per round (prep, traverse),
-    # two M2L launches, per level L2L, leaf kernel  (+ the radix sort's own launches, not counted)
-    return 1 + 1 + 1 + 2 * d + 1 + d + 1 + 2 * d + 2 + d + 1
+    sort = 8 * 5                 # per 8-bit pass: histogram, three scan kernels, scatter
+    tree = 1 + 2 * d             # init, per level (count, split)
+    upsweep = 1 + d              # P2M, per level M2M
+    traversal = 1 + 2 * d        # init, per round (prep, traverse)
+    far = 2 + d                  # two M2L launches, per level L2L
+    multi = 2 if world > 1 else 0  # partition snap, velocity half of the gather
+    return 1 + sort + 1 + tree + upsweep + traversal + far + 1 + multi   # + keys, gather, leaf kernel
 
 
 def cpu_baseline(args):
