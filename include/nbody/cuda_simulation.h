@@ -68,6 +68,21 @@ public:
 		check(nbody_cuda_checkpoint_load(checkpointPath.c_str(), config, &_sim));
 		check(nbody_cuda_get_time(_sim, &_time, nullptr));
 	}
+	// One rank of a multi-GPU run (one process or thread per GPU, Morton-range partition, NCCL):
+	// `particles` is THIS rank's contiguous slice of the global set, `globalOffset` the index of its first particle and
+	// `uniqueId` the 128 bytes nbody_cuda_comm_unique_id() returned on rank 0. Collective: every rank constructs at once.
+	CudaSimulation(device::vector_t bounds, std::vector<Particle> particles, Scalar timeStep, std::ostream& log,
+	               std::uint64_t globalCount, std::uint64_t globalOffset, int rank, int world, const std::uint8_t (&uniqueId)[128],
+	               const nbody_cuda_config* config = nullptr)
+	    : _log(log), _time(0.0f) {
+		nbody_cuda_config cfg;
+		if (config) cfg = *config; else nbody_cuda_default_config(&cfg);
+		for (int k = 0; k < 4; ++k) cfg.bounds[k] = bounds[k];
+		cfg.time_step = timeStep;
+		_log << "Creating rank " << rank << " of " << world << " of the CUDA simulation (" << particles.size() << " of " << globalCount << " particles).\n";
+		check(nbody_cuda_create_distributed(&cfg, reinterpret_cast<const nbody_particle*>(particles.data()), particles.size(), globalCount,
+		                                    globalOffset, rank, world, uniqueId, &_sim));
+	}
 	CudaSimulation(const CudaSimulation&) = delete;
 	CudaSimulation& operator=(const CudaSimulation&) = delete;
 	~CudaSimulation() override { nbody_cuda_destroy(_sim); }
@@ -93,6 +108,17 @@ public:
 		std::vector<std::uint32_t> p(nbody_cuda_num_particles(_sim));
 		check(nbody_cuda_get_permutation(_sim, p.data(), p.size()));
 		return p;
+	}
+
+	// Multi-GPU: the slice [first, first + count) of the tree-ordered particle array this rank owns after the last step, and
+	// just those particles (particles() returns the whole, replicated state on every rank).
+	void ownedRange(std::uint64_t& first, std::uint64_t& count) const { check(nbody_cuda_owned_range(_sim, &first, &count)); }
+	std::vector<Particle> ownedParticles() const {
+		std::uint64_t first = 0, count = 0;
+		ownedRange(first, count);
+		std::vector<Particle> out(count, Particle(Vector(), Vector(), 0.0f, 0.0f));
+		check(nbody_cuda_get_owned_particles(_sim, reinterpret_cast<nbody_particle*>(out.data()), count));
+		return out;
 	}
 
 	void saveCheckpoint(const std::string& path) const { check(nbody_cuda_checkpoint_save(_sim, path.c_str())); }

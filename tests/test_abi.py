@@ -95,3 +95,50 @@ def test_plain_c99_client_compiles_and_runs(tmp_path):
                            "-Wl,-rpath," + libdir, "-o", exe])
     r = subprocess.run([exe, str(tmp_path / "c.ckp")], capture_output=True, text=True, timeout=60)
     assert r.returncode == 0 and "abi_host_check: ok" in r.stdout, r.stdout + r.stderr
+
+
+CPP_CLIENT = r"""
+#include <iostream>
+#include <sstream>
+#include "nbody/cuda_simulation.h"
+int main() {
+	using S = nbody::CudaSimulation;
+	static_assert(sizeof(S::Particle) == 48 && alignof(S::Particle) == 16, "the reference's Particle layout");
+	std::vector<S::Particle> p(4, S::Particle(S::Vector(), S::Vector(), 1.0f, 1.0f));
+	std::ostringstream log;
+	int failures = 0;
+	try {                                          // every method of the wrapper is instantiated; none can run without a device
+		S sim({1.0f, 1.0f, 1.0f, 0.0f}, p, 1e-3f, log);
+		sim.step(); sim.particles(); sim.permutation(); sim.stats(); sim.setTimeStep(1e-3f); sim.timeStep(); sim.time();
+		sim.stepsDone(); sim.saveCheckpoint("x.ckp");
+		std::uint64_t a, b; sim.ownedRange(a, b); sim.ownedParticles();
+	} catch (const std::runtime_error& e) { ++failures; std::cout << e.what() << "\n"; }
+	try { S sim(std::string("/nonexistent.ckp"), log); } catch (const std::runtime_error&) { ++failures; }
+	try {
+		std::uint8_t id[128] = {0};
+		S sim({1.0f, 1.0f, 1.0f, 0.0f}, p, 1e-3f, log, 8, 0, 0, 2, id);
+	} catch (const std::runtime_error&) { ++failures; }
+	std::cout << "failures " << failures << "\n";
+	return 0;
+}
+"""
+
+
+def test_cpp_wrapper_compiles_and_fails_loudly_without_a_device(tmp_path):
+    """include/nbody/cuda_simulation.h (the drop-in for OpenClSimulation) and the demo driver compile with -Wall -Wextra
+    -Werror; without a GPU every constructor throws std::runtime_error (the reference's error channel), nothing falls back."""
+    import subprocess
+    import torch
+    libdir = os.path.dirname(nbody_b200.LIB_PATH)
+    src = tmp_path / "client.cpp"
+    src.write_text(CPP_CLIENT)
+    common = ["-std=c++14", "-O1", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(ROOT, "include"), "-L" + libdir, "-lnbody_cuda",
+              "-Wl,-rpath," + libdir]
+    subprocess.check_call(["g++", str(src), "-o", str(tmp_path / "client")] + common)
+    subprocess.check_call(["g++", os.path.join(ROOT, "examples", "nbody_main.cpp"), "-o", str(tmp_path / "nbody_main")] + common)
+    if torch.cuda.is_available():
+        return
+    r = subprocess.run([str(tmp_path / "client")], capture_output=True, text=True, timeout=60, cwd=str(tmp_path))
+    assert r.returncode == 0 and "failures 3" in r.stdout and "no CPU fallback" in r.stdout, r.stdout + r.stderr
+    r = subprocess.run([str(tmp_path / "nbody_main"), "--n", "100", "--steps", "1", "--quiet", "--csv", "none"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 1 and "no CPU fallback" in r.stderr
