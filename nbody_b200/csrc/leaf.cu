@@ -46,6 +46,39 @@ __device__ __forceinline__ void leaf_cp_async_commit() { asm volatile("cp.async.
 __device__ __forceinline__ void leaf_cp_async_wait1() { asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
 __device__ __forceinline__ void leaf_cp_async_wait0() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
+// ---- experimental tile fill with TMA 1-D bulk copies (build with -DNBODY_LEAF_BULK=1; NOT the default, not yet run on hardware) ----
+// One cp.async.bulk per contiguous run of source particles (adjacent list entries are merged: 57 particles = 910 B per run on the
+// Plummer benchmark, tests/tools/p2p_list_structure.py) with completion on a per-warp, per-buffer mbarrier, instead of eight rows of
+// per-lane 16-byte cp.async copies driven by a flat-slot -> entry bitmap. DESIGN.md section 10 has the instruction budget.
+#ifndef NBODY_LEAF_BULK
+#define NBODY_LEAF_BULK 0
+#endif
+__device__ __forceinline__ unsigned leaf_smem_addr(const void* p) { return (unsigned) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void leaf_mbar_init(uint64_t* bar, unsigned count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(leaf_smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void leaf_mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(leaf_smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void leaf_mbar_wait(uint64_t* bar, unsigned parity) {
+	asm volatile(
+	    "{\n"
+	    ".reg .pred P1;\n"
+	    "LEAF_WAIT:\n"
+	    "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+	    "@P1 bra LEAF_DONE;\n"
+	    "bra LEAF_WAIT;\n"
+	    "LEAF_DONE:\n"
+	    "}\n" ::"r"(leaf_smem_addr(bar)), "r"(parity)
+	    : "memory");
+}
+__device__ __forceinline__ void leaf_bulk_copy(void* smem_dst, const void* gmem_src, unsigned bytes, uint64_t* bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(leaf_smem_addr(smem_dst)),
+	             "l"(gmem_src), "r"(bytes), "r"(leaf_smem_addr(bar))
+	             : "memory");
+}
+__device__ __forceinline__ void leaf_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
 template <bool SOFT>
 __device__ __forceinline__ void p2p_interact(const float4& s, float tx, float ty, float tz, float eps2, float& ax, float& ay, float& az) {
 	const float dx = s.x - tx, dy = s.y - ty, dz = s.z - tz;
@@ -143,6 +176,17 @@ __global__ void __launch_bounds__(kLeafWarps * 32, kLeafMinCtas) k_leaf(const Le
 	__shared__ float4 sbuf[kLeafWarps][2][kLeafTile];
 	__shared__ float4 stgt[kLeafWarps][16];
 	const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+#if NBODY_LEAF_BULK
+	__shared__ __align__(8) uint64_t sbar[kLeafWarps][2];  // one mbarrier per warp and tile buffer; a single arrival (lane 0) + the copied bytes
+	unsigned bar_parity = 0u;                               // bit b: the phase parity the next wait on buffer b expects
+	if (lane == 0) {
+		leaf_mbar_init(&sbar[w][0], 1u);
+		leaf_mbar_init(&sbar[w][1], 1u);
+		asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+	}
+	leaf_fence_proxy_async();
+	__syncwarp();
+#endif
 	if (a.c->status) return;  // a pool overflowed: the host grows it and re-runs the step; leave the state untouched
 	const uint32_t n_nodes = a.c->n_nodes;
 	const uint32_t own_first = a.c->part[a.rank], own_end = a.c->part[a.rank + 1];
@@ -208,6 +252,23 @@ __global__ void __launch_bounds__(kLeafWarps * 32, kLeafMinCtas) k_leaf(const Le
 					if (nfull < nvalid) skip = (nfull ? 0u : skip) + (fill - (nfull ? used : 0u));  // entry nfull straddles the tile end
 					else skip = 0u;
 					e0 += nfull;
+#if NBODY_LEAF_BULK
+					// one bulk copy per contiguous run: lane l heads a run if its entry does not start where lane l-1's ends
+					const uint32_t prev_end = __shfl_up_sync(0xffffffffu, ent.x + ent.y, 1);
+					const bool head = lane < nvalid && (lane == 0u || ent.x != prev_end);
+					const unsigned heads = __ballot_sync(0xffffffffu, head);
+					const uint32_t start = inc - v;                                  // flat slot of this entry's first unconsumed particle
+					const unsigned above = lane < 31u ? heads >> (lane + 1u) : 0u;   // heads after this lane
+					const uint32_t next = above ? lane + (uint32_t) __ffs(above) : nvalid;  // lane of the next run's head (or one past the entries)
+					const uint32_t run_end = min(__shfl_sync(0xffffffffu, start, next & 31u), avail);  // (lane `next` == nvalid holds v = 0: its start is avail)
+					const uint32_t stop = min(next < nvalid ? run_end : avail, (uint32_t) kLeafTile);
+					uint64_t* bar = &sbar[w][tile == sbuf[w][0] ? 0 : 1];
+					leaf_fence_proxy_async();   // the generic-proxy reads / padding writes of this buffer's previous use precede the async writes
+					__syncwarp();
+					if (lane == 0u) leaf_mbar_expect_tx(bar, 16u * fill);
+					__syncwarp();
+					if (head && start < stop) leaf_bulk_copy(tile + start, a.posq + (ent.x + sk), 16u * (stop - start), bar);
+#else
 					const uint32_t src0 = ent.x + sk - (inc - v);  // particle index of flat slot f inside entry l: src0 + f
 					uint32_t pc = 0;
 #pragma unroll
@@ -221,9 +282,12 @@ __global__ void __launch_bounds__(kLeafWarps * 32, kLeafMinCtas) k_leaf(const Le
 						if (f < fill) leaf_cp_async16(tile + f, a.posq + (s0 + f));
 						pc += __popc(word);
 					}
+#endif
 					// pad to whole row groups with zero-charge sources (only the last tile of a segment is short)
 					for (uint32_t f = fill + lane; f < (fill + kLeafPad - 1u) / kLeafPad * kLeafPad; f += 32u) tile[f] = make_float4(0.f, 0.f, 0.f, 0.f);
+#if !NBODY_LEAF_BULK
 					leaf_cp_async_commit();
+#endif
 				};
 				uint2 ent_cur = make_uint2(0u, 0u), ent_nxt = make_uint2(0u, 0u);
 				uint32_t fill_cur = 0;
@@ -235,16 +299,25 @@ __global__ void __launch_bounds__(kLeafWarps * 32, kLeafMinCtas) k_leaf(const Le
 				while (has_cur) {
 					uint32_t fill_nxt = 0;
 					if (has_nxt) stage(ent_nxt, sbuf[w][cur ^ 1], fill_nxt);
+#if !NBODY_LEAF_BULK
 					else leaf_cp_async_commit();  // empty group keeps the wait_group arithmetic uniform
+#endif
 					uint2 ent_nn = make_uint2(0u, 0u);
 					const bool has_nn = has_nxt && fetch(ent_nn);  // entries of the batch after next: in flight during the math
+#if NBODY_LEAF_BULK
+					leaf_mbar_wait(&sbar[w][cur], (bar_parity >> cur) & 1u);
+					bar_parity ^= 1u << cur;
+#else
 					leaf_cp_async_wait1();
+#endif
 					tile_rows<SOFT>(G, sbuf[w][cur], (fill_cur + 31u) >> 5, lane, stgt[w], a.eps2, ax, ay, az);
 					nsrc += fill_cur;
 					ent_nxt = ent_nn; fill_cur = fill_nxt; has_cur = has_nxt; has_nxt = has_nn;
 					cur ^= 1;
 				}
+#if !NBODY_LEAF_BULK
 				leaf_cp_async_wait0();
+#endif
 				transpose_reduce16(ax, lane);
 				transpose_reduce16(ay, lane);
 				transpose_reduce16(az, lane);
