@@ -1,27 +1,45 @@
 #!/bin/bash
-# One gpurun call, 1 GPU (first call of round 2): the leaf kernel's TMA tile fill (-DNBODY_LEAF_BULK=1), which was written and
-# model-checked (tests/test_leaf_fill_model.py) in round 1 after the GPU budget was spent and has NOT run on hardware.
-# Build both libraries in the authoring container first (the .so files travel with the snapshot):
-#     python nbody_b200/build.py
-#     NBODY_BUILD_TAG=bulk NBODY_BUILD_DEFS="-DNBODY_LEAF_BULK=1" python nbody_b200/build.py
-# Order: parity of the experimental library under a short timeout (an mbarrier mistake hangs the kernel: the timeout, not gpurun's
-# limit, must end it), then A/B bench lines, then one ncu capture of k_leaf from the faster of the two.
+# One gpurun call, 1 GPU (first call of round 2): the leaf-kernel variants written and model-checked in round 1 after the GPU
+# budget was spent — NONE of them has run on hardware:
+#   bulk     -DNBODY_LEAF_BULK=1    tile fill with one cp.async.bulk per contiguous source run (tests/test_leaf_fill_model.py)
+#   x2       -DNBODY_P2P_F32X2=1    two-wide FP32 interactions (FADD2 / FMUL2 / FFMA2), k_leaf and k_direct
+#   bulk_x2  both
+# Build all libraries in the authoring container first (the .so files travel with the snapshot):
+#     tools/build_variants.sh
+# Order: FFMA2 microbenchmark (does a packed instruction cost one issue slot?), then per variant: parity under a short timeout
+# (an mbarrier mistake hangs the kernel: the timeout, not gpurun's limit, must end it), bench line; last, one ncu capture of
+# k_leaf from the fastest variant that passed.
 mkdir -p gpurun_out
-BULK=$PWD/nbody_b200/libnbody_cuda_bulk.so
-if [ ! -f "$BULK" ]; then echo "no $BULK: build it before the call"; exit 1; fi
-NBODY_CUDA_LIB=$BULK timeout 300 python -m pytest tests/test_golden_fmm.py tests/test_gpu_parity.py -q -m gpu -x > gpurun_out/r02a_parity_bulk.log 2>&1
-rc=$?; echo "rc=$rc" >> gpurun_out/r02a_parity_bulk.log; tail -6 gpurun_out/r02a_parity_bulk.log
+if [ -x tools/micro/fma_peak ]; then timeout 120 tools/micro/fma_peak > gpurun_out/r02a_fma_peak.log 2>&1; grep -h "FFMA2\|P2P chain" gpurun_out/r02a_fma_peak.log | grep "occ=4"; fi
 timeout 150 python bench.py --no-cpu-baseline --no-reference-capacity > gpurun_out/r02a_bench_default.json 2> gpurun_out/r02a_bench_default.err; echo "bench default rc=$?"
-if [ $rc -eq 0 ]; then
-	NBODY_CUDA_LIB=$BULK timeout 150 python bench.py --no-cpu-baseline --no-reference-capacity > gpurun_out/r02a_bench_bulk.json 2> gpurun_out/r02a_bench_bulk.err; echo "bench bulk rc=$?"
-	NBODY_CUDA_LIB=$BULK timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_leaf -c 1 -o gpurun_out/r02a_leaf_bulk \
-		python tools/prof_step.py 16777216 1 4 48 > gpurun_out/r02a_ncu_bulk.log 2>&1; echo "ncu rc=$?"
-fi
-python - <<'PY'
+for tag in x2 bulk bulk_x2; do
+	LIB=$PWD/nbody_b200/libnbody_cuda_$tag.so
+	if [ ! -f "$LIB" ]; then echo "no $LIB: build it before the call"; continue; fi
+	NBODY_CUDA_LIB=$LIB timeout 300 python -m pytest tests/test_golden_fmm.py tests/test_gpu_parity.py -q -m gpu -x > gpurun_out/r02a_parity_$tag.log 2>&1
+	rc=$?; echo "rc=$rc" >> gpurun_out/r02a_parity_$tag.log; echo "== $tag parity rc=$rc"; tail -4 gpurun_out/r02a_parity_$tag.log
+	if [ $rc -eq 0 ]; then
+		NBODY_CUDA_LIB=$LIB timeout 150 python bench.py --no-cpu-baseline --no-reference-capacity > gpurun_out/r02a_bench_$tag.json 2> gpurun_out/r02a_bench_$tag.err; echo "bench $tag rc=$?"
+	fi
+done
+BEST=$(python - <<'PY'
 import json
-for f in ("r02a_bench_default.json", "r02a_bench_bulk.json"):
+best, best_ms = "default", 1e9
+for tag in ("default", "x2", "bulk", "bulk_x2"):
     try:
-        d = json.load(open("gpurun_out/" + f)); print(f, round(d["ms_per_step"], 3), {k: round(v, 2) for k, v in d["stage_ms"].items()}, round(d["roofline"]["frac"], 4))
+        d = json.load(open(f"gpurun_out/r02a_bench_{tag}.json"))
+        ms = d["stage_ms"]["ms_leaf"]
+        import sys
+        print(tag, round(d["ms_per_step"], 3), {k: round(v, 2) for k, v in d["stage_ms"].items()}, "leaf frac", round(d["roofline"]["frac"], 4),
+              "all-pairs frac", round(d["p2p_fp32_tflops"]["all_pairs_frac_of_peak"], 4), file=sys.stderr)
+        if ms < best_ms:
+            best, best_ms = tag, ms
     except Exception as e:
-        print(f, "unreadable", e)
+        import sys
+        print(tag, "unreadable", e, file=sys.stderr)
+print(best)
 PY
+)
+echo "fastest leaf kernel: $BEST"
+LIB=$PWD/nbody_b200/libnbody_cuda.so; [ "$BEST" != default ] && LIB=$PWD/nbody_b200/libnbody_cuda_$BEST.so
+NBODY_CUDA_LIB=$LIB timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_leaf -c 1 -o gpurun_out/r02a_leaf_$BEST \
+	python tools/prof_step.py 16777216 1 4 48 > gpurun_out/r02a_ncu_$BEST.log 2>&1; echo "ncu rc=$?"
