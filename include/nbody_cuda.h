@@ -62,8 +62,11 @@ enum {
 	NBODY_FLAG_DIRECT = 4u,       /* all-pairs direct sum instead of the FMM (validation / P2P microbenchmark) */
 	NBODY_FLAG_CUB_SORT = 8u,     /* sort with CUB's DeviceRadixSort instead of the built-in radix sort (comparison only) */
 	NBODY_FLAG_STATIC_PARTITION = 16u, /* multi-GPU: equal particle counts per rank every step instead of per-step load rebalancing */
-	NBODY_FLAG_NO_OVERLAP = 32u       /* multi-GPU: exchange the velocities on the compute stream inside step() instead of on a second
+	NBODY_FLAG_NO_OVERLAP = 32u,      /* multi-GPU: exchange the velocities on the compute stream inside step() instead of on a second
 	                                     stream overlapped with the next step's sort / tree / traversal (comparison only) */
+	NBODY_FLAG_DIST_SORT = 64u        /* multi-GPU, experimental: every rank sorts only the keys of its own slice, the sorted runs are
+	                                     all-gathered and merged pairwise, instead of every rank sorting all keys. Same permutation
+	                                     bit for bit. Ignored on a single GPU and with NBODY_FLAG_CUB_SORT. */
 };
 
 typedef struct nbody_cuda_config {

@@ -18,7 +18,7 @@ LIB_PATH = os.environ.get("NBODY_CUDA_LIB") or os.path.join(_HERE, "libnbody_cud
 PARTICLE_FLOATS = 12  # 48-byte AoS record: position[4], velocity[4], mass, charge, pad[2]
 
 KICK_DRIFT, EXPLICIT_EULER = 0, 1
-FLAG_KEEP_LISTS, FLAG_NO_INTEGRATE, FLAG_DIRECT, FLAG_CUB_SORT, FLAG_STATIC_PARTITION, FLAG_NO_OVERLAP = 1, 2, 4, 8, 16, 32
+FLAG_KEEP_LISTS, FLAG_NO_INTEGRATE, FLAG_DIRECT, FLAG_CUB_SORT, FLAG_STATIC_PARTITION, FLAG_NO_OVERLAP, FLAG_DIST_SORT = 1, 2, 4, 8, 16, 32, 64
 
 EXPORTED_SYMBOLS = [
     "nbody_cuda_default_config", "nbody_cuda_create", "nbody_cuda_destroy", "nbody_cuda_set_particles", "nbody_cuda_step",

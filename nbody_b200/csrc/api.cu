@@ -130,11 +130,15 @@ int validate(const nbody_cuda_config* cfg, uint64_t n) {
 }
 
 // One attempt at a step: enqueue every stage, then one synchronisation to read the control block.
-int run_pipeline(Sim& s) {
+// `retry`: a repeat of the same step after a pool overflow. With the distributed sort the first attempt's sorted keys, permutation
+// and gathered positions are kept (nothing has overwritten them: the leaf kernel refuses to run after an overflow), because the
+// sort contains a collective and a rank retries alone — its peers are already waiting in the end-of-step exchange.
+int run_pipeline(Sim& s, bool retry) {
 	cudaStream_t st = s.stream;
 	const bool direct = (s.cfg.flags & NBODY_FLAG_DIRECT) != 0;
+	const bool keep_sort = retry && s.comm && (s.cfg.flags & NBODY_FLAG_DIST_SORT) && !(s.cfg.flags & NBODY_FLAG_CUB_SORT);
 	NB_CUDA_CHECK(cudaEventRecord(s.ev[0], st));
-	int rc = launch_keys_sort_permute(s);
+	int rc = keep_sort ? NBODY_OK : launch_keys_sort_permute(s);
 	if (rc) return rc;
 	NB_CUDA_CHECK(cudaEventRecord(s.ev[1], st));
 	launch_tree_build(s);
@@ -358,7 +362,7 @@ int nbody_cuda_step(nbody_cuda_sim* sim, float* time_out) {
 	NB_CUDA_CHECK(cudaSetDevice(s->device));
 	s->stats.retries = 0;
 	for (int attempt = 0;; ++attempt) {
-		int rc = run_pipeline(*s);
+		int rc = run_pipeline(*s, attempt > 0);
 		if (rc) return rc;
 		const uint32_t status = s->ctrl_host->status;
 		if (status == 0) break;

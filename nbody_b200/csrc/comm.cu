@@ -151,6 +151,26 @@ static int exchange(Sim& s, void* buf, size_t elem_bytes, cudaStream_t st = null
 
 int comm_exchange_aos(Sim& s) { return exchange(s, s.aos_dev, sizeof(nbody_particle)); }
 
+// Distributed sort (NBODY_FLAG_DIST_SORT). The slices are those of the last completed step (or of creation): every rank knows
+// all boundaries, and the state array every rank holds is in that order.
+void comm_own_slice(const Sim& s, uint64_t* first, uint64_t* count) {
+	const Comm& cm = *s.comm;
+	*first = cm.part_host[cm.rank];
+	*count = cm.part_host[cm.rank + 1] - cm.part_host[cm.rank];
+}
+
+// All-gather of the slice-wise sorted (key, index) runs in keys[0] / idx[0], 12 bytes per particle, on the compute stream;
+// returns the run boundaries for the merge rounds.
+int comm_sort_exchange(Sim& s, uint32_t* bound, int* nruns) {
+	Comm& cm = *s.comm;
+	int rc;
+	if ((rc = exchange(s, s.keys[0], sizeof(uint64_t)))) return rc;
+	if ((rc = exchange(s, s.idx[0], sizeof(uint32_t)))) return rc;
+	for (int r = 0; r <= cm.world; ++r) bound[r] = cm.part_host[r];
+	*nruns = cm.world;
+	return NBODY_OK;
+}
+
 // `own_ms`: device time this rank spent on the stages it runs for its own slice only (the input of the next
 // step's rebalancing); all-gathered next to the slices, on the host after the step's final synchronisation.
 int comm_step_exchange(Sim& s, float own_ms) {

@@ -142,6 +142,10 @@ void set_error(const std::string& msg);
 void launch_import(Sim& s, const nbody_particle* aos_dev, uint64_t n);                 // AoS48 -> SoA state
 void launch_export(Sim& s, nbody_particle* aos_dev, uint64_t n);                       // SoA state -> AoS48
 int launch_keys_sort_permute(Sim& s);                                                 // stage 1a: keys, radix sort, gather
+void launch_own_sort_range(Sim& s, uint64_t first, uint64_t n);                        // the radix sort over a sub-range of keys[0] / idx[0]
+void launch_merge_runs(Sim& s, const uint32_t* bound, int nruns);                      // distributed sort: pairwise merges of sorted runs
+int comm_sort_exchange(Sim& s, uint32_t* bound, int* nruns);                           // distributed sort: all-gather of the sorted runs (comm.cu)
+void comm_own_slice(const Sim& s, uint64_t* first, uint64_t* count);                   // distributed: this rank's slice of the state order
 void launch_gather_velocities(Sim& s);                                                 // distributed: the velocity half of stage 1a's gather, delayed until the leaf kernel needs it
 void launch_tree_build(Sim& s);                                                        // stage 1b: linear octree, level-major
 void launch_upsweep(Sim& s);                                                           // stage 2: P2M + M2M

@@ -6,7 +6,10 @@
 // std::stable_sort): ties between equal keys keep their previous order.
 // HBM traffic per pass: 8 B (histogram read) + 12 B read + 12 B write per element; the scatter sorts each tile by
 // digit in shared memory first, so its global writes are contiguous runs.
+#include <utility>
+
 #include "common.cuh"
+#include "merge_path.h"
 
 namespace nbody {
 
@@ -182,16 +185,17 @@ size_t own_sort_temp_bytes(uint64_t n) {
 	return (size_t) (hist + sums + 64) * sizeof(uint32_t);
 }
 
-// Sorts (keys[0], idx[0]) ascending by the low 63 key bits; the result ends in keys[0] / idx[0] (8 passes = even).
-void launch_own_sort(Sim& s) {
-	const uint64_t n = s.n;
+// Sorts the `n` (key, index) pairs starting at element `first` of (keys[0], idx[0]) ascending by the low 63 key bits; the result
+// ends in the same range of keys[0] / idx[0] (8 passes = even). keys[1] / idx[1] are scratch over the same range.
+void launch_own_sort_range(Sim& s, uint64_t first, uint64_t n) {
+	if (n == 0) return;
 	const uint32_t nblocks = (uint32_t) ((n + kSortTile - 1) / kSortTile);
 	const uint32_t hist_n = 256u * nblocks;
 	const uint32_t nsums = (hist_n + kScanTile - 1) / kScanTile;
 	uint32_t* hist = static_cast<uint32_t*>(s.sort_tmp);
 	uint32_t* sums = hist + hist_n;
-	uint64_t* kin = s.keys[0]; uint64_t* kout = s.keys[1];
-	uint32_t* vin = s.idx[0]; uint32_t* vout = s.idx[1];
+	uint64_t* kin = s.keys[0] + first; uint64_t* kout = s.keys[1] + first;
+	uint32_t* vin = s.idx[0] + first; uint32_t* vout = s.idx[1] + first;
 	cudaFuncSetAttribute(k_sort_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(ScatterSmem));
 	for (int pass = 0; pass < 8; ++pass) {
 		const int shift = 8 * pass;
@@ -203,6 +207,66 @@ void launch_own_sort(Sim& s) {
 		uint64_t* tk = kin; kin = kout; kout = tk;
 		uint32_t* tv = vin; vin = vout; vout = tv;
 	}
+}
+
+void launch_own_sort(Sim& s) { launch_own_sort_range(s, 0, s.n); }
+
+// ---- distributed sort (NBODY_FLAG_DIST_SORT): pairwise stable merges of the all-gathered, slice-wise sorted runs ----
+// One CTA per tile of kMergeTile outputs of one pair of adjacent runs (merge_path.h has the plan and the index arithmetic,
+// checked on the CPU by tests/test_merge_host.py). Two threads find the tile's split points by merge-path searches in global
+// memory (~2 x 24 dependent loads, hidden by the other resident CTAs), the inputs are staged in shared memory with coalesced
+// loads, every thread merges kMergeVT outputs from its own split point, and the merged tile goes back through shared memory so
+// that the global writes are contiguous. HBM traffic: 12 B read + 12 B written per element and round.
+__global__ void __launch_bounds__(kMergeThreads) k_merge_runs(const MergePlan pl, const uint64_t* __restrict__ kin, const uint32_t* __restrict__ vin,
+                                                              uint64_t* __restrict__ kout, uint32_t* __restrict__ vout) {
+	__shared__ uint64_t sk[kMergeTile];
+	__shared__ uint32_t sv[kMergeTile];
+	__shared__ uint32_t split[2];
+	const MergeTileRange r = merge_tile_range(pl, blockIdx.x);
+	const uint64_t* A = kin + r.a0;
+	const uint64_t* B = kin + r.a0 + r.na;
+	if (threadIdx.x == 0) split[0] = merge_path(A, r.na, B, r.nb, r.d0);
+	if (threadIdx.x == 32) split[1] = merge_path(A, r.na, B, r.nb, r.d1);
+	__syncthreads();
+	const uint32_t i0 = split[0], i1 = split[1], j0 = r.d0 - i0, j1 = r.d1 - i1;
+	const uint32_t ca = i1 - i0, cb = j1 - j0, cnt = ca + cb;  // cnt = d1 - d0 <= kMergeTile
+	for (uint32_t t = threadIdx.x; t < cnt; t += kMergeThreads) {
+		const uint32_t src = t < ca ? r.a0 + i0 + t : r.a0 + r.na + j0 + (t - ca);
+		sk[t] = kin[src];
+		sv[t] = vin[src];
+	}
+	__syncthreads();
+	const uint32_t dd = min(threadIdx.x * (uint32_t) kMergeVT, cnt);
+	const uint32_t i = merge_path(sk, ca, sk + ca, cb, dd), j = dd - i;
+	uint64_t rk[kMergeVT];
+	uint32_t rv[kMergeVT];
+	merge_serial(sk, sv, ca, sk + ca, sv + ca, cb, i, j, rk, rv);
+	__syncthreads();
+#pragma unroll
+	for (int u = 0; u < kMergeVT; ++u)
+		if (dd + u < cnt) { sk[dd + u] = rk[u]; sv[dd + u] = rv[u]; }
+	__syncthreads();
+	for (uint32_t t = threadIdx.x; t < cnt; t += kMergeThreads) {
+		kout[r.a0 + r.d0 + t] = sk[t];
+		vout[r.a0 + r.d0 + t] = sv[t];
+	}
+}
+
+// (keys[0], idx[0]) hold `nruns` sorted runs with boundaries bound[0..nruns] (bound[nruns] = n): merge them into one sorted
+// sequence. Rounds ping-pong between the two buffers; the buffer pointers are swapped at the end if needed, so the result is
+// in keys[0] / idx[0] like every other sort path.
+void launch_merge_runs(Sim& s, const uint32_t* bound, int nruns) {
+	MergePlan pl{};
+	pl.nruns = nruns;
+	for (int r = 0; r <= nruns; ++r) pl.bound[r] = bound[r];
+	int from = 0;
+	while (pl.nruns > 1) {
+		const uint32_t tiles = merge_plan_tiles(pl);
+		if (tiles) k_merge_runs<<<tiles, kMergeThreads, 0, s.stream>>>(pl, s.keys[from], s.idx[from], s.keys[from ^ 1], s.idx[from ^ 1]);
+		from ^= 1;
+		pl = merge_plan_next(pl);
+	}
+	if (from) { std::swap(s.keys[0], s.keys[1]); std::swap(s.idx[0], s.idx[1]); }
 }
 
 }  // namespace nbody

@@ -80,6 +80,16 @@ __global__ void k_keys(uint64_t n, const float4* __restrict__ posq, float sx, fl
 		idx[i] = (uint32_t) i;
 	}
 }
+// the same for the elements [first, first + count) only (distributed sort)
+__global__ void k_keys_range(uint64_t first, uint64_t count, const float4* __restrict__ posq, float sx, float sy, float sz,
+                             uint64_t* __restrict__ keys, uint32_t* __restrict__ idx) {
+	for (uint64_t t = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; t < count; t += (uint64_t) gridDim.x * blockDim.x) {
+		const uint64_t i = first + t;
+		const float4 p = posq[i];
+		keys[i] = spread3(quantise(p.x, sx)) | spread3(quantise(p.y, sy)) << 1 | spread3(quantise(p.z, sz)) << 2;
+		idx[i] = (uint32_t) i;
+	}
+}
 __global__ void k_gather(uint64_t n, const uint32_t* __restrict__ idx, const float4* __restrict__ posq_in,
                          const float4* __restrict__ velm_in, const uint32_t* __restrict__ orig_in, float4* __restrict__ posq_out,
                          float4* __restrict__ velm_out, uint32_t* __restrict__ orig_out) {
@@ -125,6 +135,23 @@ size_t sort_temp_bytes(uint64_t n) {
 int launch_keys_sort_permute(Sim& s) {
 	const uint64_t n = s.n;
 	const float sx = 2097152.0f / s.cfg.bounds[0], sy = 2097152.0f / s.cfg.bounds[1], sz = 2097152.0f / s.cfg.bounds[2];
+	if (s.comm && (s.cfg.flags & NBODY_FLAG_DIST_SORT) && !(s.cfg.flags & NBODY_FLAG_CUB_SORT)) {
+		// Distributed sort: the state is in the previous step's tree order and this rank's slice of it is [first, first + count).
+		// Keys and radix sort for that slice only (idx = index into the whole state array), all-gather of the sorted runs,
+		// pairwise stable merges. Run r holds lower previous indices than run r + 1, so the merged permutation is the stable
+		// sort of all keys, bit for bit what the replicated sort below computes (tests/test_merge_host.py).
+		uint64_t first = 0, count = 0;
+		comm_own_slice(s, &first, &count);
+		if (count) k_keys_range<<<grid_for(count, 256), 256, 0, s.stream>>>(first, count, s.posq[0], sx, sy, sz, s.keys[0], s.idx[0]);
+		launch_own_sort_range(s, first, count);
+		uint32_t bound[17];
+		int nruns = 0;
+		const int rc = comm_sort_exchange(s, bound, &nruns);
+		if (rc) return rc;
+		launch_merge_runs(s, bound, nruns);
+		k_gather_pos<<<grid_for(n, 256), 256, 0, s.stream>>>(n, s.idx[0], s.posq[0], s.orig[0], s.posq[1], s.orig[1]);
+		return NBODY_OK;
+	}
 	k_keys<<<grid_for(n, 256), 256, 0, s.stream>>>(n, s.posq[0], sx, sy, sz, s.keys[0], s.idx[0]);
 	if (s.cfg.flags & NBODY_FLAG_CUB_SORT) {
 		// comparison path only: CUB's onesweep sort, the bar the hand-written sort is measured against

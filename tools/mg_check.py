@@ -14,11 +14,12 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 200000
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 kind = sys.argv[3] if len(sys.argv) > 3 else "plummer"
 eta = float(sys.argv[4]) if len(sys.argv) > 4 else 0.0  # > 0: variable time step (the maximum |a| is all-gathered across ranks)
+flags = int(sys.argv[5]) if len(sys.argv) > 5 else 0     # nbody_cuda_config.flags of the DISTRIBUTED run (e.g. 64 = NBODY_FLAG_DIST_SORT); the 1-GPU reference runs with 0
 lo, hi = n * rank // world, n * (rank + 1) // world
 P = workloads.plummer(hi - lo, start=lo, n_total=n) if kind == "plummer" else workloads.GENERATORS[kind](n)[lo:hi]
 uid = [nbody_b200.comm_unique_id() if rank == 0 else None]
 dist.broadcast_object_list(uid, src=0)
-sim = nbody_b200.CudaSimulation([1, 1, 1], P, 1e-3, device=local, time_step_eta=eta,
+sim = nbody_b200.CudaSimulation([1, 1, 1], P, 1e-3, device=local, time_step_eta=eta, flags=flags,
                                 _distributed={"unique_id": uid[0], "n_global": n, "global_offset": lo, "rank": rank, "world": world})
 ranges = []
 dts = []
