@@ -223,6 +223,14 @@ int nbody_cuda_get_time(nbody_cuda_sim* sim, float* time, uint64_t* steps_done);
 int nbody_cuda_direct_field(int device, const float* src_posq, uint64_t n_src, const float* tgt_pos4, uint64_t n_tgt,
                             float softening, float* field_xyz, float* ms, uint32_t repeats);
 
+/* The device side of the distributed sort (NBODY_FLAG_DIST_SORT) on ONE GPU, without NCCL: `keys` (host, 63-bit) is cut
+ * into `nruns` slices with boundaries bound[0..nruns] (bound[0] = 0, bound[nruns] = n, 1..16 runs); every slice is radix-sorted
+ * as a rank would sort its own, then the runs are merged pairwise as every rank does after the all-gather. Returns the sorted
+ * keys and, per output position, the input index: by contract the stable sort of all keys, whatever the boundaries.
+ * A validation entry point (tests, bring-up of the multi-GPU path on a one-GPU box); no reference counterpart. */
+int nbody_cuda_sort_runs(int device, const uint64_t* keys, uint64_t n, const uint32_t* bound, int nruns, uint64_t* keys_out,
+                         uint32_t* index_out);
+
 /* ---- multi-GPU (one process per GPU; Morton-range partition, NCCL) ------- */
 /* 128-byte NCCL unique id created on rank 0 and sent to the other ranks by the caller. */
 int nbody_cuda_comm_unique_id(uint8_t id[128]);

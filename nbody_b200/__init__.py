@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = [
     "nbody_cuda_default_config", "nbody_cuda_create", "nbody_cuda_destroy", "nbody_cuda_set_particles", "nbody_cuda_step",
     "nbody_cuda_num_particles", "nbody_cuda_get_particles", "nbody_cuda_get_permutation", "nbody_cuda_get_accelerations",
     "nbody_cuda_get_keys", "nbody_cuda_get_tree", "nbody_cuda_get_lists", "nbody_cuda_get_expansions", "nbody_cuda_get_stats",
-    "nbody_cuda_direct_field", "nbody_cuda_comm_unique_id", "nbody_cuda_create_distributed", "nbody_cuda_owned_range",
+    "nbody_cuda_direct_field", "nbody_cuda_sort_runs", "nbody_cuda_comm_unique_id", "nbody_cuda_create_distributed", "nbody_cuda_owned_range",
     "nbody_cuda_get_owned_particles", "nbody_cuda_set_owned_particles", "nbody_cuda_rebalance",
     "nbody_cuda_set_time_step", "nbody_cuda_get_time_step", "nbody_cuda_next_time_step", "nbody_cuda_get_time",
     "nbody_cuda_checkpoint_save", "nbody_cuda_checkpoint_info", "nbody_cuda_checkpoint_read", "nbody_cuda_checkpoint_write",
@@ -99,6 +99,7 @@ def load_library():
     L.nbody_cuda_get_expansions.argtypes = [vp, vp, vp, u64]
     L.nbody_cuda_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.nbody_cuda_direct_field.argtypes = [C.c_int, vp, u64, vp, u64, C.c_float, vp, C.POINTER(C.c_float), u32]
+    L.nbody_cuda_sort_runs.argtypes = [C.c_int, vp, u64, vp, C.c_int, vp, vp]
     L.nbody_cuda_comm_unique_id.argtypes = [vp]
     L.nbody_cuda_create_distributed.argtypes = [C.POINTER(Config), vp, u64, u64, u64, C.c_int, C.c_int, vp, C.POINTER(vp)]
     L.nbody_cuda_owned_range.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
@@ -330,6 +331,17 @@ def direct_field(src_posq, tgt_pos4, softening=0.01, device=-1, repeats=1):
     _check(L.nbody_cuda_direct_field(device, _ptr(src), src.shape[0], _ptr(tgt), tgt.shape[0], softening, _ptr(out), C.byref(ms),
                                      repeats))
     return out, ms.value
+
+
+def sort_runs(keys, bound, device=-1):
+    """The device side of the distributed sort on one GPU (nbody_cuda_sort_runs): slices [bound[r], bound[r+1]) of `keys` are
+    radix-sorted separately, then merged pairwise. Returns (sorted keys, input index per output position)."""
+    L = load_library()
+    k = np.ascontiguousarray(keys, np.uint64)
+    b = np.ascontiguousarray(bound, np.uint32)
+    ko, io = np.empty_like(k), np.empty(k.shape[0], np.uint32)
+    _check(L.nbody_cuda_sort_runs(device, _ptr(k), k.shape[0], _ptr(b), b.shape[0] - 1, _ptr(ko), _ptr(io)))
+    return ko, io
 
 
 def next_time_step(acc_max, **config):

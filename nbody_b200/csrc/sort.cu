@@ -252,6 +252,11 @@ __global__ void __launch_bounds__(kMergeThreads) k_merge_runs(const MergePlan pl
 	}
 }
 
+__global__ void k_iota(uint64_t n, uint32_t* __restrict__ idx) {
+	const uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x;
+	if (i < n) idx[i] = (uint32_t) i;
+}
+
 // (keys[0], idx[0]) hold `nruns` sorted runs with boundaries bound[0..nruns] (bound[nruns] = n): merge them into one sorted
 // sequence. Rounds ping-pong between the two buffers; the buffer pointers are swapped at the end if needed, so the result is
 // in keys[0] / idx[0] like every other sort path.
@@ -270,3 +275,45 @@ void launch_merge_runs(Sim& s, const uint32_t* bound, int nruns) {
 }
 
 }  // namespace nbody
+
+using namespace nbody;
+
+extern "C" int nbody_cuda_sort_runs(int device, const uint64_t* keys, uint64_t n, const uint32_t* bound, int nruns, uint64_t* keys_out,
+                                    uint32_t* index_out) {
+	if (!keys || !bound || !keys_out || !index_out || n == 0 || n > 0xfffffff0ull || nruns < 1 || nruns > kMergeMaxRuns) {
+		set_error("bad argument");
+		return NBODY_ERR_INVALID;
+	}
+	if (bound[0] != 0 || bound[nruns] != n) { set_error("run boundaries must start at 0 and end at n"); return NBODY_ERR_INVALID; }
+	for (int r = 0; r < nruns; ++r)
+		if (bound[r] > bound[r + 1]) { set_error("run boundaries must not decrease"); return NBODY_ERR_INVALID; }
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device: this library has no CPU fallback"); return NBODY_ERR_CUDA; }
+	if (device >= 0) NB_CUDA_CHECK(cudaSetDevice(device));
+	Sim s{};
+	s.n = n;
+	auto release = [&]() {
+		for (int k = 0; k < 2; ++k) { if (s.keys[k]) cudaFree(s.keys[k]); if (s.idx[k]) cudaFree(s.idx[k]); }
+		if (s.sort_tmp) cudaFree(s.sort_tmp);
+		if (s.stream) cudaStreamDestroy(s.stream);
+	};
+	auto fail = [&](const char* what) { set_error(what); release(); return NBODY_ERR_CUDA; };
+	if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return fail("stream creation failed");
+	for (int k = 0; k < 2; ++k)
+		if (cudaMalloc((void**) &s.keys[k], n * sizeof(uint64_t)) != cudaSuccess || cudaMalloc((void**) &s.idx[k], n * sizeof(uint32_t)) != cudaSuccess)
+			return fail("device allocation failed");
+	if (cudaMalloc(&s.sort_tmp, own_sort_temp_bytes(n)) != cudaSuccess) return fail("device allocation failed");
+	uint64_t* k0 = s.keys[0];
+	uint32_t* i0 = s.idx[0];
+	if (cudaMemcpyAsync(k0, keys, n * sizeof(uint64_t), cudaMemcpyHostToDevice, s.stream) != cudaSuccess) return fail("upload failed");
+	k_iota<<<(unsigned) ((n + 255) / 256), 256, 0, s.stream>>>(n, i0);
+	for (int r = 0; r < nruns; ++r) launch_own_sort_range(s, bound[r], bound[r + 1] - bound[r]);  // what each rank does for its slice
+	launch_merge_runs(s, bound, nruns);                                                          // what every rank does after the all-gather
+	if (cudaMemcpyAsync(keys_out, s.keys[0], n * sizeof(uint64_t), cudaMemcpyDeviceToHost, s.stream) != cudaSuccess ||
+	    cudaMemcpyAsync(index_out, s.idx[0], n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream) != cudaSuccess ||
+	    cudaStreamSynchronize(s.stream) != cudaSuccess || cudaGetLastError() != cudaSuccess)
+		return fail("distributed-sort pipeline failed on the device");
+	release();
+	return NBODY_OK;
+}
+

@@ -50,6 +50,15 @@ def test_no_cpu_fallback():
     assert "no CPU fallback" in str(e.value) or "CUDA" in str(e.value)
     with pytest.raises(nbody_b200.NbodyCudaError):
         nbody_b200.direct_field(np.zeros((4, 4), np.float32), np.zeros((4, 4), np.float32))
+    with pytest.raises(nbody_b200.NbodyCudaError) as e:
+        nbody_b200.sort_runs(np.arange(8, dtype=np.uint64), [0, 4, 8])
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_sort_runs_argument_validation():
+    for keys, bound in ((np.arange(8), [1, 4, 8]), (np.arange(8), [0, 4, 7]), (np.arange(8), [0, 6, 4, 8]), (np.arange(8), [0] + [8] * 17)):
+        with pytest.raises(nbody_b200.NbodyCudaError):
+            nbody_b200.sort_runs(np.asarray(keys, np.uint64), bound)
 
 
 def test_argument_validation_without_gpu():

@@ -4,6 +4,7 @@ against the CPU oracle on the same seeded inputs.
 Bars: bit-exact for integer work (Morton keys, permutation, octree topology,
 interaction lists); multipoles / locals within FP32 round-off of the FP64 oracle;
 accelerations within 1e-3 RMS of FP64 direct summation (BASELINE.json north_star)."""
+import os
 from math import factorial
 
 import numpy as np
@@ -334,3 +335,19 @@ def test_full_size_plummer_16m_properties():
     assert rms_rel(acc[spot], gd * scale[spot]) < ACC_TOL
     F = acc.astype(np.float64) * out[:, 8:9]                              # equal masses: total force must cancel
     assert np.abs(F.sum(0)).max() / np.abs(F).sum(0).max() < 1e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get("NBODY_TEST_EXPERIMENTAL") != "1", reason="distributed-sort kernels have not run on hardware yet: "
+                    "set NBODY_TEST_EXPERIMENTAL=1 (tools/gpu_call_r02a.sh does); becomes unconditional once it has passed on a B200")
+@pytest.mark.parametrize("n,nruns", [(1, 1), (5000, 2), (70001, 3), (300000, 8), (1 << 21, 16)])
+def test_distributed_sort_pipeline_equals_stable_sort(n, nruns):
+    """nbody_cuda_sort_runs = what NBODY_FLAG_DIST_SORT does on the device (slice radix sorts + pairwise merge rounds), on one GPU:
+    the stable sort of all keys for any boundaries — the oracle's std::stable_sort, ties included."""
+    rng = np.random.default_rng(n)
+    keys = rng.integers(0, 1 << 62, n, dtype=np.uint64)
+    keys[rng.integers(0, n, n // 3)] = keys[0]                                       # heavy ties
+    bound = np.concatenate([[0], np.sort(rng.integers(0, n + 1, nruns - 1)), [n]])  # includes empty runs
+    k, i = nbody_b200.sort_runs(keys, bound)
+    sk, perm = oracle.sort_keys(keys)
+    assert np.array_equal(k, sk) and np.array_equal(i.astype(np.int64), np.asarray(perm, np.int64))

@@ -11,6 +11,8 @@
 # k_leaf from the fastest variant that passed.
 mkdir -p gpurun_out
 if [ -x tools/micro/fma_peak ]; then timeout 120 tools/micro/fma_peak > gpurun_out/r02a_fma_peak.log 2>&1; grep -h "FFMA2\|P2P chain" gpurun_out/r02a_fma_peak.log | grep "occ=4"; fi
+# the distributed sort's device pipeline (slice sorts + merge rounds) on one GPU, default library
+NBODY_TEST_EXPERIMENTAL=1 timeout 200 python -m pytest tests/test_gpu_parity.py -q -m gpu -k distributed_sort > gpurun_out/r02a_dist_sort_1gpu.log 2>&1; echo "dist sort 1-GPU rc=$?"; tail -3 gpurun_out/r02a_dist_sort_1gpu.log
 timeout 150 python bench.py --no-cpu-baseline --no-reference-capacity > gpurun_out/r02a_bench_default.json 2> gpurun_out/r02a_bench_default.err; echo "bench default rc=$?"
 for tag in x2 bulk bulk_x2; do
 	LIB=$PWD/nbody_b200/libnbody_cuda_$tag.so
