@@ -279,7 +279,8 @@ def main():
     # every step: H2D of this rank's slice of the state from pinned host memory (set_owned_particles, which
     # also re-assembles the full state over NVLink when N > 1), the step, D2H of the rank's updated slice.
     first, count = sim.owned_range()
-    out = torch.empty((max(count, 1) + (n // world) // 8 + 1024, 12), dtype=torch.float32).pin_memory()  # owned counts drift by a few leaves
+    # owned counts drift with the per-step rebalancing (a few leaves on the Plummer benchmark): room for +50 % on a multi-GPU run
+    out = torch.empty((max(count, 1) + ((n // world) // 2 if world > 1 else 0) + 1024, 12), dtype=torch.float32).pin_memory()
     sim.owned_particles_into_ptr(out.data_ptr(), out.shape[0])  # warm the export path
     barrier()
     h2d = d2h = 0
@@ -372,6 +373,8 @@ def launches_per_step(sim, world):
     """Kernels of ours launched by one step() (matches the ncu launch lists under profiles/: 174 on one GPU at max_depth 21)."""
     d = int(sim.config.max_depth)
     sort = 8 * 5                 # per 8-bit pass: histogram, three scan kernels, scatter
+    if world > 1 and (int(sim.config.flags) & 64):
+        sort += (world - 1).bit_length()   # NBODY_FLAG_DIST_SORT: the same passes over the rank's slice, then log2(world) merge rounds
     tree = 1 + 2 * d             # init, per level (count, split)
     upsweep = 1 + d              # P2M, per level M2M
     traversal = 1 + 2 * d        # init, per round (prep, traverse)
