@@ -99,7 +99,8 @@ __device__ __forceinline__ void p2p_interact(const float4& s, float tx, float ty
 // issue, not by the FP32 pipe (profiles/r01k_summary.md: 13.7 of 18.3 issue slots per pair are the interaction itself), so one
 // source is applied to TWO targets per instruction: 12 two-wide instructions + 2 MUFU.RSQ per two pair evaluations instead of
 // 2 x (12 + 1). Every component goes through the same IEEE operations in the same order as p2p_interact (s - t == s + (-t)
-// exactly), so the results are bit-identical to the scalar path. `nt*` hold the NEGATED coordinates of the two targets.
+// exactly), so with softening the results are bit-identical to the scalar path (with eps = 0 the only difference is which
+// vanishing distances count as coincident). `nt*` hold the NEGATED coordinates of the two targets.
 #ifndef NBODY_P2P_F32X2
 #define NBODY_P2P_F32X2 0
 #endif
@@ -113,8 +114,12 @@ __device__ __forceinline__ void p2p_interact2(const float4& s, const float2 ntx,
 		asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(inv.x) : "f"(r2.x));
 		asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(inv.y) : "f"(r2.y));
 	} else {
-		inv.x = r2.x > 0.0f ? rsqrtf(r2.x) : 0.0f;
-		inv.y = r2.y > 0.0f ? rsqrtf(r2.y) : 0.0f;
+		// eps = 0: coincident points (and i == j) exert no force. A bare MUFU.RSQ here too (rsqrtf's denormal fix-up costs the
+		// registers this kernel does not have): squared distances below the smallest normal number count as coincident.
+		asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(inv.x) : "f"(r2.x));
+		asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(inv.y) : "f"(r2.y));
+		inv.x = r2.x >= 1.17549435e-38f ? inv.x : 0.0f;
+		inv.y = r2.y >= 1.17549435e-38f ? inv.y : 0.0f;
 	}
 	const float2 inv2 = __fmul2_rn(inv, inv);
 	const float2 w = __fmul2_rn(__fmul2_rn(make_float2(s.w, s.w), inv), inv2);
