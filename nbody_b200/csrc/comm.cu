@@ -61,6 +61,7 @@ static bool nccl_load() {
 }
 
 int create_for_comm(const nbody_cuda_config* cfg, uint64_t n, Sim** out);
+int comm_wait_velocities(Sim& s);
 void destroy_for_comm(Sim* s);
 
 struct Comm {
@@ -164,6 +165,10 @@ void comm_own_slice(const Sim& s, uint64_t* first, uint64_t* count) {
 int comm_sort_exchange(Sim& s, uint32_t* bound, int* nruns) {
 	Comm& cm = *s.comm;
 	int rc;
+	// The previous step's velocity broadcasts may still be running on the second stream, and two collectives of ONE communicator
+	// must never be in flight at once: order the compute stream behind them first (the rank's own slice sort, enqueued before
+	// this point, still overlaps them). A second communicator for the velocity stream would restore the full overlap.
+	if ((rc = comm_wait_velocities(s))) return rc;
 	if ((rc = exchange(s, s.keys[0], sizeof(uint64_t)))) return rc;
 	if ((rc = exchange(s, s.idx[0], sizeof(uint32_t)))) return rc;
 	for (int r = 0; r <= cm.world; ++r) bound[r] = cm.part_host[r];
