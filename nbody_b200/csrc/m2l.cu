@@ -44,14 +44,27 @@ __device__ __forceinline__ void m2l_one(float (&Lacc)[Expansion<P>::NC], const f
 	Expansion<P>::template m2l<1, PE>(Lacc, M, D);
 }
 
+#ifndef NBODY_M2L_F32X2
+#define NBODY_M2L_F32X2 0
+#endif
 // Two independent interactions at order PE: both derivative tensors first, then both contractions, so the
 // compiler can interleave two dependency chains (the order-3 tensors are small enough to keep two in registers).
 template <int P, int PE>
 __device__ __forceinline__ void m2l_two(float (&Lacc)[Expansion<P>::NC], const float4& tg, const float4& ga, const float* Ma, const float4& gb,
                                         const float* Mb, float eps2) {
 	float Da[Expansion<PE>::NC], Db[Expansion<PE>::NC];
+#if NBODY_M2L_F32X2
+	{  // both derivative tensors with two-wide instructions (half the issue slots of this part), then the scalar contractions
+		float2 D2[Expansion<PE>::NC];
+		Expansion<PE>::derivatives2(make_float2(tg.x - ga.x, tg.x - gb.x), make_float2(tg.y - ga.y, tg.y - gb.y), make_float2(tg.z - ga.z, tg.z - gb.z),
+		                            eps2, D2);
+#pragma unroll
+		for (int n = 0; n < Expansion<PE>::NC; ++n) { Da[n] = D2[n].x; Db[n] = D2[n].y; }
+	}
+#else
 	Expansion<PE>::derivatives(tg.x - ga.x, tg.y - ga.y, tg.z - ga.z, eps2, Da);
 	Expansion<PE>::derivatives(tg.x - gb.x, tg.y - gb.y, tg.z - gb.z, eps2, Db);
+#endif
 	const SmemCoefs A{reinterpret_cast<const float4*>(Ma)}, B{reinterpret_cast<const float4*>(Mb)};
 	Expansion<P>::template m2l<1, PE>(Lacc, A, Da);
 	Expansion<P>::template m2l<1, PE>(Lacc, B, Db);

@@ -2,6 +2,13 @@
 // Exposes each operator for P = 2,3,4 through a C ABI used by tests/test_expansion.py.
 #include <cmath>
 #include <cstdint>
+// plain-C++ stand-ins for CUDA's float2 and sm_100's two-wide FP32 operations, so that Expansion::derivatives2 compiles here
+#define NBODY_HOST_F32X2_SHIM 1
+struct float2 { float x, y; };
+static inline float2 make_float2(float x, float y) { return float2{x, y}; }
+static inline float2 __fmul2_rn(float2 a, float2 b) { return float2{a.x * b.x, a.y * b.y}; }
+static inline float2 __fadd2_rn(float2 a, float2 b) { return float2{a.x + b.x, a.y + b.y}; }
+static inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return float2{fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)}; }
 #include "../../nbody_b200/csrc/expansion.cuh"
 
 using namespace nbody;
@@ -41,4 +48,18 @@ void exp_derivatives(int p, float x, float y, float z, float eps2, float* D) {
 	if (p == 3) { float d[ncoef(3)]; Expansion<3>::derivatives(x, y, z, eps2, d); for (int a = 0; a < ncoef(3); ++a) D[a] = d[a]; }
 	if (p == 4) { float d[ncoef(4)]; Expansion<4>::derivatives(x, y, z, eps2, d); for (int a = 0; a < ncoef(4); ++a) D[a] = d[a]; }
 }
+}
+
+// both halves of the packed derivative tensor (Expansion::derivatives2) for two separation vectors
+template <int P>
+static void run_derivatives2(const float* a, const float* b, float eps2, float* Da, float* Db) {
+	using E = Expansion<P>;
+	float2 D[E::NC];
+	E::derivatives2(make_float2(a[0], b[0]), make_float2(a[1], b[1]), make_float2(a[2], b[2]), eps2, D);
+	for (int n = 0; n < E::NC; ++n) { Da[n] = D[n].x; Db[n] = D[n].y; }
+}
+extern "C" void exp_derivatives2(int p, const float* a, const float* b, float eps2, float* Da, float* Db) {
+	if (p == 2) run_derivatives2<2>(a, b, eps2, Da, Db);
+	else if (p == 3) run_derivatives2<3>(a, b, eps2, Da, Db);
+	else run_derivatives2<4>(a, b, eps2, Da, Db);
 }

@@ -22,6 +22,7 @@ def hostlib():
     L = C.CDLL(so)
     L.exp_chain.argtypes = [C.c_int, f32p, C.c_int, f32p, f32p, f32p, f32p, f32p, C.c_int, C.c_float, f32p, f32p, f32p]
     L.exp_derivatives.argtypes = [C.c_int] + [C.c_float] * 4 + [f32p]
+    L.exp_derivatives2.argtypes = [C.c_int, f32p, f32p, C.c_float, f32p, f32p]
     return L
 
 
@@ -83,3 +84,19 @@ def test_operator_chain_converges(hostlib, p, tol):
     for a, (i, j, k) in enumerate(multi_indices(p)):
         ref = (src[:, 3] * r[:, 0] ** i * r[:, 1] ** j * r[:, 2] ** k).sum() / (f(i) * f(j) * f(k))
         assert abs(M[a] - ref) <= 1e-5 * max(abs(ref), 1e-3), (i, j, k)
+
+
+@pytest.mark.parametrize("p", [2, 3, 4])
+def test_packed_derivative_tensors_equal_the_scalar_ones(hostlib, p):
+    """Expansion::derivatives2 (two tensors with two-wide FP32 operations, -DNBODY_M2L_F32X2=1) against derivatives(), per half"""
+    rng = np.random.default_rng(p)
+    nc = hostlib.exp_ncoef(p)
+    for _ in range(50):
+        a, b = rng.uniform(-1, 1, 3).astype(np.float32), rng.uniform(-1, 1, 3).astype(np.float32)
+        eps2 = float(rng.choice([0.0, 1e-4, 0.3]))
+        Da, Db, Ra, Rb = (np.zeros(nc, np.float32) for _ in range(4))
+        hostlib.exp_derivatives2(p, a, b, eps2, Da, Db)
+        hostlib.exp_derivatives(p, float(a[0]), float(a[1]), float(a[2]), eps2, Ra)
+        hostlib.exp_derivatives(p, float(b[0]), float(b[1]), float(b[2]), eps2, Rb)
+        for got, ref in ((Da, Ra), (Db, Rb)):
+            assert np.allclose(got, ref, rtol=2e-5, atol=2e-5 * np.abs(ref).max())
