@@ -124,7 +124,10 @@ struct Expansion {
 	// Two derivative tensors at once with sm_100's two-wide FP32 instructions (FMUL2 / FFMA2): x, y, z hold the components of
 	// two separation vectors, D[n] = {D_n of the first, D_n of the second}. Same formula as derivatives(); experimental, used by
 	// the M2L kernel's two-interaction path when built with -DNBODY_M2L_F32X2=1 (not yet run on hardware).
-	NB_HD static void derivatives2(float2 x, float2 y, float2 z, float eps2, float2 (&D)[NC]) {
+	// MASK: `keep` = {1 or 0, 1 or 0} switches a half off (its tensor comes out as exact zeros: every term carries a factor g_k,
+	// and all g_k are multiples of the masked 1/R).
+	template <bool MASK = false>
+	NB_HD static void derivatives2(float2 x, float2 y, float2 z, float eps2, float2 (&D)[NC], float2 keep = float2{1.0f, 1.0f}) {
 		float2 mono[NC];
 		mono[0] = make_float2(1.0f, 1.0f);
 		NB_FOR_MI(o, i, j, k, 1, P) {
@@ -141,6 +144,7 @@ struct Expansion {
 #else
 		inv = make_float2(1.0f / sqrtf(R2.x), 1.0f / sqrtf(R2.y));
 #endif
+		if (MASK) inv = __fmul2_rn(inv, keep);
 		const float2 inv2 = __fmul2_rn(inv, inv);
 		float2 g[P + 1];
 		g[0] = inv;
@@ -161,6 +165,21 @@ struct Expansion {
 				first = false;
 			}
 			D[mi_index(i, j, k)] = acc;
+		}
+	}
+
+	// The M2L contraction for TWO TARGETS against one source: L[n] = {Lt_n of the first target, of the second}, D from
+	// derivatives2 (the two separations target - source), the source's multipole coefficient is a scalar that the two-wide FMA
+	// broadcasts to both halves (no register pairing needed). Same loop order as m2l().
+	template <int LO, int PE = P, typename MT, int ND>
+	NB_HD static void m2l_bc(float2 (&L)[NC], const MT& M, const float2 (&D)[ND]) {
+		static_assert(PE <= P && ND >= ncoef(PE), "derivative tensor too short for the evaluation order");
+		NB_FOR_MI(o2, a, b, c, 0, PE - LO) {
+			const float mraw = M[mi_index(a, b, c)];
+			const float m = (o2 & 1) ? -mraw : mraw;
+			NB_FOR_MI(o, i, j, k, LO, PE - o2) {
+				L[mi_index(i, j, k)] = __ffma2_rn(float2{m, m}, D[mi_index(i + a, j + b, k + c)], L[mi_index(i, j, k)]);
+			}
 		}
 	}
 #endif

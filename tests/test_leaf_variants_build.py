@@ -65,3 +65,34 @@ def test_variant_builds_within_budget_and_contains_its_instructions(tmp_path, ta
         assert count(sass[d], r"\bFFMA2\b") > 0
     else:
         assert n2 == 0 and count(body, r"\bFADD2\b") == 0 and count(body, r"\bFMUL2\b") == 0
+
+
+def test_pair_m2l_variant_builds_and_is_two_wide(tmp_path):
+    """-DNBODY_M2L_PAIR=1 (two sibling targets per warp): fits 3 CTAs of 128 threads per SM (170 registers) with at most a few
+    bytes of spill, and its arithmetic is FFMA2 / FMUL2; the default m2l.o has no two-wide instruction."""
+    src = os.path.join(ROOT, "nbody_b200", "csrc", "m2l.cu")
+    obj = str(tmp_path / "m2l_pair.o")
+    r = subprocess.run([NVCC, "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "--expt-relaxed-constexpr",
+                        "-Xptxas", "-v", "-DNBODY_M2L_PAIR=1", "-c", src, "-o", obj], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    out = {"pair": (r.stdout + r.stderr, subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True).stdout)}
+    import nbody_b200
+    default_obj = os.path.join(os.path.dirname(nbody_b200.LIB_PATH), "build", "m2l.o")     # the product build (nbody_b200/build.py)
+    if os.path.exists(default_obj):
+        sass_default = subprocess.run(["cuobjdump", "-sass", default_obj], capture_output=True, text=True).stdout
+        assert not re.search(r"\bFFMA2\b|\bFMUL2\b|\bFADD2\b", sass_default)
+    log, sass = out["pair"]
+    found = 0
+    for m in re.finditer(r"Compiling entry function '(\S*k_m2l_pair\S*)' for 'sm_100a'.*?(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads"
+                         r".*?Used (\d+) registers", log, re.S):
+        found += 1
+        assert int(m.group(5)) <= 170 and int(m.group(3)) + int(m.group(4)) <= 64, m.groups()
+    assert found == 3
+    body, name = [], None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            name = m.group(1)
+        elif name and "k_m2l_pairILi4E" in name:
+            body.append(line)
+    assert count(body, r"\bFFMA2\b") >= 250 and count(body, r"\bFMUL2\b") >= 80

@@ -5,6 +5,8 @@
 #   x2       -DNBODY_P2P_F32X2=1    two-wide FP32 interactions (FADD2 / FMUL2 / FFMA2), k_leaf and k_direct
 #   bulk_x2  both
 #   m2lx2    -DNBODY_M2L_F32X2=1    M2L: the two derivative tensors of the two-interaction (order P-1) path computed two-wide
+#   m2lpair  -DNBODY_M2L_PAIR=1     M2L: two sibling targets per warp, everything two-wide (k_m2l_pair)
+#   all      bulk + x2 + m2lpair
 # Build all libraries in the authoring container first (the .so files travel with the snapshot):
 #     tools/build_variants.sh
 # Order: FFMA2 microbenchmark (does a packed instruction cost one issue slot?), then per variant: parity under a short timeout
@@ -15,7 +17,7 @@ if [ -x tools/micro/fma_peak ]; then timeout 120 tools/micro/fma_peak > gpurun_o
 # the distributed sort's device pipeline (slice sorts + merge rounds) on one GPU, default library
 NBODY_TEST_EXPERIMENTAL=1 timeout 200 python -m pytest tests/test_gpu_parity.py -q -m gpu -k distributed_sort > gpurun_out/r02a_dist_sort_1gpu.log 2>&1; echo "dist sort 1-GPU rc=$?"; tail -3 gpurun_out/r02a_dist_sort_1gpu.log
 timeout 150 python bench.py --no-cpu-baseline --no-reference-capacity > gpurun_out/r02a_bench_default.json 2> gpurun_out/r02a_bench_default.err; echo "bench default rc=$?"
-for tag in x2 bulk bulk_x2 m2lx2; do
+for tag in x2 bulk bulk_x2 m2lx2 m2lpair all; do
 	LIB=$PWD/nbody_b200/libnbody_cuda_$tag.so
 	if [ ! -f "$LIB" ]; then echo "no $LIB: build it before the call"; continue; fi
 	NBODY_CUDA_LIB=$LIB timeout 300 python -m pytest tests/test_golden_fmm.py tests/test_gpu_parity.py -q -m gpu -x > gpurun_out/r02a_parity_$tag.log 2>&1
@@ -27,14 +29,14 @@ done
 BEST=$(python - <<'PY'
 import json
 best, best_ms = "default", 1e9
-for tag in ("default", "x2", "bulk", "bulk_x2", "m2lx2"):
+for tag in ("default", "x2", "bulk", "bulk_x2", "m2lx2", "m2lpair", "all"):
     try:
         d = json.load(open(f"gpurun_out/r02a_bench_{tag}.json"))
         ms = d["stage_ms"]["ms_leaf"]
         import sys
         print(tag, round(d["ms_per_step"], 3), {k: round(v, 2) for k, v in d["stage_ms"].items()}, "leaf frac", round(d["roofline"]["frac"], 4),
               "all-pairs frac", round(d["p2p_fp32_tflops"]["all_pairs_frac_of_peak"], 4), file=sys.stderr)
-        if ms < best_ms and tag != "m2lx2":
+        if ms < best_ms and tag in ("default", "x2", "bulk", "bulk_x2"):
             best, best_ms = tag, ms
     except Exception as e:
         import sys
