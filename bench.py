@@ -350,7 +350,8 @@ def main():
             "config": {"workload": f"{args.workload} sphere N={n}" if args.workload == "plummer" else f"{args.workload} N={n}",
                        "order": args.order, "leaf_capacity": args.leaf_capacity, "mac_ratio": 0.5, "softening": 0.01,
                        "integrator": "kick-drift", "l2_policy": "working set (>1 GB of lists and particle state per step) exceeds the 126 MB L2",
-                       "partition": "morton-range" if world > 1 else "single", "flags": args.flags},
+                       "partition": "morton-range" if world > 1 else "single", "flags": args.flags,
+                       "library": os.path.basename(nbody_b200.LIB_PATH)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": K * launches_per_step(sim, world),
             "roofline": roof,
             "p2p_fp32_tflops": {"tree_p2p_kernel": p2p_tf, "tree_p2p_frac_of_peak": p2p_tf / peak,
