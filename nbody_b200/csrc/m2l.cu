@@ -256,7 +256,10 @@ k_m2l(Ctrl* __restrict__ c, const Group* __restrict__ items, uint32_t items_cap,
 #endif
 #if NBODY_M2L_PAIR
 constexpr int kPairThreads = 128;
-constexpr int kPairCtas = 3;  // CTAs per SM the register allocation is held to: 65536 / (3 x 128) = 170 registers per thread
+#ifndef NBODY_M2L_PAIR_CTAS
+#define NBODY_M2L_PAIR_CTAS 3
+#endif
+constexpr int kPairCtas = NBODY_M2L_PAIR_CTAS;  // CTAs per SM the register allocation is held to: 3 -> 65536 / (3 x 128) = 170 registers per thread
 
 template <int P>
 struct M2LPairShared {

@@ -6,6 +6,7 @@
 #   bulk_x2  both
 #   m2lx2    -DNBODY_M2L_F32X2=1    M2L: the two derivative tensors of the two-interaction (order P-1) path computed two-wide
 #   m2lpair  -DNBODY_M2L_PAIR=1     M2L: two sibling targets per warp, everything two-wide (k_m2l_pair)
+#   m2lpair2 the same held to 2 CTAs per SM (224 registers, no spill) instead of 3 (168 registers, 20 bytes of spill)
 #   all      bulk + x2 + m2lpair
 # Build all libraries in the authoring container first (the .so files travel with the snapshot):
 #     tools/build_variants.sh
@@ -13,11 +14,14 @@
 # (an mbarrier mistake hangs the kernel: the timeout, not gpurun's limit, must end it), bench line; last, one ncu capture of
 # k_leaf from the fastest variant that passed.
 mkdir -p gpurun_out
+if [ $# -eq 0 ]; then   # the microbenchmark, the one-GPU distributed-sort check and the default bench line only on the first call
 if [ -x tools/micro/fma_peak ]; then timeout 120 tools/micro/fma_peak > gpurun_out/r02a_fma_peak.log 2>&1; grep -h "FFMA2\|P2P chain" gpurun_out/r02a_fma_peak.log | grep "occ=4"; fi
 # the distributed sort's device pipeline (slice sorts + merge rounds) on one GPU, default library
 NBODY_TEST_EXPERIMENTAL=1 timeout 200 python -m pytest tests/test_gpu_parity.py -q -m gpu -k distributed_sort > gpurun_out/r02a_dist_sort_1gpu.log 2>&1; echo "dist sort 1-GPU rc=$?"; tail -3 gpurun_out/r02a_dist_sort_1gpu.log
 timeout 150 python bench.py --no-cpu-baseline --no-reference-capacity > gpurun_out/r02a_bench_default.json 2> gpurun_out/r02a_bench_default.err; echo "bench default rc=$?"
-for tag in x2 bulk bulk_x2 m2lx2 m2lpair all; do
+fi
+TAGS=${@:-x2 bulk bulk_x2}   # second call: tools/gpu_call_r02a.sh m2lx2 m2lpair m2lpair2 all  (~2.5 GPU-minutes per tag)
+for tag in $TAGS; do
 	LIB=$PWD/nbody_b200/libnbody_cuda_$tag.so
 	if [ ! -f "$LIB" ]; then echo "no $LIB: build it before the call"; continue; fi
 	NBODY_CUDA_LIB=$LIB timeout 300 python -m pytest tests/test_golden_fmm.py tests/test_gpu_parity.py -q -m gpu -x > gpurun_out/r02a_parity_$tag.log 2>&1
@@ -29,7 +33,7 @@ done
 BEST=$(python - <<'PY'
 import json
 best, best_ms = "default", 1e9
-for tag in ("default", "x2", "bulk", "bulk_x2", "m2lx2", "m2lpair", "all"):
+for tag in ("default", "x2", "bulk", "bulk_x2", "m2lx2", "m2lpair", "m2lpair2", "all"):
     try:
         d = json.load(open(f"gpurun_out/r02a_bench_{tag}.json"))
         ms = d["stage_ms"]["ms_leaf"]
@@ -45,6 +49,7 @@ print(best)
 PY
 )
 echo "fastest leaf kernel: $BEST"
+[ $# -ne 0 ] && exit 0   # the ncu capture belongs to the first call (leaf variants)
 LIB=$PWD/nbody_b200/libnbody_cuda.so; [ "$BEST" != default ] && LIB=$PWD/nbody_b200/libnbody_cuda_$BEST.so
 NBODY_CUDA_LIB=$LIB timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_leaf -c 1 -o gpurun_out/r02a_leaf_$BEST \
 	python tools/prof_step.py 16777216 1 4 48 > gpurun_out/r02a_ncu_$BEST.log 2>&1; echo "ncu rc=$?"
