@@ -18,6 +18,7 @@ if [ $# -eq 0 ]; then   # the microbenchmark, the one-GPU distributed-sort check
 if [ -x tools/micro/fma_peak ]; then timeout 120 tools/micro/fma_peak > gpurun_out/r02a_fma_peak.log 2>&1; grep -h "FFMA2\|P2P chain" gpurun_out/r02a_fma_peak.log | grep "occ=4"; fi
 # the distributed sort's device pipeline (slice sorts + merge rounds) on one GPU, default library
 NBODY_TEST_EXPERIMENTAL=1 timeout 200 python -m pytest tests/test_gpu_parity.py -q -m gpu -k distributed_sort > gpurun_out/r02a_dist_sort_1gpu.log 2>&1; echo "dist sort 1-GPU rc=$?"; tail -3 gpurun_out/r02a_dist_sort_1gpu.log
+NBODY_TEST_EXPERIMENTAL=1 NBODY_VARIANT_LIB=$PWD/nbody_b200/libnbody_cuda_x2.so timeout 100 python -m pytest tests/test_gpu_parity.py -q -m gpu -k two_wide_all_pairs > gpurun_out/r02a_x2_bitwise.log 2>&1; echo "x2 all-pairs bitwise rc=$?"
 timeout 150 python bench.py --no-cpu-baseline --no-reference-capacity > gpurun_out/r02a_bench_default.json 2> gpurun_out/r02a_bench_default.err; echo "bench default rc=$?"
 fi
 TAGS=${@:-x2 bulk bulk_x2}   # second call: tools/gpu_call_r02a.sh m2lx2 m2lpair m2lpair2 all  (~2.5 GPU-minutes per tag)
