@@ -15,7 +15,7 @@
 # k_leaf from the fastest variant that passed.
 mkdir -p gpurun_out
 if [ $# -eq 0 ]; then   # the microbenchmark, the one-GPU distributed-sort check and the default bench line only on the first call
-if [ -x tools/micro/fma_peak ]; then timeout 120 tools/micro/fma_peak > gpurun_out/r02a_fma_peak.log 2>&1; grep -h "FFMA2\|P2P chain" gpurun_out/r02a_fma_peak.log | grep "occ=4"; fi
+if [ -x tools/micro/fma_peak ]; then timeout 120 tools/micro/fma_peak > gpurun_out/r02a_fma_peak.log 2>&1; grep -h "FFMA2\|P2P chain\|dependent" gpurun_out/r02a_fma_peak.log | grep "occ=4\|dependent"; fi
 # the distributed sort's device pipeline (slice sorts + merge rounds) on one GPU, default library
 NBODY_TEST_EXPERIMENTAL=1 timeout 200 python -m pytest tests/test_gpu_parity.py -q -m gpu -k distributed_sort > gpurun_out/r02a_dist_sort_1gpu.log 2>&1; echo "dist sort 1-GPU rc=$?"; tail -3 gpurun_out/r02a_dist_sort_1gpu.log
 NBODY_TEST_EXPERIMENTAL=1 NBODY_VARIANT_LIB=$PWD/nbody_b200/libnbody_cuda_x2.so timeout 100 python -m pytest tests/test_gpu_parity.py -q -m gpu -k two_wide_all_pairs > gpurun_out/r02a_x2_bitwise.log 2>&1; echo "x2 all-pairs bitwise rc=$?"

@@ -137,7 +137,36 @@ void run2(const char* name, int blocks_per_sm) {
 	cudaFree(out);
 }
 
+// Dependent-issue latency: one chain per thread, one warp per SM sub-partition (128 threads per SM), clock64 around the loop.
+template <bool PACKED>
+__global__ void k_lat(float* out, long long* cycles, float a0, int iters) {
+	float2 x = make_float2(a0 * threadIdx.x, a0);
+	const float2 a = make_float2(1.0001f, 0.9999f), b = make_float2(0.5f, 0.25f);
+	const long long t0 = clock64();
+	for (int it = 0; it < iters; ++it) {
+#pragma unroll
+		for (int r = 0; r < 16; ++r) {
+			if (PACKED) x = __ffma2_rn(x, a, b);
+			else x.x = fmaf(x.x, a.x, b.x);
+		}
+	}
+	const long long t1 = clock64();
+	out[blockIdx.x * blockDim.x + threadIdx.x] = x.x + x.y;
+	if (threadIdx.x == 0 && blockIdx.x == 0) *cycles = t1 - t0;
+}
+template <bool PACKED>
+void run_lat(const char* name) {
+	float* out; long long* cyc; cudaMalloc(&out, 148 * 128 * 4); cudaMalloc(&cyc, 8);
+	const int iters = 4000;
+	k_lat<PACKED><<<148, 128>>>(out, cyc, 1.0001f, iters);
+	long long h = 0; cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+	printf("%-52s %.2f cycles per dependent instruction\n", name, (double) h / (iters * 16.0));
+	cudaFree(out); cudaFree(cyc);
+}
+
 int main() {
+	run_lat<false>("FFMA dependent chain");
+	run_lat<true>("FFMA2 dependent chain");
 	for (int occ : {1, 2, 4}) {
 		run2<0>("FFMA2 x2 += a2*b2", occ);
 		run2<1>("FFMA2 x2 += s*b2 (32-bit broadcast operand)", occ);
