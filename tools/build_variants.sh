@@ -6,6 +6,7 @@ cd "$(dirname "$0")/.."
 python nbody_b200/build.py
 NBODY_BUILD_TAG=x2 NBODY_BUILD_DEFS="-DNBODY_P2P_F32X2=1" python nbody_b200/build.py
 NBODY_BUILD_TAG=bulk NBODY_BUILD_DEFS="-DNBODY_LEAF_BULK=1" python nbody_b200/build.py
+NBODY_BUILD_TAG=bulk_rows2 NBODY_BUILD_DEFS="-DNBODY_LEAF_BULK=1 -DNBODY_LEAF_ROWS=2" python nbody_b200/build.py   # tiles padded to 64 instead of 128 sources
 NBODY_BUILD_TAG=bulk_x2 NBODY_BUILD_DEFS="-DNBODY_LEAF_BULK=1 -DNBODY_P2P_F32X2=1" python nbody_b200/build.py
 NBODY_BUILD_TAG=m2lx2 NBODY_BUILD_DEFS="-DNBODY_M2L_F32X2=1" python nbody_b200/build.py
 NBODY_BUILD_TAG=m2lpair NBODY_BUILD_DEFS="-DNBODY_M2L_PAIR=1" python nbody_b200/build.py

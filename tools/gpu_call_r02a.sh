@@ -21,7 +21,7 @@ NBODY_TEST_EXPERIMENTAL=1 timeout 200 python -m pytest tests/test_gpu_parity.py 
 NBODY_TEST_EXPERIMENTAL=1 NBODY_VARIANT_LIB=$PWD/nbody_b200/libnbody_cuda_x2.so timeout 100 python -m pytest tests/test_gpu_parity.py -q -m gpu -k two_wide_all_pairs > gpurun_out/r02a_x2_bitwise.log 2>&1; echo "x2 all-pairs bitwise rc=$?"
 timeout 150 python bench.py --no-cpu-baseline --no-reference-capacity > gpurun_out/r02a_bench_default.json 2> gpurun_out/r02a_bench_default.err; echo "bench default rc=$?"
 fi
-TAGS=${@:-bulk}   # the two-wide variants (x2 bulk_x2 m2lx2 m2lpair m2lpair2 all) only on request: FFMA2 does not pay (profiles/r01o_summary.md); ~2.5 GPU-minutes per tag
+TAGS=${@:-bulk bulk_rows2}   # the two-wide variants (x2 bulk_x2 m2lx2 m2lpair m2lpair2 all) only on request: FFMA2 does not pay (profiles/r01o_summary.md); ~2.5 GPU-minutes per tag
 for tag in $TAGS; do
 	LIB=$PWD/nbody_b200/libnbody_cuda_$tag.so
 	if [ ! -f "$LIB" ]; then echo "no $LIB: build it before the call"; continue; fi
@@ -34,14 +34,14 @@ done
 BEST=$(python - <<'PY'
 import json
 best, best_ms = "default", 1e9
-for tag in ("default", "x2", "bulk", "bulk_x2", "m2lx2", "m2lpair", "m2lpair2", "all"):
+for tag in ("default", "bulk", "bulk_rows2", "x2", "bulk_x2", "m2lx2", "m2lpair", "m2lpair2", "all"):
     try:
         d = json.load(open(f"gpurun_out/r02a_bench_{tag}.json"))
         ms = d["stage_ms"]["ms_leaf"]
         import sys
         print(tag, round(d["ms_per_step"], 3), {k: round(v, 2) for k, v in d["stage_ms"].items()}, "leaf frac", round(d["roofline"]["frac"], 4),
               "all-pairs frac", round(d["p2p_fp32_tflops"]["all_pairs_frac_of_peak"], 4), file=sys.stderr)
-        if ms < best_ms and tag in ("default", "x2", "bulk", "bulk_x2"):
+        if ms < best_ms and tag in ("default", "bulk", "bulk_rows2", "x2", "bulk_x2"):
             best, best_ms = tag, ms
     except Exception as e:
         import sys
