@@ -119,71 +119,6 @@ struct Expansion {
 		}
 	}
 
-#if (defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000) || defined(NBODY_HOST_F32X2_SHIM)
-	// (NBODY_HOST_F32X2_SHIM: tests/host/expansion_host.cpp supplies float2 and the three packed operations as plain C++.)
-	// Two derivative tensors at once with sm_100's two-wide FP32 instructions (FMUL2 / FFMA2): x, y, z hold the components of
-	// two separation vectors, D[n] = {D_n of the first, D_n of the second}. Same formula as derivatives(); experimental, used by
-	// the M2L kernel's two-interaction path when built with -DNBODY_M2L_F32X2=1 (not yet run on hardware).
-	// MASK: `keep` = {1 or 0, 1 or 0} switches a half off (its tensor comes out as exact zeros: every term carries a factor g_k,
-	// and all g_k are multiples of the masked 1/R).
-	template <bool MASK = false>
-	NB_HD static void derivatives2(float2 x, float2 y, float2 z, float eps2, float2 (&D)[NC], float2 keep = float2{1.0f, 1.0f}) {
-		float2 mono[NC];
-		mono[0] = make_float2(1.0f, 1.0f);
-		NB_FOR_MI(o, i, j, k, 1, P) {
-			if (o == 1) mono[mi_index(i, j, k)] = i > 0 ? x : j > 0 ? y : z;
-			else if (i > 0) mono[mi_index(i, j, k)] = __fmul2_rn(mono[mi_index(i - 1, j, k)], x);
-			else if (j > 0) mono[mi_index(i, j, k)] = __fmul2_rn(mono[mi_index(i, j - 1, k)], y);
-			else mono[mi_index(i, j, k)] = __fmul2_rn(mono[mi_index(i, j, k - 1)], z);
-		}
-		const float2 R2 = __ffma2_rn(z, z, __ffma2_rn(y, y, __ffma2_rn(x, x, make_float2(eps2, eps2))));
-		float2 inv;
-#if defined(__CUDA_ARCH__)
-		asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(inv.x) : "f"(R2.x));
-		asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(inv.y) : "f"(R2.y));
-#else
-		inv = make_float2(1.0f / sqrtf(R2.x), 1.0f / sqrtf(R2.y));
-#endif
-		if (MASK) inv = __fmul2_rn(inv, keep);
-		const float2 inv2 = __fmul2_rn(inv, inv);
-		float2 g[P + 1];
-		g[0] = inv;
-		NB_FOR_ORDER(q, 1, P) g[q] = __fmul2_rn(__fmul2_rn(make_float2(-(float) (2 * q - 1), -(float) (2 * q - 1)), g[q - 1]), inv2);
-		NB_FOR_MI(o, i, j, k, 0, P) {
-			float2 acc = make_float2(0.0f, 0.0f);
-			bool first = true;
-			_Pragma("unroll") for (int a = 0; a <= P / 2; ++a)
-			_Pragma("unroll") for (int b = 0; b <= P / 2; ++b)
-			_Pragma("unroll") for (int c = 0; c <= P / 2; ++c)
-			if (2 * a <= i && 2 * b <= j && 2 * c <= k) {
-				const int coef = (facti(i) / (facti(a) * facti(i - 2 * a) << a)) * (facti(j) / (facti(b) * facti(j - 2 * b) << b)) *
-				                 (facti(k) / (facti(c) * facti(k - 2 * c) << c));
-				const float2 cg = coef == 1 ? g[o - a - b - c] : __fmul2_rn(make_float2((float) coef, (float) coef), g[o - a - b - c]);
-				const int mi = mi_index(i - 2 * a, j - 2 * b, k - 2 * c);
-				if (first) acc = mi == 0 ? cg : __fmul2_rn(cg, mono[mi]);
-				else acc = mi == 0 ? __fadd2_rn(acc, cg) : __ffma2_rn(cg, mono[mi], acc);
-				first = false;
-			}
-			D[mi_index(i, j, k)] = acc;
-		}
-	}
-
-	// The M2L contraction for TWO TARGETS against one source: L[n] = {Lt_n of the first target, of the second}, D from
-	// derivatives2 (the two separations target - source), the source's multipole coefficient is a scalar that the two-wide FMA
-	// broadcasts to both halves (no register pairing needed). Same loop order as m2l().
-	template <int LO, int PE = P, typename MT, int ND>
-	NB_HD static void m2l_bc(float2 (&L)[NC], const MT& M, const float2 (&D)[ND]) {
-		static_assert(PE <= P && ND >= ncoef(PE), "derivative tensor too short for the evaluation order");
-		NB_FOR_MI(o2, a, b, c, 0, PE - LO) {
-			const float mraw = M[mi_index(a, b, c)];
-			const float m = (o2 & 1) ? -mraw : mraw;
-			NB_FOR_MI(o, i, j, k, LO, PE - o2) {
-				L[mi_index(i, j, k)] = __ffma2_rn(float2{m, m}, D[mi_index(i + a, j + b, k + c)], L[mi_index(i, j, k)]);
-			}
-		}
-	}
-#endif
-
 	// M2L: Lt_n += sum_{|m| <= PE-|n|} (-1)^|m| M_m D_{n+m} for LO <= |n| <= PE.
 	// LO = lowest local order kept: 1 when only the field (gradient) is needed, 0 to carry the
 	// potential too. PE <= P is the order this pair is evaluated at (adaptive-order M2L: well

@@ -93,41 +93,6 @@ __device__ __forceinline__ void p2p_interact(const float4& s, float tx, float ty
 	az = fmaf(w, dz, az);
 }
 
-// ---- experimental packed-FP32 interactions (build with -DNBODY_P2P_F32X2=1; NOT the default, not yet run on hardware) ----
-// sm_100 has two-wide FP32 instructions (FADD2 / FMUL2 / FFMA2 on 64-bit register pairs, PTX add/mul/fma.rn.f32x2; a 32-bit
-// operand is broadcast to both halves, so scalars cost no extra registers or moves). The P2P kernels are bound by instruction
-// issue, not by the FP32 pipe (profiles/r01k_summary.md: 13.7 of 18.3 issue slots per pair are the interaction itself), so one
-// source is applied to TWO targets per instruction: 12 two-wide instructions + 2 MUFU.RSQ per two pair evaluations instead of
-// 2 x (12 + 1). Every component goes through the same IEEE operations in the same order as p2p_interact (s - t == s + (-t)
-// exactly), so with softening the results are bit-identical to the scalar path (with eps = 0 the only difference is which
-// vanishing distances count as coincident). `nt*` hold the NEGATED coordinates of the two targets.
-#ifndef NBODY_P2P_F32X2
-#define NBODY_P2P_F32X2 0
-#endif
-template <bool SOFT>
-__device__ __forceinline__ void p2p_interact2(const float4& s, const float2 ntx, const float2 nty, const float2 ntz, float eps2, float2& ax,
-                                              float2& ay, float2& az) {
-	const float2 dx = __fadd2_rn(make_float2(s.x, s.x), ntx), dy = __fadd2_rn(make_float2(s.y, s.y), nty), dz = __fadd2_rn(make_float2(s.z, s.z), ntz);
-	const float2 r2 = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __ffma2_rn(dx, dx, make_float2(eps2, eps2))));
-	float2 inv;
-	if (SOFT) {
-		asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(inv.x) : "f"(r2.x));
-		asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(inv.y) : "f"(r2.y));
-	} else {
-		// eps = 0: coincident points (and i == j) exert no force. A bare MUFU.RSQ here too (rsqrtf's denormal fix-up costs the
-		// registers this kernel does not have): squared distances below the smallest normal number count as coincident.
-		asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(inv.x) : "f"(r2.x));
-		asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(inv.y) : "f"(r2.y));
-		inv.x = r2.x >= 1.17549435e-38f ? inv.x : 0.0f;
-		inv.y = r2.y >= 1.17549435e-38f ? inv.y : 0.0f;
-	}
-	const float2 inv2 = __fmul2_rn(inv, inv);
-	const float2 w = __fmul2_rn(__fmul2_rn(make_float2(s.w, s.w), inv), inv2);
-	ax = __ffma2_rn(w, dx, ax);
-	ay = __ffma2_rn(w, dy, ay);
-	az = __ffma2_rn(w, dz, az);
-}
-
 struct LeafArgs {
 	Ctrl* c;
 	const float4* posq;      // sorted positions of this step (sources and targets)
@@ -180,42 +145,6 @@ __device__ __forceinline__ void tile_rows(unsigned G, const float4* __restrict__
 	__syncwarp();
 }
 
-// The same for pairs of targets (NBODY_P2P_F32X2): GP = number of target pairs of the block, tp[k] = the negated coordinates of
-// pair k. An odd block is completed by a copy of its last target, whose sums are never read.
-struct __align__(16) TargetPair {
-	float4 xy;  // -x0, -x1, -y0, -y1
-	float2 z;   // -z0, -z1
-	float2 pad;
-};
-template <bool SOFT>
-__device__ __forceinline__ void tile_rows2(unsigned GP, const float4* __restrict__ buf, uint32_t nrows, unsigned lane, const TargetPair* __restrict__ tp,
-                                           float eps2, float2 (&ax)[8], float2 (&ay)[8], float2 (&az)[8]) {
-	__syncwarp();
-#pragma unroll 1
-	for (uint32_t r = 0; r < nrows; r += kLeafRows) {
-		float4 s[kLeafRows];
-#pragma unroll
-		for (int u = 0; u < kLeafRows; ++u) s[u] = buf[(r + u) * 32u + lane];
-		float4 t = tp[GP - 1u].xy;
-		float2 tzz = tp[GP - 1u].z;
-#define NB_LEAF_T2(k)                                                                                       \
-	case k + 1: {                                                                                              \
-		const float4 tn = tp[k > 0 ? k - 1 : 0].xy;                                                              \
-		const float2 zn = tp[k > 0 ? k - 1 : 0].z;                                                               \
-		_Pragma("unroll") for (int u = 0; u < kLeafRows; ++u)                                                    \
-		    p2p_interact2<SOFT>(s[u], make_float2(t.x, t.y), make_float2(t.z, t.w), tzz, eps2, ax[k], ay[k], az[k]); \
-		t = tn;                                                                                                  \
-		tzz = zn;                                                                                                \
-	}
-		switch (GP) {
-			NB_LEAF_T2(7) NB_LEAF_T2(6) NB_LEAF_T2(5) NB_LEAF_T2(4) NB_LEAF_T2(3) NB_LEAF_T2(2) NB_LEAF_T2(1) NB_LEAF_T2(0)
-			default: break;
-		}
-#undef NB_LEAF_T2
-	}
-	__syncwarp();
-}
-
 // Sum v[k] over the 32 lanes for 16 values at once: each halving step exchanges the half of the values the
 // partner lane is responsible for, so 16 shuffles do the work of 80. On return v[0] of lanes 2k and 2k+1 holds
 // the total of value k.
@@ -246,10 +175,6 @@ __global__ void __launch_bounds__(kLeafWarps * 32, kLeafMinCtas) k_leaf(const Le
 	constexpr uint32_t END = 0xffffffffu;
 	__shared__ float4 sbuf[kLeafWarps][2][kLeafTile];
 	__shared__ float4 stgt[kLeafWarps][16];
-#if NBODY_P2P_F32X2
-	__shared__ TargetPair stp[kLeafWarps][8];  // negated coordinates, two targets per record
-	static_assert(kLeafG == 16, "the packed variant evaluates up to 8 pairs of targets per block");
-#endif
 	const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
 #if NBODY_LEAF_BULK
 	__shared__ __align__(8) uint64_t sbar[kLeafWarps][2];  // one mbarrier per warp and tile buffer; a single arrival (lane 0) + the copied bytes
@@ -286,33 +211,15 @@ __global__ void __launch_bounds__(kLeafWarps * 32, kLeafMinCtas) k_leaf(const Le
 			const uint32_t nt = __shfl_sync(0xffffffffu, nf_l.y, kk), b = __shfl_sync(0xffffffffu, b_l, kk);
 			++leaves;
 			const float4 g = a.geom[node];
-#if NBODY_P2P_F32X2
-			const uint32_t nblk = (nt + kLeafG - 1) / kLeafG, gmax = ((nt + nblk - 1) / nblk + 1u) & ~1u;  // whole pairs; only a leaf's last block can be odd
-#else
 			const uint32_t nblk = (nt + kLeafG - 1) / kLeafG, gmax = (nt + nblk - 1) / nblk;  // even blocks of <= kLeafG targets
-#endif
 #pragma unroll 1
 			for (uint32_t t0 = 0; t0 < nt; t0 += gmax) {
 				const unsigned G = min(gmax, nt - t0);
 				__syncwarp();
-#if NBODY_P2P_F32X2
-				if (lane < ((G + 1u) & ~1u)) {  // lane G of an odd block repeats target G - 1
-					const float4 p = a.posq[b + t0 + min(lane, G - 1u)];
-					if (lane < G) stgt[w][lane] = p;
-					float* pr = reinterpret_cast<float*>(&stp[w][lane >> 1]);
-					pr[lane & 1u] = -p.x;
-					pr[2u + (lane & 1u)] = -p.y;
-					pr[4u + (lane & 1u)] = -p.z;
-				}
-				float2 ax2[8], ay2[8], az2[8];
-#pragma unroll
-				for (int k = 0; k < 8; ++k) ax2[k] = ay2[k] = az2[k] = make_float2(0.f, 0.f);
-#else
 				if (lane < G) stgt[w][lane] = a.posq[b + t0 + lane];
 				float ax[16], ay[16], az[16];
 #pragma unroll
 				for (int k = 0; k < 16; ++k) ax[k] = ay[k] = az[k] = 0.f;
-#endif
 				unsigned long long nsrc = 0;
 				// ---- cursor over the segment chain: entry e0 of segment sg, of which `skip` particles are consumed ----
 				uint32_t si = a.p2p_head[node], e0 = 0, skip = 0;
@@ -403,26 +310,13 @@ __global__ void __launch_bounds__(kLeafWarps * 32, kLeafMinCtas) k_leaf(const Le
 #else
 					leaf_cp_async_wait1();
 #endif
-#if NBODY_P2P_F32X2
-					tile_rows2<SOFT>((G + 1u) >> 1, sbuf[w][cur], (fill_cur + 31u) >> 5, lane, stp[w], a.eps2, ax2, ay2, az2);
-#else
 					tile_rows<SOFT>(G, sbuf[w][cur], (fill_cur + 31u) >> 5, lane, stgt[w], a.eps2, ax, ay, az);
-#endif
 					nsrc += fill_cur;
 					ent_nxt = ent_nn; fill_cur = fill_nxt; has_cur = has_nxt; has_nxt = has_nn;
 					cur ^= 1;
 				}
 #if !NBODY_LEAF_BULK
 				leaf_cp_async_wait0();
-#endif
-#if NBODY_P2P_F32X2
-				float ax[16], ay[16], az[16];
-#pragma unroll
-				for (int k = 0; k < 8; ++k) {
-					ax[2 * k] = ax2[k].x; ax[2 * k + 1] = ax2[k].y;
-					ay[2 * k] = ay2[k].x; ay[2 * k + 1] = ay2[k].y;
-					az[2 * k] = az2[k].x; az[2 * k + 1] = az2[k].y;
-				}
 #endif
 				transpose_reduce16(ax, lane);
 				transpose_reduce16(ay, lane);
@@ -523,30 +417,12 @@ __global__ void __launch_bounds__(kDirThreads) k_direct(const float4* __restrict
 			tile[q] = j < n_src ? src[j] : make_float4(0.f, 0.f, 0.f, 0.f);  // q = 0 padding exerts no force
 		}
 		__syncthreads();
-#if NBODY_P2P_F32X2
-		{  // targets (0,1) and (2,3) as two-wide operands; component for component the same arithmetic as below
-			static_assert(kDirTargets == 4, "two pairs of targets per thread");
-			const float2 ntx0 = make_float2(-tx[0], -tx[1]), nty0 = make_float2(-ty[0], -ty[1]), ntz0 = make_float2(-tz[0], -tz[1]);
-			const float2 ntx1 = make_float2(-tx[2], -tx[3]), nty1 = make_float2(-ty[2], -ty[3]), ntz1 = make_float2(-tz[2], -tz[3]);
-			float2 ax0 = make_float2(0.f, 0.f), ay0 = ax0, az0 = ax0, ax1 = ax0, ay1 = ax0, az1 = ax0;
-#pragma unroll 4
-			for (int q = 0; q < kDirTile; ++q) {
-				const float4 s = tile[q];
-				p2p_interact2<SOFT>(s, ntx0, nty0, ntz0, eps2, ax0, ay0, az0);
-				p2p_interact2<SOFT>(s, ntx1, nty1, ntz1, eps2, ax1, ay1, az1);
-			}
-			ax[0] = ax0.x; ax[1] = ax0.y; ax[2] = ax1.x; ax[3] = ax1.y;
-			ay[0] = ay0.x; ay[1] = ay0.y; ay[2] = ay1.x; ay[3] = ay1.y;
-			az[0] = az0.x; az[1] = az0.y; az[2] = az1.x; az[3] = az1.y;
-		}
-#else
 #pragma unroll 4
 		for (int q = 0; q < kDirTile; ++q) {
 			const float4 s = tile[q];
 #pragma unroll
 			for (int t = 0; t < kDirTargets; ++t) p2p_interact<SOFT>(s, tx[t], ty[t], tz[t], eps2, ax[t], ay[t], az[t]);
 		}
-#endif
 #pragma unroll
 		for (int t = 0; t < kDirTargets; ++t) {  // fold the tile's partial sum into the compensated total
 			float y, u;

@@ -44,27 +44,14 @@ __device__ __forceinline__ void m2l_one(float (&Lacc)[Expansion<P>::NC], const f
 	Expansion<P>::template m2l<1, PE>(Lacc, M, D);
 }
 
-#ifndef NBODY_M2L_F32X2
-#define NBODY_M2L_F32X2 0
-#endif
 // Two independent interactions at order PE: both derivative tensors first, then both contractions, so the
 // compiler can interleave two dependency chains (the order-3 tensors are small enough to keep two in registers).
 template <int P, int PE>
 __device__ __forceinline__ void m2l_two(float (&Lacc)[Expansion<P>::NC], const float4& tg, const float4& ga, const float* Ma, const float4& gb,
                                         const float* Mb, float eps2) {
 	float Da[Expansion<PE>::NC], Db[Expansion<PE>::NC];
-#if NBODY_M2L_F32X2
-	{  // both derivative tensors with two-wide instructions (half the issue slots of this part), then the scalar contractions
-		float2 D2[Expansion<PE>::NC];
-		Expansion<PE>::derivatives2(make_float2(tg.x - ga.x, tg.x - gb.x), make_float2(tg.y - ga.y, tg.y - gb.y), make_float2(tg.z - ga.z, tg.z - gb.z),
-		                            eps2, D2);
-#pragma unroll
-		for (int n = 0; n < Expansion<PE>::NC; ++n) { Da[n] = D2[n].x; Db[n] = D2[n].y; }
-	}
-#else
 	Expansion<PE>::derivatives(tg.x - ga.x, tg.y - ga.y, tg.z - ga.z, eps2, Da);
 	Expansion<PE>::derivatives(tg.x - gb.x, tg.y - gb.y, tg.z - gb.z, eps2, Db);
-#endif
 	const SmemCoefs A{reinterpret_cast<const float4*>(Ma)}, B{reinterpret_cast<const float4*>(Mb)};
 	Expansion<P>::template m2l<1, PE>(Lacc, A, Da);
 	Expansion<P>::template m2l<1, PE>(Lacc, B, Db);
@@ -243,175 +230,6 @@ k_m2l(Ctrl* __restrict__ c, const Group* __restrict__ items, uint32_t items_cap,
 	}
 }
 
-// ---- experimental: two sibling targets per warp, two-wide FP32 (build with -DNBODY_M2L_PAIR=1; NOT the default, not yet run on hardware) ----
-// The siblings 2w and 2w+1 of a group accept almost the same candidates: on the Plummer benchmark 93-95 % of the (target pair,
-// candidate) evaluations serve both targets (oracle lists). Warp w of a 4-warp CTA therefore evaluates every
-// candidate either of its two targets accepts ONCE, for both, with FADD2 / FMUL2 / FFMA2: the two separation vectors share one
-// instruction stream (derivatives2), the source's multipole coefficients are scalars that the two-wide FMA broadcasts to both
-// halves, and the two local expansions are accumulated as register pairs. A target that does not accept the candidate is masked
-// out through 1/R (its tensor is exact zeros); a pair that is order P for one target and order P-1 for the other runs at order P.
-// 0.57 x the issue slots of the one-target-per-warp kernel by that count. Staging (cp.async double buffering, id ring) as in k_m2l.
-#ifndef NBODY_M2L_PAIR
-#define NBODY_M2L_PAIR 0
-#endif
-#if NBODY_M2L_PAIR
-constexpr int kPairThreads = 128;
-#ifndef NBODY_M2L_PAIR_CTAS
-#define NBODY_M2L_PAIR_CTAS 3
-#endif
-constexpr int kPairCtas = NBODY_M2L_PAIR_CTAS;  // CTAs per SM the register allocation is held to: 3 -> 65536 / (3 x 128) = 170 registers per thread
-
-template <int P>
-struct M2LPairShared {
-	static constexpr int CH = 256;                  // candidate slots per chunk (two per thread)
-	static constexpr int MS = coef_stride(P - 1);
-	float sM[2][CH * MS];
-	float4 sgeom[2][CH];
-	uint32_t sid[3][CH];
-	uint8_t smask[3][CH], smask_lo[3][CH];
-	uint8_t list_hi[4][CH], list_lo[4][CH];         // per warp: slots evaluated at order P / at order P-1
-	uint32_t item;
-};
-
-// One source against the warp's two targets at order PE. tx/ty/tz = the two target centres, `v` bit t = target t accepts.
-template <int P, int PE>
-__device__ __forceinline__ void m2l_pair_one(float2 (&Lacc)[Expansion<P>::NC], const float2 tx, const float2 ty, const float2 tz, const float4& sg,
-                                             const float* sM, float eps2, unsigned v) {
-	float2 D[Expansion<PE>::NC];
-	const float2 keep = make_float2((v & 1u) ? 1.0f : 0.0f, (v & 2u) ? 1.0f : 0.0f);
-	Expansion<PE>::template derivatives2<true>(__fadd2_rn(tx, make_float2(-sg.x, -sg.x)), __fadd2_rn(ty, make_float2(-sg.y, -sg.y)),
-	                                           __fadd2_rn(tz, make_float2(-sg.z, -sg.z)), eps2, D, keep);
-	const SmemCoefs M{reinterpret_cast<const float4*>(sM)};
-	Expansion<P>::template m2l_bc<1, PE>(Lacc, M, D);
-}
-
-template <int P>
-__global__ void __launch_bounds__(kPairThreads, kPairCtas)
-k_m2l_pair(Ctrl* __restrict__ c, const Group* __restrict__ items, uint32_t items_cap, const float4* __restrict__ geom, const float* __restrict__ M,
-           float* __restrict__ L, const uint32_t* __restrict__ m2l_id, const uint8_t* __restrict__ m2l_mask, const uint8_t* __restrict__ m2l_mask_lo,
-           float eps2) {
-	using E = Expansion<P>;
-	using SH = M2LPairShared<P>;
-	constexpr int CH = SH::CH, T = kPairThreads, HALVES = CH / T;
-	constexpr int STRIDE = coef_stride(P), S4 = STRIDE / 4, MS = SH::MS, MS4 = MS / 4;
-	constexpr int PL = P > 2 ? P - 1 : P;
-	extern __shared__ __align__(16) unsigned char smem_raw[];
-	SH& S = *reinterpret_cast<SH*>(smem_raw);
-	const unsigned tid = threadIdx.x, lane = tid & 31u, w = tid >> 5;  // w = 0..3: targets 2w, 2w+1
-	const unsigned lt_mask = (1u << lane) - 1u;
-	const uint32_t n_items = min(c->items_count[0], items_cap);
-	const float4* M4 = reinterpret_cast<const float4*>(M);
-	for (;;) {
-		__syncthreads();
-		if (tid == 0) S.item = atomicAdd(&c->work_ticket[0], 1u);
-		__syncthreads();
-		const uint32_t it = S.item;
-		if (it >= n_items) break;
-		const Group G = items[it];
-		const uint32_t t0 = G.first + 2u * w;
-		const float4 g0 = geom[t0], g1 = geom[t0 + 1u];
-		const float2 tx = make_float2(g0.x, g1.x), ty = make_float2(g0.y, g1.y), tz = make_float2(g0.z, g1.z);
-		float2 Lacc[E::NC];
-#pragma unroll
-		for (int a = 0; a < E::NC; ++a) Lacc[a] = make_float2(0.0f, 0.0f);
-		unsigned any = 0u;  // bit t: target t accumulated something
-		const uint32_t nchunks = (G.list_cnt + CH - 1) / CH;
-		uint32_t id_n[HALVES], mk_n[HALVES];
-		auto fetch = [&](uint32_t chunk) {
-#pragma unroll
-			for (int h = 0; h < HALVES; ++h) {
-				const uint32_t e = chunk * CH + tid + T * h;
-				id_n[h] = 0; mk_n[h] = 0;
-				if (chunk < nchunks && e < G.list_cnt) { id_n[h] = m2l_id[G.list_off + e]; mk_n[h] = m2l_mask[G.list_off + e] | (uint32_t) m2l_mask_lo[G.list_off + e] << 8; }
-			}
-		};
-		auto publish = [&](uint32_t chunk) {
-			const int r = chunk % 3;
-#pragma unroll
-			for (int h = 0; h < HALVES; ++h) {
-				S.sid[r][tid + T * h] = id_n[h]; S.smask[r][tid + T * h] = (uint8_t) mk_n[h]; S.smask_lo[r][tid + T * h] = (uint8_t) (mk_n[h] >> 8);
-			}
-		};
-		auto issue = [&](uint32_t chunk, int buf) {
-			const uint32_t ns = min((uint32_t) CH, G.list_cnt - chunk * CH);
-			const uint32_t* ids = S.sid[chunk % 3];
-			float4* dst = reinterpret_cast<float4*>(S.sM[buf]);
-#pragma unroll
-			for (int r = 0; r < MS4 * HALVES; ++r) {
-				const uint32_t piece = tid + r * T, slot = piece / MS4, j = piece - slot * MS4;
-				if (slot < ns) cp_async16(dst + piece, M4 + (size_t) ids[slot] * S4 + j);
-			}
-#pragma unroll
-			for (int h = 0; h < HALVES; ++h)
-				if (tid + T * h < ns) cp_async16(&S.sgeom[buf][tid + T * h], geom + ids[tid + T * h]);
-			cp_async_commit();
-		};
-		fetch(0); publish(0);
-		fetch(1); publish(1);
-		fetch(2);
-		__syncthreads();
-		issue(0, 0);
-		for (uint32_t ch = 0; ch < nchunks; ++ch) {
-			const int cur = ch & 1;
-			cp_async_wait_all();
-			__syncthreads();  // chunk ch has landed for everyone; everyone has finished chunk ch-1; ids of ch+1 are visible
-			if (ch + 1 < nchunks) issue(ch + 1, cur ^ 1);
-			const uint32_t ns = min((uint32_t) CH, G.list_cnt - ch * CH);
-			const uint8_t* mk_acc = S.smask[ch % 3];
-			const uint8_t* mk_lo = S.smask_lo[ch % 3];
-			// ---- compact the slots either target accepts into the two order classes (order P if either target needs it) ----
-			uint32_t cnt_h = 0, cnt_l = 0;
-#pragma unroll
-			for (int i = 0; i < CH / 32; ++i) {
-				const uint32_t s = lane + 32 * i;
-				unsigned a2 = 0u, l2 = 0u;
-				if (s < ns) { a2 = (mk_acc[s] >> (2u * w)) & 3u; l2 = (mk_lo[s] >> (2u * w)) & 3u; }
-				const bool hi = (a2 & ~l2) != 0u, lo = a2 != 0u && !hi;
-				const unsigned bh = __ballot_sync(0xffffffffu, hi), bl = __ballot_sync(0xffffffffu, lo);
-				if (hi) S.list_hi[w][cnt_h + __popc(bh & lt_mask)] = (uint8_t) s;
-				if (lo) S.list_lo[w][cnt_l + __popc(bl & lt_mask)] = (uint8_t) s;
-				cnt_h += __popc(bh); cnt_l += __popc(bl);
-				any |= a2;
-			}
-			__syncwarp();
-			// idle lanes of the last order-P step take pairs from the tail of the order-(P-1) list, as in k_m2l
-			const uint32_t take = min((32u - (cnt_h & 31u)) & 31u, cnt_l);
-			cnt_l -= take;
-			const uint32_t tot_h = cnt_h + take;
-			for (uint32_t k = lane; k < tot_h; k += 32) {
-				const uint32_t s = k < cnt_h ? S.list_hi[w][k] : S.list_lo[w][cnt_l + (k - cnt_h)];
-				m2l_pair_one<P, P>(Lacc, tx, ty, tz, S.sgeom[cur][s], S.sM[cur] + s * MS, eps2, (mk_acc[s] >> (2u * w)) & 3u);
-			}
-			for (uint32_t k = lane; k < cnt_l; k += 32) {
-				const uint32_t s = S.list_lo[w][k];
-				m2l_pair_one<P, PL>(Lacc, tx, ty, tz, S.sgeom[cur][s], S.sM[cur] + s * MS, eps2, (mk_acc[s] >> (2u * w)) & 3u);
-			}
-			publish(ch + 2);
-			fetch(ch + 3);
-		}
-		any = __reduce_or_sync(0xffffffffu, any);
-		// warp reductions (transposing: 31 shuffles for 32 coefficients) per target, then lane a-1 adds coefficient a
-#pragma unroll
-		for (int t = 0; t < 2; ++t) {
-			if (!(any >> t & 1u)) continue;  // warp-uniform
-			float v[32];
-#pragma unroll
-			for (int a = 0; a < 32; ++a) v[a] = a + 1 < E::NC ? (t ? Lacc[a + 1].y : Lacc[a + 1].x) : 0.0f;
-			transpose_reduce32(v, lane);
-			float* Lt = L + (size_t) (t0 + t) * STRIDE;
-			if (lane + 1u < (unsigned) E::NC) atomicAdd(Lt + lane + 1u, v[0]);
-#pragma unroll
-			for (int a = 33; a < E::NC; ++a) {
-				float x = t ? Lacc[a].y : Lacc[a].x;
-#pragma unroll
-				for (int d = 16; d >= 1; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
-				if (lane == (unsigned) (a & 31)) atomicAdd(Lt + a, x);
-			}
-		}
-	}
-}
-#endif  // NBODY_M2L_PAIR
-
 // L2L: every non-empty node adds the shifted local expansion of its parent; levels ascending.
 template <int P>
 __global__ void __launch_bounds__(128) k_l2l(const Ctrl* __restrict__ c, int l, const float4* __restrict__ geom,
@@ -452,14 +270,8 @@ static void m2l_t(Sim& s) {
 	const float eps2 = s.cfg.softening * s.cfg.softening;
 	cudaFuncSetAttribute(k_m2l<P, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(M2LShared<P, 8>));
 	cudaFuncSetAttribute(k_m2l<P, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(M2LShared<P, 1>));
-#if NBODY_M2L_PAIR
-	cudaFuncSetAttribute(k_m2l_pair<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(M2LPairShared<P>));
-	k_m2l_pair<P><<<kNumSM * kPairCtas, kPairThreads, sizeof(M2LPairShared<P>), s.stream>>>(s.ctrl, s.pools.items[0], s.pools.items_cap, s.geom, s.M,
-	                                                                                      s.L, s.pools.m2l_id, s.pools.m2l_mask, s.pools.m2l_mask_lo, eps2);
-#else
 	k_m2l<P, 8><<<kNumSM * 2, 256, sizeof(M2LShared<P, 8>), s.stream>>>(s.ctrl, s.pools.items[0], s.pools.items_cap, s.geom, s.M, s.L,
 	                                                                  s.pools.m2l_id, s.pools.m2l_mask, s.pools.m2l_mask_lo, eps2);
-#endif
 	k_m2l<P, 1><<<kNumSM * 16, 32, sizeof(M2LShared<P, 1>), s.stream>>>(s.ctrl, s.pools.items[1], s.pools.items_cap, s.geom, s.M, s.L,
 	                                                                  s.pools.m2l_id, s.pools.m2l_mask, s.pools.m2l_mask_lo, eps2);
 }

@@ -22,8 +22,6 @@ def hostlib():
     L = C.CDLL(so)
     L.exp_chain.argtypes = [C.c_int, f32p, C.c_int, f32p, f32p, f32p, f32p, f32p, C.c_int, C.c_float, f32p, f32p, f32p]
     L.exp_derivatives.argtypes = [C.c_int] + [C.c_float] * 4 + [f32p]
-    L.exp_derivatives2.argtypes = [C.c_int, f32p, f32p, C.c_float, f32p, f32p]
-    L.exp_pair.argtypes = [C.c_int, C.c_int, f32p, f32p, f32p, C.c_float, C.c_uint, f32p, f32p, f32p, f32p]
     return L
 
 
@@ -85,42 +83,3 @@ def test_operator_chain_converges(hostlib, p, tol):
     for a, (i, j, k) in enumerate(multi_indices(p)):
         ref = (src[:, 3] * r[:, 0] ** i * r[:, 1] ** j * r[:, 2] ** k).sum() / (f(i) * f(j) * f(k))
         assert abs(M[a] - ref) <= 1e-5 * max(abs(ref), 1e-3), (i, j, k)
-
-
-@pytest.mark.parametrize("p", [2, 3, 4])
-def test_packed_derivative_tensors_equal_the_scalar_ones(hostlib, p):
-    """Expansion::derivatives2 (two tensors with two-wide FP32 operations, -DNBODY_M2L_F32X2=1) against derivatives(), per half"""
-    rng = np.random.default_rng(p)
-    nc = hostlib.exp_ncoef(p)
-    for _ in range(50):
-        a, b = rng.uniform(-1, 1, 3).astype(np.float32), rng.uniform(-1, 1, 3).astype(np.float32)
-        eps2 = float(rng.choice([0.0, 1e-4, 0.3]))
-        Da, Db, Ra, Rb = (np.zeros(nc, np.float32) for _ in range(4))
-        hostlib.exp_derivatives2(p, a, b, eps2, Da, Db)
-        hostlib.exp_derivatives(p, float(a[0]), float(a[1]), float(a[2]), eps2, Ra)
-        hostlib.exp_derivatives(p, float(b[0]), float(b[1]), float(b[2]), eps2, Rb)
-        for got, ref in ((Da, Ra), (Db, Rb)):
-            assert np.allclose(got, ref, rtol=2e-5, atol=2e-5 * np.abs(ref).max())
-
-
-@pytest.mark.parametrize("p,pe", [(4, 4), (4, 3), (3, 3), (3, 2), (2, 2)])
-def test_two_target_m2l_equals_two_scalar_m2l(hostlib, p, pe):
-    """k_m2l_pair's arithmetic (-DNBODY_M2L_PAIR=1): masked derivatives2 + broadcast contraction m2l_bc for one source against two
-    targets equals the two scalar M2Ls; a masked-out target receives exact zeros."""
-    rng = np.random.default_rng(10 * p + pe)
-    nc = hostlib.exp_ncoef(p)
-    for trial in range(40):
-        d0 = (rng.uniform(-1, 1, 3) + np.array([3.0, 0, 0])).astype(np.float32)
-        d1 = (rng.uniform(-1, 1, 3) + np.array([3.0, 0.5, 0])).astype(np.float32)
-        M = rng.normal(size=nc).astype(np.float32)
-        keep = [3, 1, 2, 0][trial % 4]
-        out = [np.zeros(nc, np.float32) for _ in range(4)]
-        hostlib.exp_pair(p, pe, d0, d1, M, 1e-4, keep, *out)
-        L0, L1, R0, R1 = out
-        scale = max(np.abs(R0).max(), np.abs(R1).max(), 1e-30)
-        assert np.allclose(L0, R0, rtol=2e-5, atol=2e-6 * scale) and np.allclose(L1, R1, rtol=2e-5, atol=2e-6 * scale)
-        if not keep & 1:
-            assert not L0.any()
-        if not keep & 2:
-            assert not L1.any()
-        assert L0[0] == 0 and L1[0] == 0                                         # the potential term is not carried

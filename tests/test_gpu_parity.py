@@ -352,24 +352,3 @@ def test_distributed_sort_pipeline_equals_stable_sort(n, nruns):
     sk, perm = oracle.sort_keys(keys)
     assert np.array_equal(k, sk) and np.array_equal(i.astype(np.int64), np.asarray(perm, np.int64))
 
-
-@pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("NBODY_TEST_EXPERIMENTAL") != "1", reason="compares an experimental library variant with the default one; "
-                    "set NBODY_TEST_EXPERIMENTAL=1 and NBODY_VARIANT_LIB=<path to libnbody_cuda_x2.so>")
-def test_two_wide_all_pairs_field_is_bit_identical_to_the_scalar_one():
-    """-DNBODY_P2P_F32X2=1 claims the same IEEE operations in the same order per component: with softening the all-pairs kernel
-    (deterministic summation order) must return the same bits from both libraries."""
-    import ctypes as C
-    variant = os.environ.get("NBODY_VARIANT_LIB", os.path.join(os.path.dirname(nbody_b200.LIB_PATH), "libnbody_cuda_x2.so"))
-    if not os.path.exists(variant) or os.path.realpath(variant) == os.path.realpath(nbody_b200.LIB_PATH):
-        pytest.skip("no separate variant library")
-    P = workloads.plummer(30000)
-    src = np.ascontiguousarray(np.concatenate([P[:, 0:3], P[:, 9:10]], axis=1))
-    ref, _ = nbody_b200.direct_field(src, src[:5000], 0.01)
-    V = C.CDLL(variant)
-    V.nbody_cuda_direct_field.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_float, C.c_void_p, C.POINTER(C.c_float), C.c_uint32]
-    out = np.empty((5000, 3), np.float32)
-    ms = C.c_float()
-    tgt = np.ascontiguousarray(src[:5000])
-    assert V.nbody_cuda_direct_field(-1, src.ctypes.data, src.shape[0], tgt.ctypes.data, 5000, 0.01, out.ctypes.data, C.byref(ms), 1) == 0
-    assert np.array_equal(out.view(np.uint32), ref.view(np.uint32))

@@ -4,13 +4,7 @@
 set -e
 cd "$(dirname "$0")/.."
 python nbody_b200/build.py
-NBODY_BUILD_TAG=x2 NBODY_BUILD_DEFS="-DNBODY_P2P_F32X2=1" python nbody_b200/build.py
 NBODY_BUILD_TAG=bulk NBODY_BUILD_DEFS="-DNBODY_LEAF_BULK=1" python nbody_b200/build.py
 NBODY_BUILD_TAG=bulk_rows2 NBODY_BUILD_DEFS="-DNBODY_LEAF_BULK=1 -DNBODY_LEAF_ROWS=2" python nbody_b200/build.py   # tiles padded to 64 instead of 128 sources
-NBODY_BUILD_TAG=bulk_x2 NBODY_BUILD_DEFS="-DNBODY_LEAF_BULK=1 -DNBODY_P2P_F32X2=1" python nbody_b200/build.py
-NBODY_BUILD_TAG=m2lx2 NBODY_BUILD_DEFS="-DNBODY_M2L_F32X2=1" python nbody_b200/build.py
-NBODY_BUILD_TAG=m2lpair NBODY_BUILD_DEFS="-DNBODY_M2L_PAIR=1" python nbody_b200/build.py
-NBODY_BUILD_TAG=m2lpair2 NBODY_BUILD_DEFS="-DNBODY_M2L_PAIR=1 -DNBODY_M2L_PAIR_CTAS=2" python nbody_b200/build.py
-NBODY_BUILD_TAG=all NBODY_BUILD_DEFS="-DNBODY_LEAF_BULK=1 -DNBODY_P2P_F32X2=1 -DNBODY_M2L_PAIR=1" python nbody_b200/build.py
 (cd tools/micro && nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o fma_peak fma_peak.cu)
-for t in x2 bulk bulk_x2; do grep -A3 "k_leafILi4ELb1" nbody_b200/build_$t/leaf.o.log | grep -E "Used|spill" | tr '\n' ' '; echo " <- $t"; done
+for t in bulk bulk_rows2; do grep -A3 "k_leafILi4ELb1" nbody_b200/build_$t/leaf.o.log | grep -E "Used|spill" | tr '\n' ' '; echo " <- $t"; done
