@@ -1,5 +1,5 @@
 """How often two sibling targets share an M2L candidate, from the oracle's lists (CPU only): the basis of the two-targets-per-warp
-M2L kernel (m2l.cu: k_m2l_pair).    python tests/tools/m2l_pairing.py N CAPACITY
+M2L kernel that was written, shown not to pay (two-wide FP32 costs two issue cycles on B200) and removed.    python tests/tools/m2l_pairing.py N CAPACITY
 Prints, for the three ways of pairing the eight children, evaluations needed when a pair of targets shares one evaluation, and the
 issue-slot ratio against one evaluation per (target, candidate) when a shared evaluation runs at the higher of the two orders."""
 import sys, numpy as np
