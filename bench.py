@@ -375,7 +375,7 @@ def launches_per_step(sim, world):
     d = int(sim.config.max_depth)
     sort = 8 * 5                 # per 8-bit pass: histogram, three scan kernels, scatter
     if world > 1 and (int(sim.config.flags) & 64):
-        sort += (world - 1).bit_length()   # NBODY_FLAG_DIST_SORT: the same passes over the rank's slice, then log2(world) merge rounds
+        sort += 2 * (world - 1).bit_length()   # NBODY_FLAG_DIST_SORT: the same passes over the rank's slice, then log2(world) merge rounds of two kernels
     tree = 1 + 2 * d             # init, per level (count, split)
     upsweep = 1 + d              # P2M, per level M2M
     traversal = 1 + 2 * d        # init, per round (prep, traverse)

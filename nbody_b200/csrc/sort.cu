@@ -212,23 +212,27 @@ void launch_own_sort_range(Sim& s, uint64_t first, uint64_t n) {
 void launch_own_sort(Sim& s) { launch_own_sort_range(s, 0, s.n); }
 
 // ---- distributed sort (NBODY_FLAG_DIST_SORT): pairwise stable merges of the all-gathered, slice-wise sorted runs ----
-// One CTA per tile of kMergeTile outputs of one pair of adjacent runs (merge_path.h has the plan and the index arithmetic,
-// checked on the CPU by tests/test_merge_host.py). Two threads find the tile's split points by merge-path searches in global
-// memory (~2 x 24 dependent loads, hidden by the other resident CTAs), the inputs are staged in shared memory with coalesced
-// loads, every thread merges kMergeVT outputs from its own split point, and the merged tile goes back through shared memory so
-// that the global writes are contiguous. HBM traffic: 12 B read + 12 B written per element and round.
-__global__ void __launch_bounds__(kMergeThreads) k_merge_runs(const MergePlan pl, const uint64_t* __restrict__ kin, const uint32_t* __restrict__ vin,
-                                                              uint64_t* __restrict__ kout, uint32_t* __restrict__ vout) {
+// merge_path.h has the plan and the index arithmetic (checked on the CPU by tests/test_merge_host.py). Two kernels per round:
+// k_merge_partition finds every tile's split point with one merge-path search in global memory per thread (all tiles at once: one
+// latency chain of ~24 dependent loads for the whole round instead of one per CTA); k_merge_runs then streams: one CTA per tile of
+// kMergeTile outputs stages its inputs in shared memory with coalesced loads, every thread merges kMergeVT outputs from its own
+// split point, and the merged tile goes back through shared memory so that the global writes are contiguous.
+// HBM traffic: 12 B read + 12 B written per element and round.
+__global__ void __launch_bounds__(256) k_merge_partition(const MergePlan pl, uint32_t tiles, const uint64_t* __restrict__ kin, uint32_t* __restrict__ split) {
+	const uint32_t tile = blockIdx.x * blockDim.x + threadIdx.x;
+	if (tile >= tiles) return;
+	const MergeTileRange r = merge_tile_range(pl, tile);
+	split[tile] = merge_path(kin + r.a0, r.na, kin + r.a0 + r.na, r.nb, r.d0);
+}
+
+__global__ void __launch_bounds__(kMergeThreads) k_merge_runs(const MergePlan pl, const uint32_t* __restrict__ split, const uint64_t* __restrict__ kin,
+                                                              const uint32_t* __restrict__ vin, uint64_t* __restrict__ kout, uint32_t* __restrict__ vout) {
 	__shared__ uint64_t sk[kMergeTile];
 	__shared__ uint32_t sv[kMergeTile];
-	__shared__ uint32_t split[2];
 	const MergeTileRange r = merge_tile_range(pl, blockIdx.x);
-	const uint64_t* A = kin + r.a0;
-	const uint64_t* B = kin + r.a0 + r.na;
-	if (threadIdx.x == 0) split[0] = merge_path(A, r.na, B, r.nb, r.d0);
-	if (threadIdx.x == 32) split[1] = merge_path(A, r.na, B, r.nb, r.d1);
-	__syncthreads();
-	const uint32_t i0 = split[0], i1 = split[1], j0 = r.d0 - i0, j1 = r.d1 - i1;
+	// this tile's split, and the next tile's (the end of the A run when this is the pair's last tile)
+	const uint32_t i0 = split[blockIdx.x], i1 = r.d1 == r.na + r.nb ? r.na : split[blockIdx.x + 1];
+	const uint32_t j0 = r.d0 - i0, j1 = r.d1 - i1;
 	const uint32_t ca = i1 - i0, cb = j1 - j0, cnt = ca + cb;  // cnt = d1 - d0 <= kMergeTile
 	for (uint32_t t = threadIdx.x; t < cnt; t += kMergeThreads) {
 		const uint32_t src = t < ca ? r.a0 + i0 + t : r.a0 + r.na + j0 + (t - ca);
@@ -267,7 +271,11 @@ void launch_merge_runs(Sim& s, const uint32_t* bound, int nruns) {
 	int from = 0;
 	while (pl.nruns > 1) {
 		const uint32_t tiles = merge_plan_tiles(pl);
-		if (tiles) k_merge_runs<<<tiles, kMergeThreads, 0, s.stream>>>(pl, s.keys[from], s.idx[from], s.keys[from ^ 1], s.idx[from ^ 1]);
+		uint32_t* split = static_cast<uint32_t*>(s.sort_tmp);  // the radix sort's histogram scratch (256 words per 4096 elements) is free by now
+		if (tiles) {
+			k_merge_partition<<<(tiles + 255) / 256, 256, 0, s.stream>>>(pl, tiles, s.keys[from], split);
+			k_merge_runs<<<tiles, kMergeThreads, 0, s.stream>>>(pl, split, s.keys[from], s.idx[from], s.keys[from ^ 1], s.idx[from ^ 1]);
+		}
 		from ^= 1;
 		pl = merge_plan_next(pl);
 	}

@@ -1,6 +1,6 @@
 // Host build of nbody_b200/csrc/merge_path.h for CPU-side unit tests (g++): runs the distributed sort's merge rounds exactly as
-// the kernel k_merge_runs (sort.cu) decomposes them — tile ranges from the plan, two merge-path searches per tile in the global
-// arrays, staging, one merge-path search and one serial merge per thread — with loops in place of CTAs and threads.
+// the kernels k_merge_partition / k_merge_runs (sort.cu) decompose them — tile ranges from the plan, one merge-path search per tile
+// in the global arrays, staging, one merge-path search and one serial merge per thread — with loops in place of CTAs and threads.
 #include <algorithm>
 #include <cstdint>
 #include <vector>
@@ -11,11 +11,14 @@ using namespace nbody;
 static void merge_round(const MergePlan& pl, uint32_t tiles, const uint64_t* kin, const uint32_t* vin, uint64_t* kout, uint32_t* vout) {
 	std::vector<uint64_t> sk(kMergeTile);
 	std::vector<uint32_t> sv(kMergeTile);
-	for (uint32_t tile = 0; tile < tiles; ++tile) {
+	std::vector<uint32_t> split(tiles);
+	for (uint32_t tile = 0; tile < tiles; ++tile) {  // k_merge_partition: one search per tile
 		const MergeTileRange r = merge_tile_range(pl, tile);
-		const uint64_t* A = kin + r.a0;
-		const uint64_t* B = kin + r.a0 + r.na;
-		const uint32_t i0 = merge_path(A, r.na, B, r.nb, r.d0), i1 = merge_path(A, r.na, B, r.nb, r.d1);
+		split[tile] = merge_path(kin + r.a0, r.na, kin + r.a0 + r.na, r.nb, r.d0);
+	}
+	for (uint32_t tile = 0; tile < tiles; ++tile) {  // k_merge_runs
+		const MergeTileRange r = merge_tile_range(pl, tile);
+		const uint32_t i0 = split[tile], i1 = r.d1 == r.na + r.nb ? r.na : split[tile + 1];
 		const uint32_t j0 = r.d0 - i0, j1 = r.d1 - i1, ca = i1 - i0, cb = j1 - j0, cnt = ca + cb;
 		for (uint32_t t = 0; t < cnt; ++t) {
 			const uint32_t src = t < ca ? r.a0 + i0 + t : r.a0 + r.na + j0 + (t - ca);

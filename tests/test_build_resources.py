@@ -37,7 +37,7 @@ def select(pattern):
 def test_every_kernel_is_built_for_sm_100a_and_found():
     names = "".join(K)
     for kernel in ("k_keys", "k_sort_hist", "k_sort_scatter", "k_gather", "k_level_count", "k_level_split", "k_p2m", "k_m2m", "k_traverse",
-                   "k_m2l", "k_l2l", "k_leaf", "k_direct", "k_acc_max", "k_partition", "k_gather_vel", "k_keys_range", "k_merge_runs"):
+                   "k_m2l", "k_l2l", "k_leaf", "k_direct", "k_acc_max", "k_partition", "k_gather_vel", "k_keys_range", "k_merge_partition", "k_merge_runs"):
         assert kernel in names, kernel
 
 
