@@ -14,6 +14,7 @@
 #include <dlfcn.h>
 #include <nccl.h>  // types and enums only: the library itself is bound at run time (see NcclApi)
 
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -30,6 +31,7 @@ struct NcclApi {
 	ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
 	ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
 	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+	ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t*, void*) = nullptr;  // optional (NCCL >= 2.18); last argument: ncclConfig_t*
 	ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
 	ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
 	ncclResult_t (*GroupStart)() = nullptr;
@@ -49,6 +51,7 @@ static bool nccl_load() {
 	g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId)) sym("ncclGetUniqueId");
 	g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank)) sym("ncclCommInitRank");
 	g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy)) sym("ncclCommDestroy");
+	g_nccl.CommSplit = (decltype(g_nccl.CommSplit)) sym("ncclCommSplit");
 	g_nccl.AllGather = (decltype(g_nccl.AllGather)) sym("ncclAllGather");
 	g_nccl.Broadcast = (decltype(g_nccl.Broadcast)) sym("ncclBroadcast");
 	g_nccl.GroupStart = (decltype(g_nccl.GroupStart)) sym("ncclGroupStart");
@@ -66,6 +69,7 @@ void destroy_for_comm(Sim* s);
 
 struct Comm {
 	ncclComm_t comm = nullptr;
+	ncclComm_t vel_comm = nullptr;  // a duplicate of `comm` for the velocity stream (only with NBODY_FLAG_DIST_SORT, when ncclCommSplit exists)
 	int rank = 0, world = 1;
 	uint32_t* part_host = nullptr;  // pinned, world + 1: boundaries of the last step
 	float* work_host = nullptr;     // pinned, world: per-rank device time of the owned-slice stages of the last step
@@ -136,15 +140,16 @@ void comm_adopt_partition(Sim& s) {
 	s.own_count = cm.part_host[cm.rank + 1] - cm.part_host[cm.rank];
 }
 
-static int exchange(Sim& s, void* buf, size_t elem_bytes, cudaStream_t st = nullptr) {
+static int exchange(Sim& s, void* buf, size_t elem_bytes, cudaStream_t st = nullptr, ncclComm_t comm = nullptr) {
 	Comm& cm = *s.comm;
 	if (!st) st = s.stream;
+	if (!comm) comm = cm.comm;
 	NB_NCCL_CHECK(g_nccl.GroupStart());
 	for (int r = 0; r < cm.world; ++r) {
 		const size_t off = (size_t) cm.part_host[r] * elem_bytes, cnt = (size_t) (cm.part_host[r + 1] - cm.part_host[r]) * elem_bytes;
 		if (cnt == 0) continue;
 		char* p = static_cast<char*>(buf) + off;
-		NB_NCCL_CHECK(g_nccl.Broadcast(p, p, cnt, ncclChar, r, cm.comm, st));
+		NB_NCCL_CHECK(g_nccl.Broadcast(p, p, cnt, ncclChar, r, comm, st));
 	}
 	NB_NCCL_CHECK(g_nccl.GroupEnd());
 	return NBODY_OK;
@@ -166,9 +171,9 @@ int comm_sort_exchange(Sim& s, uint32_t* bound, int* nruns) {
 	Comm& cm = *s.comm;
 	int rc;
 	// The previous step's velocity broadcasts may still be running on the second stream, and two collectives of ONE communicator
-	// must never be in flight at once: order the compute stream behind them first (the rank's own slice sort, enqueued before
-	// this point, still overlaps them). A second communicator for the velocity stream would restore the full overlap.
-	if ((rc = comm_wait_velocities(s))) return rc;
+	// must never be in flight at once. With a communicator of their own (vel_comm) they simply keep running; without one the
+	// compute stream is ordered behind them first (the rank's own slice sort, enqueued before this point, still overlaps them).
+	if (!cm.vel_comm && (rc = comm_wait_velocities(s))) return rc;
 	if ((rc = exchange(s, s.keys[0], sizeof(uint64_t)))) return rc;
 	if ((rc = exchange(s, s.idx[0], sizeof(uint32_t)))) return rc;
 	for (int r = 0; r <= cm.world; ++r) bound[r] = cm.part_host[r];
@@ -197,7 +202,7 @@ int comm_step_exchange(Sim& s, float own_ms) {
 		// upsweep and traversal; the consumer orders itself after ev_vel (comm_wait_velocities).
 		NB_CUDA_CHECK(cudaEventRecord(cm.ev_step, s.stream));
 		NB_CUDA_CHECK(cudaStreamWaitEvent(cm.vel_stream, cm.ev_step, 0));
-		if ((rc = exchange(s, s.velm[0], sizeof(float4), cm.vel_stream))) return rc;
+		if ((rc = exchange(s, s.velm[0], sizeof(float4), cm.vel_stream, cm.vel_comm))) return rc;
 		NB_CUDA_CHECK(cudaEventRecord(cm.ev_vel, cm.vel_stream));
 		cm.vel_pending = true;
 	}
@@ -251,6 +256,7 @@ void comm_destroy(Sim& s) {
 	if (s.comm->vel_stream) { cudaStreamSynchronize(s.comm->vel_stream); cudaStreamDestroy(s.comm->vel_stream); }
 	if (s.comm->ev_step) cudaEventDestroy(s.comm->ev_step);
 	if (s.comm->ev_vel) cudaEventDestroy(s.comm->ev_vel);
+	if (s.comm->vel_comm) g_nccl.CommDestroy(s.comm->vel_comm);
 	if (s.comm->comm) g_nccl.CommDestroy(s.comm->comm);
 	if (s.comm->part_host) cudaFreeHost(s.comm->part_host);
 	if (s.comm->work_host) cudaFreeHost(s.comm->work_host);
@@ -311,6 +317,10 @@ int nbody_cuda_create_distributed(const nbody_cuda_config* cfg, const nbody_part
 	std::memcpy(&u, id, 128);
 	ncclResult_t nr = g_nccl.CommInitRank(&cm.comm, world, u, rank);
 	if (nr != ncclSuccess) { set_error(std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(nr)); cm.comm = nullptr; return fail(NBODY_ERR_COMM); }
+	if ((cfg->flags & NBODY_FLAG_DIST_SORT) && g_nccl.CommSplit && !std::getenv("NBODY_NO_COMM_SPLIT")) {  // (the variable: A/B runs)
+		// collective: every rank passes the same flags, so either all ranks split or none does
+		if (g_nccl.CommSplit(cm.comm, 0, rank, &cm.vel_comm, nullptr) != ncclSuccess) cm.vel_comm = nullptr;
+	}
 	// assemble the global AoS array: every rank contributes its slice (all-gather with unequal counts)
 	std::vector<unsigned long long> h(2 * world, 0ull);
 	unsigned long long* d = nullptr;
