@@ -10,9 +10,10 @@ timeout 150 $TR --master-port 29656 tools/mg_check.py 3000000 4 plummer 0 64 > g
 grep -h "MG_CHECK\|single-GPU vs\|state identical\|rc=" gpurun_out/r02b_mg_check_dist_sort_3M.log | cut -c1-320
 timeout 150 $TR --master-port 29657 bench.py --gpus 2 --steps 6 --warmup 3 --no-reference-capacity --e2e-steps 2 > gpurun_out/r02b_bench_16M_2gpu.json 2> gpurun_out/r02b_bench_2gpu.err; echo "bench rc=$?"
 timeout 150 $TR --master-port 29658 bench.py --gpus 2 --steps 6 --warmup 3 --no-reference-capacity --e2e-steps 2 --flags 64 > gpurun_out/r02b_bench_16M_2gpu_dist_sort.json 2> gpurun_out/r02b_bench_2gpu_dist_sort.err; echo "bench rc=$?"
+NBODY_NO_COMM_SPLIT=1 timeout 150 $TR --master-port 29659 bench.py --gpus 2 --steps 6 --warmup 3 --no-reference-capacity --e2e-steps 2 --flags 64 > gpurun_out/r02b_bench_16M_2gpu_dist_sort_one_comm.json 2> gpurun_out/r02b_bench_2gpu_dist_sort_one_comm.err; echo "bench rc=$?"
 python - <<'PY'
 import json
-for f in ("r02b_bench_16M_2gpu.json", "r02b_bench_16M_2gpu_dist_sort.json"):
+for f in ("r02b_bench_16M_2gpu.json", "r02b_bench_16M_2gpu_dist_sort.json", "r02b_bench_16M_2gpu_dist_sort_one_comm.json"):
     try:
         d = json.load(open("gpurun_out/" + f)); print(f, round(d["ms_per_step"], 3), round(d["device_ms_per_step"], 3), {k: round(v, 2) for k, v in d["stage_ms"].items()}, round(d["e2e"]["ms_per_step"], 2))
     except Exception as e:
