@@ -79,8 +79,9 @@ struct Comm {
 	float* red_dev = nullptr;       // device, world
 	// velocities travel on a second stream: the other ranks need them only in the next step's leaf kernel
 	cudaStream_t vel_stream = nullptr;
-	cudaEvent_t ev_step = nullptr, ev_vel = nullptr;
+	cudaEvent_t ev_step = nullptr, ev_vel = nullptr, ev_pos = nullptr;
 	bool vel_pending = false;       // a velocity exchange was issued that the compute stream has not been ordered after yet
+	bool pos_pending = false;       // the same for a position exchange on the second stream (only with vel_comm)
 };
 
 struct PartitionTargets { uint32_t t[17]; };
@@ -186,9 +187,13 @@ int comm_sort_exchange(Sim& s, uint32_t* bound, int* nruns) {
 int comm_step_exchange(Sim& s, float own_ms) {
 	Comm& cm = *s.comm;
 	int rc;
-	// positions first: every rank's next step starts with the keys of ALL particles
-	if ((rc = exchange(s, s.posq[0], sizeof(float4)))) return rc;
 	const bool overlap = !(s.cfg.flags & NBODY_FLAG_NO_OVERLAP);
+	// positions first: every rank's next step starts with the keys of ALL particles — unless the distributed sort is on, where a
+	// rank computes keys for its own slice only and the other ranks' positions are first read by the gather AFTER the sort: with a
+	// communicator of its own the second stream then carries the positions as well, behind this step's kernels and overlapped with
+	// the next step's slice sort, key all-gather and merge rounds (comm_wait_positions orders the gather after them).
+	const bool pos_on_second = overlap && cm.vel_comm != nullptr && (s.cfg.flags & NBODY_FLAG_DIST_SORT) && !(s.cfg.flags & NBODY_FLAG_CUB_SORT);
+	if (!pos_on_second && (rc = exchange(s, s.posq[0], sizeof(float4)))) return rc;
 	if (!overlap && (rc = exchange(s, s.velm[0], sizeof(float4)))) return rc;
 	s.acc_partial = true;  // accelerations stay rank-local until somebody asks for them (comm_exchange_acc)
 	cm.work_host[cm.rank] = own_ms;
@@ -202,6 +207,11 @@ int comm_step_exchange(Sim& s, float own_ms) {
 		// upsweep and traversal; the consumer orders itself after ev_vel (comm_wait_velocities).
 		NB_CUDA_CHECK(cudaEventRecord(cm.ev_step, s.stream));
 		NB_CUDA_CHECK(cudaStreamWaitEvent(cm.vel_stream, cm.ev_step, 0));
+		if (pos_on_second) {
+			if ((rc = exchange(s, s.posq[0], sizeof(float4), cm.vel_stream, cm.vel_comm))) return rc;
+			NB_CUDA_CHECK(cudaEventRecord(cm.ev_pos, cm.vel_stream));
+			cm.pos_pending = true;
+		}
 		if ((rc = exchange(s, s.velm[0], sizeof(float4), cm.vel_stream, cm.vel_comm))) return rc;
 		NB_CUDA_CHECK(cudaEventRecord(cm.ev_vel, cm.vel_stream));
 		cm.vel_pending = true;
@@ -216,6 +226,17 @@ int comm_wait_velocities(Sim& s) {
 	if (!cm.vel_pending) return NBODY_OK;
 	NB_CUDA_CHECK(cudaStreamWaitEvent(s.stream, cm.ev_vel, 0));
 	cm.vel_pending = false;
+	cm.pos_pending = false;  // the positions travel ahead of the velocities on the same stream
+	return NBODY_OK;
+}
+
+// Orders the compute stream after a position exchange in flight on the second stream, if any: before the first reader of other
+// ranks' positions in the next step (the gather after the distributed sort). Exports and imports go through comm_wait_velocities.
+int comm_wait_positions(Sim& s) {
+	Comm& cm = *s.comm;
+	if (!cm.pos_pending) return NBODY_OK;
+	NB_CUDA_CHECK(cudaStreamWaitEvent(s.stream, cm.ev_pos, 0));
+	cm.pos_pending = false;
 	return NBODY_OK;
 }
 
@@ -256,6 +277,7 @@ void comm_destroy(Sim& s) {
 	if (s.comm->vel_stream) { cudaStreamSynchronize(s.comm->vel_stream); cudaStreamDestroy(s.comm->vel_stream); }
 	if (s.comm->ev_step) cudaEventDestroy(s.comm->ev_step);
 	if (s.comm->ev_vel) cudaEventDestroy(s.comm->ev_vel);
+	if (s.comm->ev_pos) cudaEventDestroy(s.comm->ev_pos);
 	if (s.comm->vel_comm) g_nccl.CommDestroy(s.comm->vel_comm);
 	if (s.comm->comm) g_nccl.CommDestroy(s.comm->comm);
 	if (s.comm->part_host) cudaFreeHost(s.comm->part_host);
@@ -312,7 +334,8 @@ int nbody_cuda_create_distributed(const nbody_cuda_config* cfg, const nbody_part
 	    cudaMalloc((void**) &cm.red_dev, sizeof(float) * world) != cudaSuccess ||
 	    cudaStreamCreateWithFlags(&cm.vel_stream, cudaStreamNonBlocking) != cudaSuccess ||
 	    cudaEventCreateWithFlags(&cm.ev_step, cudaEventDisableTiming) != cudaSuccess ||
-	    cudaEventCreateWithFlags(&cm.ev_vel, cudaEventDisableTiming) != cudaSuccess) { set_error("allocation of the partition tables failed"); return fail(NBODY_ERR_CUDA); }
+	    cudaEventCreateWithFlags(&cm.ev_vel, cudaEventDisableTiming) != cudaSuccess ||
+	    cudaEventCreateWithFlags(&cm.ev_pos, cudaEventDisableTiming) != cudaSuccess) { set_error("allocation of the partition tables failed"); return fail(NBODY_ERR_CUDA); }
 	ncclUniqueId u;
 	std::memcpy(&u, id, 128);
 	ncclResult_t nr = g_nccl.CommInitRank(&cm.comm, world, u, rank);

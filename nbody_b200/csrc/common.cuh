@@ -146,6 +146,7 @@ void launch_own_sort_range(Sim& s, uint64_t first, uint64_t n);                 
 void launch_merge_runs(Sim& s, const uint32_t* bound, int nruns);                      // distributed sort: pairwise merges of sorted runs
 int comm_sort_exchange(Sim& s, uint32_t* bound, int* nruns);                           // distributed sort: all-gather of the sorted runs (comm.cu)
 void comm_own_slice(const Sim& s, uint64_t* first, uint64_t* count);                   // distributed: this rank's slice of the state order
+int comm_wait_positions(Sim& s);                                                      // distributed sort: order the stream after a position exchange on the second stream
 void launch_gather_velocities(Sim& s);                                                 // distributed: the velocity half of stage 1a's gather, delayed until the leaf kernel needs it
 void launch_tree_build(Sim& s);                                                        // stage 1b: linear octree, level-major
 void launch_upsweep(Sim& s);                                                           // stage 2: P2M + M2M

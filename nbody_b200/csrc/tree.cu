@@ -149,6 +149,8 @@ int launch_keys_sort_permute(Sim& s) {
 		const int rc = comm_sort_exchange(s, bound, &nruns);
 		if (rc) return rc;
 		launch_merge_runs(s, bound, nruns);
+		const int rcw = comm_wait_positions(s);  // the other ranks' positions may still be travelling on the second stream
+		if (rcw) return rcw;
 		k_gather_pos<<<grid_for(n, 256), 256, 0, s.stream>>>(n, s.idx[0], s.posq[0], s.orig[0], s.posq[1], s.orig[1]);
 		return NBODY_OK;
 	}
