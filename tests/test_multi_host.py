@@ -123,3 +123,45 @@ def test_rebalance_rule():
     assert rebalance([0, 7], [3.0], 0.5) == [0, 7]
     two = rebalance([0, 0, 100], [1.0, 9.0], 1.0)                              # an empty slice that reported time receives work
     assert two[0] == 0 and two[2] == 100 and 0 < two[1] <= 100
+
+
+def _dist_sort_worker(rank, world, port, tmp):
+    """The data flow of NBODY_FLAG_DIST_SORT with gloo standing in for NCCL: keys of the own slice, slice sort, all-gather of the
+    sorted (key, index) runs with unequal counts, then the merge rounds of merge_path.h (host build) on every rank."""
+    import ctypes as C
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    keys = np.load(os.path.join(tmp, "keys.npy"))                      # the replicated state every rank holds (previous order)
+    part = np.load(os.path.join(tmp, "part.npy"))                      # the previous step's slice boundaries, known to every rank
+    lo, hi = int(part[rank]), int(part[rank + 1])
+    order = np.argsort(keys[lo:hi], kind="stable")                     # the rank's radix sort of its own slice
+    my_k, my_i = keys[lo:hi][order], (np.arange(lo, hi, dtype=np.uint32))[order]
+    gk, gi = [None] * world, [None] * world
+    dist.all_gather_object(gk, my_k)                                   # = one grouped broadcast per rank (comm.cu: exchange)
+    dist.all_gather_object(gi, my_i)
+    k, i = np.ascontiguousarray(np.concatenate(gk)), np.ascontiguousarray(np.concatenate(gi))
+    L = C.CDLL(os.path.join(ROOT, "tests", "host", "libmerge_host.so"))
+    L.merge_all_runs.argtypes = [np.ctypeslib.ndpointer(np.uint64, flags="C"), np.ctypeslib.ndpointer(np.uint32, flags="C"), C.c_uint64,
+                                 np.ctypeslib.ndpointer(np.uint32, flags="C"), C.c_int]
+    L.merge_all_runs(k, i, len(k), np.ascontiguousarray(part, np.uint32), world)
+    np.save(os.path.join(tmp, f"perm{rank}.npy"), i)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_distributed_sort_data_flow_across_two_processes(tmp_path):
+    src = os.path.join(ROOT, "tests", "host", "merge_host.cpp")
+    so = os.path.join(ROOT, "tests", "host", "libmerge_host.so")
+    hdr = os.path.join(ROOT, "nbody_b200", "csrc", "merge_path.h")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-Wall", "-Werror", src, "-o", so])
+    rng = np.random.default_rng(5)
+    n, world = 30011, 2
+    keys = rng.integers(0, 1 << 20, n, dtype=np.uint64)                # plenty of ties
+    part = np.array([0, 13007, n], np.int64)                           # unequal slices
+    np.save(tmp_path / "keys.npy", keys)
+    np.save(tmp_path / "part.npy", part)
+    mp.spawn(_dist_sort_worker, args=(world, 29533, str(tmp_path)), nprocs=world, join=True)
+    ref = np.argsort(keys, kind="stable")
+    for r in range(world):
+        assert np.array_equal(np.load(tmp_path / f"perm{r}.npy").astype(np.int64), ref)   # every rank: the stable sort of all keys
