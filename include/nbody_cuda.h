@@ -64,7 +64,10 @@ enum {
 	NBODY_FLAG_STATIC_PARTITION = 16u, /* multi-GPU: equal particle counts per rank every step instead of per-step load rebalancing */
 	NBODY_FLAG_NO_OVERLAP = 32u,      /* multi-GPU: exchange the velocities on the compute stream inside step() instead of on a second
 	                                     stream overlapped with the next step's sort / tree / traversal (comparison only) */
-	NBODY_FLAG_DIST_SORT = 64u        /* multi-GPU, experimental: every rank sorts only the keys of its own slice, the sorted runs are
+	NBODY_FLAG_PARTITIONED = 128u,    /* multi-GPU: every rank holds only the particles of its Morton-key range and imports a locally
+	                                     essential tree (the other ranks' trees by NCCL all-gather, halo particles by NVLink peer loads)
+	                                     instead of replicating the particle state and the tree on every rank. Memory per GPU ~ N/W + halo. */
+	NBODY_FLAG_DIST_SORT = 64u        /* multi-GPU (replicated scheme): every rank sorts only the keys of its own slice, the sorted runs are
 	                                     all-gathered and merged pairwise, instead of every rank sorting all keys. Same permutation
 	                                     bit for bit. Ignored on a single GPU and with NBODY_FLAG_CUB_SORT. */
 };
@@ -112,6 +115,10 @@ typedef struct nbody_cuda_stats {
 	/* device time of the last step, milliseconds (CUDA events on the compute stream) */
 	float ms_total, ms_sort, ms_tree, ms_upsweep, ms_traverse, ms_m2l, ms_l2l, ms_leaf, ms_comm;
 	float work_imbalance;      /* multi-GPU: max over ranks / mean over ranks - 1 of the owned-slice device time of the last step */
+	/* partitioned mode (NBODY_FLAG_PARTITIONED); 0 otherwise */
+	uint64_t halo_particles;     /* other ranks' particles fetched for the P2P lists of the last step */
+	uint64_t imported_nodes;     /* nodes of the other ranks' trees held as sources */
+	uint64_t migrated_particles; /* particles that arrived from other ranks at the start of the last step */
 } nbody_cuda_stats;
 
 typedef struct nbody_cuda_sim nbody_cuda_sim; /* opaque; single-threaded use */
@@ -239,6 +246,15 @@ int nbody_cuda_comm_unique_id(uint8_t id[128]);
 int nbody_cuda_create_distributed(const nbody_cuda_config* cfg, const nbody_particle* local_particles, uint64_t n_local,
                                   uint64_t n_global, uint64_t global_offset, int rank, int world, const uint8_t id[128],
                                   nbody_cuda_sim** out);
+/* Virtual ranks: the partitioned scheme (NBODY_FLAG_PARTITIONED) with `world` ranks inside ONE process on ONE GPU — the same
+ * phases and kernels, peer pointers to the other members' arrays instead of cudaIpc mappings, device-to-device copies instead of
+ * NCCL. Rank r starts with particles [n r / world, n (r+1) / world). A validation entry point (the parity tests run 2, 4 and 8
+ * ranks on a one-GPU box); each member answers the per-rank calls (get_particles, get_permutation, get_keys, get_accelerations,
+ * get_stats: its own particles, in tree order; concatenated in rank order they are the global tree order). */
+int nbody_cuda_create_group(const nbody_cuda_config* cfg, const nbody_particle* particles, uint64_t n, int world, nbody_cuda_sim** sims_out);
+int nbody_cuda_group_step(nbody_cuda_sim** sims, int world, float* time_out);
+void nbody_cuda_destroy_group(nbody_cuda_sim** sims, int world);
+
 /* Range [first, first+count) of the tree-ordered particle array owned by this rank after the last step
  * (before the first step: the slice passed to nbody_cuda_create_distributed). Single GPU: [0, n). */
 int nbody_cuda_owned_range(nbody_cuda_sim* sim, uint64_t* first, uint64_t* count);

@@ -19,6 +19,7 @@ PARTICLE_FLOATS = 12  # 48-byte AoS record: position[4], velocity[4], mass, char
 
 KICK_DRIFT, EXPLICIT_EULER = 0, 1
 FLAG_KEEP_LISTS, FLAG_NO_INTEGRATE, FLAG_DIRECT, FLAG_CUB_SORT, FLAG_STATIC_PARTITION, FLAG_NO_OVERLAP, FLAG_DIST_SORT = 1, 2, 4, 8, 16, 32, 64
+FLAG_PARTITIONED = 128
 
 EXPORTED_SYMBOLS = [
     "nbody_cuda_default_config", "nbody_cuda_create", "nbody_cuda_destroy", "nbody_cuda_set_particles", "nbody_cuda_step",
@@ -29,6 +30,7 @@ EXPORTED_SYMBOLS = [
     "nbody_cuda_set_time_step", "nbody_cuda_get_time_step", "nbody_cuda_next_time_step", "nbody_cuda_get_time",
     "nbody_cuda_checkpoint_save", "nbody_cuda_checkpoint_info", "nbody_cuda_checkpoint_read", "nbody_cuda_checkpoint_write",
     "nbody_cuda_checkpoint_load",
+    "nbody_cuda_create_group", "nbody_cuda_group_step", "nbody_cuda_destroy_group",
     "nbody_cuda_last_error",
 ]
 CHECKPOINT_MAGIC = 0x31504B435944424E  # the bytes "NBDYCKP1"
@@ -53,7 +55,8 @@ class Stats(C.Structure):
     _fields_ = [(k, C.c_uint64) for k in ("n_particles", "n_nodes", "n_leaves", "n_levels", "m2l_entries", "m2l_interactions",
                                           "m2l_interactions_low", "p2p_entries", "p2p_interactions", "near_entries", "retries", "device_bytes")] + \
                [(k, C.c_float) for k in ("ms_total", "ms_sort", "ms_tree", "ms_upsweep", "ms_traverse", "ms_m2l", "ms_l2l",
-                                         "ms_leaf", "ms_comm", "work_imbalance")]
+                                         "ms_leaf", "ms_comm", "work_imbalance")] + \
+               [(k, C.c_uint64) for k in ("halo_particles", "imported_nodes", "migrated_particles")]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if not k.startswith("_")}
@@ -115,6 +118,10 @@ def load_library():
     L.nbody_cuda_checkpoint_read.argtypes = [C.c_char_p, vp, vp, u64]
     L.nbody_cuda_checkpoint_write.argtypes = [C.c_char_p, C.POINTER(CheckpointHeader), vp, vp]
     L.nbody_cuda_checkpoint_load.argtypes = [C.c_char_p, C.POINTER(Config), C.POINTER(vp)]
+    L.nbody_cuda_create_group.argtypes = [C.POINTER(Config), vp, u64, C.c_int, C.POINTER(vp)]
+    L.nbody_cuda_group_step.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(C.c_float)]
+    L.nbody_cuda_destroy_group.argtypes = [C.POINTER(vp), C.c_int]
+    L.nbody_cuda_destroy_group.restype = None
     L.nbody_cuda_last_error.restype = C.c_char_p
     _lib = L
     return L
@@ -197,6 +204,7 @@ class CudaSimulation:
         t = C.c_float()
         _check(self._lib.nbody_cuda_step(self._h, C.byref(t)))
         self.time = t.value
+        self.n = int(self._lib.nbody_cuda_num_particles(self._h))  # partitioned mode: a rank's particle count changes from step to step
         if self._log is not None:
             self._log.write("Step finished.\n")
         return t.value
@@ -312,6 +320,82 @@ class CudaSimulation:
         if getattr(self, "_h", None) and self._h.value:
             self._lib.nbody_cuda_destroy(self._h)
             self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _Member(CudaSimulation):
+    """One rank of a VirtualGroup: answers the per-rank calls (its own particles, in tree order)."""
+
+    def __init__(self, lib, handle, config):
+        self._lib, self._h, self.config, self._log = lib, C.c_void_p(handle), config, None
+        self.n = int(lib.nbody_cuda_num_particles(self._h))
+        self.time = 0.0
+
+    def step(self):
+        raise NbodyCudaError("a member of a virtual group steps with VirtualGroup.step()")
+
+    def close(self):
+        self._h = C.c_void_p()  # owned by the group
+
+
+class VirtualGroup:
+    """The partitioned multi-GPU scheme (FLAG_PARTITIONED: own particles + locally essential tree) with `world` ranks inside one
+    process on ONE GPU (nbody_cuda_create_group): same kernels and phases, the exchanges are device copies. The parity tests use
+    it to run 2, 4 and 8 ranks on a one-GPU box. particles(), permutation(), keys(), accelerations() concatenate the members in rank
+    order, which is the global tree order."""
+
+    def __init__(self, bounds, particles, time_step, world, **config):
+        self._lib = load_library()
+        particles = np.ascontiguousarray(particles, np.float32)
+        if particles.ndim != 2 or particles.shape[1] != PARTICLE_FLOATS:
+            raise ValueError("particles must be float32 [N, 12]")
+        config["flags"] = int(config.get("flags", 0)) | FLAG_PARTITIONED
+        self.config = default_config(bounds=list(bounds) + [0.0] * (4 - len(bounds)), time_step=time_step, **config)
+        self.world = world
+        self._hs = (C.c_void_p * world)()
+        _check(self._lib.nbody_cuda_create_group(C.byref(self.config), _ptr(particles), particles.shape[0], world, self._hs))
+        self.members = [_Member(self._lib, self._hs[r], self.config) for r in range(world)]
+        self.n = particles.shape[0]
+        self.time = 0.0
+
+    def step(self):
+        t = C.c_float()
+        _check(self._lib.nbody_cuda_group_step(self._hs, self.world, C.byref(t)))
+        self.time = t.value
+        for m in self.members:
+            m.n = int(self._lib.nbody_cuda_num_particles(m._h))
+            m.time = t.value
+        return t.value
+
+    def counts(self):
+        return [m.n for m in self.members]
+
+    def particles(self):
+        return np.concatenate([m.particles() for m in self.members])
+
+    def permutation(self):
+        return np.concatenate([m.permutation() for m in self.members])
+
+    def keys(self):
+        return np.concatenate([m.keys() for m in self.members])
+
+    def accelerations(self):
+        return np.concatenate([m.accelerations() for m in self.members])
+
+    def stats(self):
+        return [m.stats() for m in self.members]
+
+    def close(self):
+        if getattr(self, "_hs", None) is not None and self._hs[0]:
+            self._lib.nbody_cuda_destroy_group(self._hs, self.world)
+            self._hs = None
+            for m in self.members:
+                m._h = C.c_void_p()
 
     def __del__(self):
         try:

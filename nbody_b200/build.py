@@ -11,8 +11,11 @@ CSRC = os.path.join(HERE, "csrc")
 TAG = os.environ.get("NBODY_BUILD_TAG", "")
 OBJ = os.path.join(HERE, "build" + ("_" + TAG if TAG else ""))
 LIB = os.path.join(HERE, "libnbody_cuda" + ("_" + TAG if TAG else "") + ".so")
-SOURCES = ["api.cu", "tree.cu", "sort.cu", "upsweep.cu", "traverse.cu", "m2l.cu", "leaf.cu", "comm.cu", "checkpoint.cu"]
-HEADERS = ["common.cuh", "expansion.cuh", os.path.join("..", "..", "include", "nbody_cuda.h")]
+import glob
+SOURCES = sorted(os.path.basename(f) for f in glob.glob(os.path.join(CSRC, "*.cu")))
+# every header a source may include: editing any of them rebuilds everything
+HEADERS = sorted(os.path.basename(f) for f in glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h"))) + \
+          [os.path.join("..", "..", "include", "nbody_cuda.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v"] + os.environ.get("NBODY_BUILD_DEFS", "").split()

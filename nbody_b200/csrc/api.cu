@@ -22,6 +22,8 @@ int comm_all_max(Sim& s, float* value);             // comm.cu
 int comm_wait_velocities(Sim& s);                   // comm.cu
 float next_time_step(const nbody_cuda_config& cfg, float acc_max);  // checkpoint.cu
 void comm_adopt_partition(Sim& s);                  // comm.cu
+void let_destroy(Sim& s);                           // let.cu
+int let_step(Sim& s);                               // let.cu
 
 namespace {
 
@@ -38,24 +40,30 @@ void dev_free(Sim& s, T*& p, size_t count) {
 	if (p) { cudaFree(p); s.device_bytes -= std::max<size_t>(count, 1) * sizeof(T); p = nullptr; }
 }
 
-int alloc_nodes(Sim& s, uint32_t max_nodes) {
+// Source-side arrays (geometry, child / count record, first particle, multipole: what a node is read for as a SOURCE) have room for
+// `src_nodes` >= max_nodes entries: in partitioned mode the other ranks' trees are imported behind the own tree. Everything a node
+// carries as a TARGET (local expansion, list heads, parent, key) exists for the own tree only.
+int alloc_nodes(Sim& s, uint32_t max_nodes, uint32_t src_nodes) {
+	if (src_nodes < max_nodes) src_nodes = max_nodes;
 	s.max_nodes = max_nodes;
+	s.src_nodes = src_nodes;
 	int rc;
-	if ((rc = dev_alloc(s, s.geom, max_nodes))) return rc;
-	if ((rc = dev_alloc(s, s.info, max_nodes))) return rc;
-	if ((rc = dev_alloc(s, s.nbegin, max_nodes))) return rc;
+	if ((rc = dev_alloc(s, s.geom, src_nodes))) return rc;
+	if ((rc = dev_alloc(s, s.info, src_nodes))) return rc;
+	if ((rc = dev_alloc(s, s.nbegin, src_nodes))) return rc;
+	if ((rc = dev_alloc(s, s.M, (size_t) src_nodes * s.nc_stride))) return rc;
 	if ((rc = dev_alloc(s, s.nparent, max_nodes))) return rc;
 	if ((rc = dev_alloc(s, s.nkey, max_nodes))) return rc;
-	if ((rc = dev_alloc(s, s.M, (size_t) max_nodes * s.nc_stride))) return rc;
 	if ((rc = dev_alloc(s, s.L, (size_t) max_nodes * s.nc_stride))) return rc;
 	if ((rc = dev_alloc(s, s.near_ref, max_nodes))) return rc;
 	if ((rc = dev_alloc(s, s.p2p_head, max_nodes))) return rc;
 	return NBODY_OK;
 }
 void free_nodes(Sim& s) {
-	const size_t m = s.max_nodes;
-	dev_free(s, s.geom, m); dev_free(s, s.info, m); dev_free(s, s.nbegin, m); dev_free(s, s.nparent, m); dev_free(s, s.nkey, m);
-	dev_free(s, s.M, m * s.nc_stride); dev_free(s, s.L, m * s.nc_stride); dev_free(s, s.near_ref, m); dev_free(s, s.p2p_head, m);
+	const size_t m = s.max_nodes, sn = s.src_nodes;
+	dev_free(s, s.geom, sn); dev_free(s, s.info, sn); dev_free(s, s.nbegin, sn); dev_free(s, s.M, sn * s.nc_stride);
+	dev_free(s, s.nparent, m); dev_free(s, s.nkey, m);
+	dev_free(s, s.L, m * s.nc_stride); dev_free(s, s.near_ref, m); dev_free(s, s.p2p_head, m);
 }
 
 struct PoolPlan { uint64_t near, p2p, m2l; uint32_t seg, gq, items; };
@@ -92,13 +100,14 @@ void free_all(Sim* s) {
 	if (!s) return;
 	cudaSetDevice(s->device);
 	comm_destroy(*s);
+	let_destroy(*s);
 	for (int k = 0; k < 2; ++k) {
-		dev_free(*s, s->posq[k], s->n); dev_free(*s, s->velm[k], s->n); dev_free(*s, s->orig[k], s->n);
-		dev_free(*s, s->keys[k], s->n); dev_free(*s, s->idx[k], s->n);
+		dev_free(*s, s->posq[k], k == 1 ? s->src_cap : s->cap); dev_free(*s, s->velm[k], s->cap); dev_free(*s, s->orig[k], s->cap);
+		dev_free(*s, s->keys[k], s->cap); dev_free(*s, s->idx[k], s->cap);
 	}
-	dev_free(*s, s->acc, s->n);
+	dev_free(*s, s->acc, s->cap);
 	if (s->sort_tmp) { cudaFree(s->sort_tmp); s->sort_tmp = nullptr; }
-	dev_free(*s, s->aos_dev, s->n);
+	dev_free(*s, s->aos_dev, s->cap);
 	dev_free(*s, s->scan_sums, (size_t) kScanBlocks + 1);
 	free_nodes(*s);
 	free_pools(*s);
@@ -185,11 +194,13 @@ int grow_after_overflow(Sim& s, uint32_t status) {
 	const double g = 1.6;
 	if (status & kOvfNodes) {
 		const uint32_t want = (uint32_t) clamp32((double) s.max_nodes * g + 1024);
+		const uint32_t extra = s.src_nodes - s.max_nodes;  // partitioned mode: keep the room for the imported trees
 		free_nodes(s);
-		int rc = alloc_nodes(s, want);
+		int rc = alloc_nodes(s, want, (uint32_t) clamp32((double) want + extra));
 		if (rc) return rc;
 	}
-	if (status & ~kOvfNodes) {
+	if (status & kOvfDepth) s.depth_bound = s.trav_bound = kMaxDepth;  // the tree outgrew last step's depth + 1: unbounded level loops
+	if (status & ~(kOvfNodes | kOvfDepth)) {
 		PoolPlan pl = current_plan(s);
 		if (status & kOvfNear) pl.near = clamp32((double) pl.near * g);
 		if (status & kOvfP2P) pl.p2p = clamp32((double) pl.p2p * g);
@@ -209,7 +220,10 @@ int grow_after_overflow(Sim& s, uint32_t status) {
 	return NBODY_OK;
 }
 
-int create_common(const nbody_cuda_config* cfg, uint64_t n, Sim** out) {
+// `cap` >= n: allocated length of the per-particle arrays; `halo`: extra room behind posq[1] (both only differ from n / 0 in
+// partitioned mode, where a rank's particle count changes from step to step and the sources include other ranks' particles).
+int create_common(const nbody_cuda_config* cfg, uint64_t n, Sim** out, uint64_t cap = 0, uint64_t halo = 0) {
+	if (cap < n) cap = n;
 	int rc = validate(cfg, n);
 	if (rc) return rc;
 	int ndev = 0;
@@ -227,19 +241,19 @@ int create_common(const nbody_cuda_config* cfg, uint64_t n, Sim** out) {
 	cudaDeviceProp prop{};
 	cudaGetDeviceProperties(&prop, s->device);
 	if (prop.major < 10) { set_error(std::string("device '") + prop.name + "' is not sm_100: this library is built for B200 only"); return fail(NBODY_ERR_CUDA); }
-	s->n = n;
+	s->n = n; s->cap = cap; s->src_cap = cap + halo; s->n_global = n;
 	s->own_first = 0; s->own_count = n;
 	s->nc_stride = coef_stride((int) s->cfg.order);
 	if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream creation failed"); return fail(NBODY_ERR_CUDA); }
 	for (auto& e : s->ev) if (cudaEventCreate(&e) != cudaSuccess) { set_error("event creation failed"); return fail(NBODY_ERR_CUDA); }
 	for (int k = 0; k < 2; ++k) {
-		if ((rc = dev_alloc(*s, s->posq[k], n)) || (rc = dev_alloc(*s, s->velm[k], n)) || (rc = dev_alloc(*s, s->orig[k], n)) ||
-		    (rc = dev_alloc(*s, s->keys[k], n)) || (rc = dev_alloc(*s, s->idx[k], n)))
+		if ((rc = dev_alloc(*s, s->posq[k], k == 1 ? s->src_cap : cap)) || (rc = dev_alloc(*s, s->velm[k], cap)) || (rc = dev_alloc(*s, s->orig[k], cap)) ||
+		    (rc = dev_alloc(*s, s->keys[k], cap)) || (rc = dev_alloc(*s, s->idx[k], cap)))
 			return fail(rc);
 	}
-	if ((rc = dev_alloc(*s, s->acc, n)) || (rc = dev_alloc(*s, s->aos_dev, n)) || (rc = dev_alloc(*s, s->scan_sums, (size_t) kScanBlocks + 1)))
+	if ((rc = dev_alloc(*s, s->acc, cap)) || (rc = dev_alloc(*s, s->aos_dev, cap)) || (rc = dev_alloc(*s, s->scan_sums, (size_t) kScanBlocks + 1)))
 		return fail(rc);
-	s->sort_tmp_bytes = sort_temp_bytes(n);
+	s->sort_tmp_bytes = sort_temp_bytes(cap);
 	if (cudaMalloc(&s->sort_tmp, std::max<size_t>(s->sort_tmp_bytes, 16)) != cudaSuccess) { set_error("sort scratch allocation failed"); return fail(NBODY_ERR_CUDA); }
 	s->device_bytes += s->sort_tmp_bytes;
 	if (cudaMalloc((void**) &s->ctrl, sizeof(Ctrl)) != cudaSuccess || cudaMallocHost((void**) &s->ctrl_host, sizeof(Ctrl)) != cudaSuccess) {
@@ -247,10 +261,11 @@ int create_common(const nbody_cuda_config* cfg, uint64_t n, Sim** out) {
 		return fail(NBODY_ERR_CUDA);
 	}
 	std::memset(s->ctrl_host, 0, sizeof(Ctrl));
-	const double sc = s->cfg.pool_scale, dn = (double) n;
+	const double sc = s->cfg.pool_scale, dn = (double) cap;
 	// node budget: ~0.35-0.6 nodes per particle at capacity 8 (measured with the oracle); fewer for larger leaves
 	const double per_particle = std::min(1.25, 10.0 / (double) s->cfg.leaf_capacity);
-	if ((rc = alloc_nodes(*s, (uint32_t) clamp32(sc * (per_particle * dn + 65536))))) return fail(rc);
+	const uint32_t nodes0 = (uint32_t) clamp32(sc * (per_particle * dn + 65536));
+	if ((rc = alloc_nodes(*s, nodes0, nodes0))) return fail(rc);
 	PoolPlan pl;
 	pl.near = clamp32(sc * (128.0 * dn * std::min(1.0, 16.0 / s->cfg.leaf_capacity) + 1048576));
 	pl.p2p = clamp32(sc * (96.0 * dn * std::min(1.0, 16.0 / s->cfg.leaf_capacity) + 1048576));
@@ -351,7 +366,7 @@ int nbody_cuda_set_particles(nbody_cuda_sim* sim, const nbody_particle* particle
 	Sim* s = reinterpret_cast<Sim*>(sim);
 	if (!s || !particles) { set_error("NULL argument"); return NBODY_ERR_INVALID; }
 	if (n != s->n) { set_error("set_particles: particle count differs from the simulation's"); return NBODY_ERR_INVALID; }
-	if (s->comm) { set_error("set_particles is not available on a distributed simulation"); return NBODY_ERR_STATE; }
+	if (s->comm || s->let) { set_error("set_particles is not available on a distributed simulation"); return NBODY_ERR_STATE; }
 	NB_CUDA_CHECK(cudaSetDevice(s->device));
 	return upload(*s, particles, n);
 }
@@ -360,6 +375,11 @@ int nbody_cuda_step(nbody_cuda_sim* sim, float* time_out) {
 	Sim* s = reinterpret_cast<Sim*>(sim);
 	if (!s) { set_error("NULL simulation"); return NBODY_ERR_INVALID; }
 	NB_CUDA_CHECK(cudaSetDevice(s->device));
+	if (s->let) {  // partitioned mode: own particles + locally essential tree (let.cu)
+		const int rc = let_step(*s);
+		if (rc == NBODY_OK && time_out) *time_out = s->time;
+		return rc;
+	}
 	s->stats.retries = 0;
 	for (int attempt = 0;; ++attempt) {
 		int rc = run_pipeline(*s, attempt > 0);
@@ -373,6 +393,8 @@ int nbody_cuda_step(nbody_cuda_sim* sim, float* time_out) {
 	std::swap(s->orig[0], s->orig[1]);
 	s->time += s->dt;  // FP32 accumulation like src/open_cl_simulation.cpp:103
 	++s->steps_done;
+	// next step's level loops: one level deeper than this step's tree at most (kOvfDepth re-runs unbounded)
+	s->depth_bound = s->trav_bound = std::min<int>((int) s->cfg.max_depth, (int) s->ctrl_host->n_levels);
 	s->dt_last = s->dt;
 	if (s->cfg.time_step_eta > 0.0f) {
 		// variable time step: this step's largest acceleration sets the next step (rule in nbody_cuda_next_time_step)
@@ -612,7 +634,8 @@ int nbody_cuda_get_owned_particles(nbody_cuda_sim* sim, nbody_particle* out, uin
 	NB_CUDA_CHECK(cudaSetDevice(s->device));
 	if (s->comm) { int rc = comm_wait_velocities(*s); if (rc) return rc; }
 	launch_export(*s, s->aos_dev, s->n);
-	NB_CUDA_CHECK(cudaMemcpyAsync(out, s->aos_dev + s->own_first, s->own_count * sizeof(nbody_particle), cudaMemcpyDeviceToHost, s->stream));
+	const uint64_t first = s->let ? 0 : s->own_first;  // partitioned mode: the arrays hold the owned particles only
+	NB_CUDA_CHECK(cudaMemcpyAsync(out, s->aos_dev + first, s->own_count * sizeof(nbody_particle), cudaMemcpyDeviceToHost, s->stream));
 	NB_CUDA_CHECK(cudaStreamSynchronize(s->stream));
 	return NBODY_OK;
 }
@@ -622,6 +645,13 @@ int nbody_cuda_set_owned_particles(nbody_cuda_sim* sim, const nbody_particle* pa
 	if (!s || !particles) { set_error("NULL argument"); return NBODY_ERR_INVALID; }
 	if (n != s->own_count) { set_error("set_owned_particles: count differs from the owned range"); return NBODY_ERR_INVALID; }
 	NB_CUDA_CHECK(cudaSetDevice(s->device));
+	if (s->let) {  // partitioned mode: nothing to exchange, the rank holds exactly its own particles; identities are kept
+		NB_CUDA_CHECK(cudaMemcpyAsync(s->aos_dev, particles, n * sizeof(nbody_particle), cudaMemcpyHostToDevice, s->stream));
+		launch_import_ids(*s, s->aos_dev, n, 0u, true);
+		NB_CUDA_CHECK(cudaStreamSynchronize(s->stream));
+		NB_CUDA_CHECK(cudaGetLastError());
+		return NBODY_OK;
+	}
 	if (s->comm) { int rc = comm_wait_velocities(*s); if (rc) return rc; }  // the import below overwrites the velocity plane
 	NB_CUDA_CHECK(cudaMemcpyAsync(s->aos_dev + s->own_first, particles, n * sizeof(nbody_particle), cudaMemcpyHostToDevice, s->stream));
 	if (s->comm) { int rc = comm_exchange_aos(*s); if (rc) return rc; }
@@ -651,5 +681,8 @@ const char* nbody_cuda_last_error(void) { return g_error.c_str(); }
 // used by comm.cu
 namespace nbody {
 int create_for_comm(const nbody_cuda_config* cfg, uint64_t n, Sim** out) { return create_common(cfg, n, out); }
+int create_for_let(const nbody_cuda_config* cfg, uint64_t n, uint64_t cap, uint64_t halo, Sim** out) { return create_common(cfg, n, out, cap, halo); }
+int grow_pools_after_overflow(Sim& s, uint32_t status) { return grow_after_overflow(s, status); }
+int realloc_nodes(Sim& s, uint32_t max_nodes, uint32_t src_nodes) { free_nodes(s); return alloc_nodes(s, max_nodes, src_nodes); }
 void destroy_for_comm(Sim* s) { free_all(s); }
 }  // namespace nbody

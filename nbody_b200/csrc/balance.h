@@ -10,11 +10,17 @@
 #pragma once
 #include <cstdint>
 
+#if defined(__CUDACC__)
+#define NB_BAL_HD __host__ __device__
+#else
+#define NB_BAL_HD
+#endif
+
 namespace nbody {
 
 // part[0..world]: last step's boundaries (part[0] = 0, part[world] = n); work_ms[0..world): per-rank work time.
 // target[0..world] receives the wanted boundaries of the next step (before they are snapped to leaf boundaries).
-inline void rebalance_boundaries(int world, const uint32_t* part, const float* work_ms, float damping, uint32_t* target) {
+NB_BAL_HD inline void rebalance_boundaries(int world, const uint32_t* part, const float* work_ms, float damping, uint32_t* target) {
 	const uint32_t n = part[world];
 	target[0] = 0;
 	target[world] = n;

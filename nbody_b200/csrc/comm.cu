@@ -12,7 +12,6 @@
 // Determinism of the radix sort and of the tree build makes the replicated structures
 // bit-identical across ranks, so no tree data ever needs to travel.
 #include <dlfcn.h>
-#include <nccl.h>  // types and enums only: the library itself is bound at run time (see NcclApi)
 
 #include <cstdlib>
 #include <cstring>
@@ -20,28 +19,13 @@
 
 #include "balance.h"
 #include "common.cuh"
+#include "nccl_api.h"
 
 namespace nbody {
 
-// NCCL is resolved with dlopen at the first distributed call instead of being a link-time
-// dependency: a host process that also runs PyTorch already carries its own libnccl.so.2
-// (a newer one than the system's), and two copies of one SONAME cannot coexist. RTLD_NOLOAD
-// first re-uses whatever the process has loaded; a single-GPU run never touches NCCL at all.
-struct NcclApi {
-	ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
-	ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
-	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
-	ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t*, void*) = nullptr;  // optional (NCCL >= 2.18); last argument: ncclConfig_t*
-	ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
-	ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
-	ncclResult_t (*GroupStart)() = nullptr;
-	ncclResult_t (*GroupEnd)() = nullptr;
-	const char* (*GetErrorString)(ncclResult_t) = nullptr;
-	bool ok = false;
-};
-static NcclApi g_nccl;
+NcclApi g_nccl;
 
-static bool nccl_load() {
+bool nccl_load() {
 	if (g_nccl.ok) return true;
 	void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
 	if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
@@ -64,6 +48,8 @@ static bool nccl_load() {
 }
 
 int create_for_comm(const nbody_cuda_config* cfg, uint64_t n, Sim** out);
+int let_create_distributed(const nbody_cuda_config* cfg, const nbody_particle* local_particles, uint64_t n_local, uint64_t n_global,
+                           uint64_t global_offset, int rank, int world, const uint8_t* id, nbody_cuda_sim** out);  // let.cu
 int comm_wait_velocities(Sim& s);
 void destroy_for_comm(Sim* s);
 
@@ -84,16 +70,8 @@ struct Comm {
 	bool pos_pending = false;       // the same for a position exchange on the second stream (only with vel_comm)
 };
 
-struct PartitionTargets { uint32_t t[17]; };
+struct PartitionTargets { uint32_t t[kMaxRanks + 1]; };
 
-#define NB_NCCL_CHECK(expr)                                                                  \
-	do {                                                                                        \
-		ncclResult_t _r = (expr);                                                                 \
-		if (_r != ncclSuccess) {                                                                  \
-			set_error(std::string(#expr) + ": " + g_nccl.GetErrorString(_r));                          \
-			return NBODY_ERR_COMM;                                                                  \
-		}                                                                                         \
-	} while (0)
 
 // Boundary r = the wanted position, moved down to the first particle of the leaf that contains it.
 __global__ void k_partition(Ctrl* c, int world, uint32_t n, const PartitionTargets want, const uint2* __restrict__ info,
@@ -319,6 +297,8 @@ int nbody_cuda_create_distributed(const nbody_cuda_config* cfg, const nbody_part
 	if (world < 1 || world > 16 || rank < 0 || rank >= world) { set_error("bad rank / world size (1..16 ranks)"); return NBODY_ERR_INVALID; }
 	if (global_offset + n_local > n_global) { set_error("local slice exceeds the global particle count"); return NBODY_ERR_INVALID; }
 	if (!nccl_load()) return NBODY_ERR_COMM;
+	if (cfg && (cfg->flags & NBODY_FLAG_PARTITIONED))
+		return let_create_distributed(cfg, local_particles, n_local, n_global, global_offset, rank, world, id, out);
 	Sim* s = nullptr;
 	int rc = create_for_comm(cfg, n_global, &s);
 	if (rc) return rc;

@@ -18,8 +18,11 @@ constexpr int kScanBlocks = 592;        // 4 * 148 tiles per level scan (<= 1024
 
 // status bits raised by kernels when a pool is too small; the host grows the pool and re-runs the step
 enum : uint32_t {
-	kOvfNodes = 1u, kOvfNear = 2u, kOvfP2P = 4u, kOvfM2L = 8u, kOvfSeg = 16u, kOvfGroups = 32u, kOvfItems = 64u
+	kOvfNodes = 1u, kOvfNear = 2u, kOvfP2P = 4u, kOvfM2L = 8u, kOvfSeg = 16u, kOvfGroups = 32u, kOvfItems = 64u,
+	kOvfDepth = 128u,  // the tree wanted to grow below the depth the level loops were bounded to (last step's depth + 1): re-run unbounded
+	kOvfHalo = 256u    // partitioned mode: the halo particles do not fit behind the own particles
 };
+constexpr int kMaxRanks = 16;
 
 // One work item of the traversal / of the M2L kernel: `nt` sibling targets
 // (8 = the children of one parent, 1 = a carried childless node) that share one
@@ -33,7 +36,8 @@ struct Group {
 	uint32_t _pad[3];
 };
 
-struct Segment { uint32_t off, cnt, next; };  // one piece of a target leaf's P2P source list (chained)
+struct Segment { uint32_t off, cnt, next; };
+struct TraverseSeeds { uint32_t n = 1; uint32_t id[16] = {}; };  // source roots of the traversal: the own root (0), then the imported trees' roots  // one piece of a target leaf's P2P source list (chained)
 
 // Device-resident control block: everything the host would otherwise have to read back between launches.
 struct Ctrl {
@@ -51,7 +55,7 @@ struct Ctrl {
 	unsigned long long m2l_cursor;
 	unsigned long long stat_m2l_inter, stat_m2l_low, stat_p2p_entries, stat_p2p_inter, stat_near, stat_leaves;
 	uint32_t work_ticket[4];             // dynamic work distribution of the persistent kernels
-	uint32_t part[17];                   // distributed: rank r owns particles [part[r], part[r+1]) of the tree-ordered array
+	uint32_t part[kMaxRanks + 1];        // distributed: rank r owns particles [part[r], part[r+1]) of the tree-ordered array
 	uint32_t acc_max2_bits;              // variable time step: bits of max |a|^2 over this rank's slice (k_acc_max; non-negative floats order like uints)
 };
 
@@ -73,12 +77,30 @@ struct Pools {
 };
 
 struct Comm;  // NCCL state (comm.cu)
+struct Let;   // partitioned mode: own particles + locally essential tree (let.cu)
+
+// Partitioned mode, device side. Rank r owns the particles whose Morton key lies in [split[r], split[r+1]).
+// A cell that contains a splitter strictly inside its key range holds particles of several ranks ("straddling" cell; at most one
+// per splitter and level): whether it splits is decided by its GLOBAL particle count, so that every rank's tree is the global
+// octree restricted to the cells that hold its own particles.
+struct LetCtrl {
+	uint64_t split[kMaxRanks + 1];               // split[0] = 0, split[world] = 2^63
+	uint32_t force[kMaxRanks][kNumLevels];       // [b][d]: global particle count of the depth-d cell that straddles splitter b (0: none)
+	int world, rank;
+	uint32_t imp_base;                           // node id of the first imported node (= the own tree's capacity)
+	uint32_t imp_off[kMaxRanks + 1];             // imported tree of rank s occupies node ids [imp_base + imp_off[s], imp_base + imp_off[s+1])
+	uint32_t halo_base, halo_cap, halo_count;    // halo particles live at posq[1][halo_base ...)
+	unsigned long long t_begin, t_end;           // %globaltimer around the stages whose cost follows the partition (rebalancing input)
+};
 
 struct Sim {
 	nbody_cuda_config cfg;
 	int device = 0;
 	cudaStream_t stream = nullptr;
-	uint64_t n = 0;
+	uint64_t n = 0;           // particles this object holds (partitioned mode: the rank's own particles in the current step)
+	uint64_t cap = 0;         // allocated length of the per-particle arrays (= n except in partitioned mode, where n varies)
+	uint64_t src_cap = 0;     // allocated length of posq[1] (partitioned mode: cap + room for the halo particles)
+	uint64_t n_global = 0;
 	float time = 0.0f;
 	uint64_t steps_done = 0;  // steps taken by this object (0 = no tree, lists or accelerations yet)
 	uint64_t steps_base = 0;  // steps taken before the checkpoint this object was loaded from
@@ -100,7 +122,12 @@ struct Sim {
 	nbody_particle* aos_host = nullptr;    // pinned
 
 	// octree, level-major; the 8 children of a split node are contiguous
-	uint32_t max_nodes = 0;
+	uint32_t max_nodes = 0;      // capacity of the own tree
+	uint32_t src_nodes = 0;      // allocated length of the source-side arrays geom / info / nbegin / M (>= max_nodes; partitioned mode:
+	                             // the other ranks' trees are imported at ids [max_nodes, src_nodes))
+	int depth_bound = kMaxDepth; // the level loops of a step run to this depth (last step's depth + 1; kOvfDepth re-runs unbounded)
+	TraverseSeeds seeds;
+	int trav_bound = kMaxDepth;  // rounds of the traversal (partitioned mode: the deepest tree of any rank; otherwise depth_bound)
 	float4* geom = nullptr;      // centre xyz, dimensions.x
 	uint2* info = nullptr;       // {first child (0 = childless), particle count}
 	uint32_t* nbegin = nullptr;  // first particle
@@ -116,6 +143,8 @@ struct Sim {
 	Ctrl* ctrl = nullptr;        // device
 	Ctrl* ctrl_host = nullptr;   // pinned copy read after each step
 	Comm* comm = nullptr;
+	Let* let = nullptr;
+	LetCtrl* let_ctrl = nullptr;   // device (nullptr unless partitioned)
 	// distributed: this rank's slice of the tree-ordered particle array
 	uint64_t own_first = 0, own_count = 0;
 	int rank = 0;                // index into Ctrl::part (0 on a single GPU)
@@ -140,6 +169,10 @@ void set_error(const std::string& msg);
 
 // ---- stage launchers (each enqueues on sim.stream; no host synchronisation) --
 void launch_import(Sim& s, const nbody_particle* aos_dev, uint64_t n);                 // AoS48 -> SoA state
+void launch_import_ids(Sim& s, const nbody_particle* aos_dev, uint64_t n, uint32_t first_id, bool keep_ids);
+void launch_keys(Sim& s, const float4* pos, uint64_t n);                               // keys[0] / idx[0] of pos[0..n)
+void launch_gather(Sim& s, uint64_t n);                                                // state [0] -> sorted [1] through idx[0]
+void launch_exclusive_scan(Sim& s, uint32_t* data, uint32_t n);                        // in place, scratch = sort_tmp (sort.cu)
 void launch_export(Sim& s, nbody_particle* aos_dev, uint64_t n);                       // SoA state -> AoS48
 int launch_keys_sort_permute(Sim& s);                                                 // stage 1a: keys, radix sort, gather
 void launch_own_sort_range(Sim& s, uint64_t first, uint64_t n);                        // the radix sort over a sub-range of keys[0] / idx[0]

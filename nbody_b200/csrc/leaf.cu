@@ -46,12 +46,13 @@ __device__ __forceinline__ void leaf_cp_async_commit() { asm volatile("cp.async.
 __device__ __forceinline__ void leaf_cp_async_wait1() { asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
 __device__ __forceinline__ void leaf_cp_async_wait0() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
-// ---- experimental tile fill with TMA 1-D bulk copies (build with -DNBODY_LEAF_BULK=1; NOT the default, not yet run on hardware) ----
+// ---- tile fill with TMA 1-D bulk copies (default; -DNBODY_LEAF_BULK=0 builds the cp.async row fill it replaced, for A/B runs) ----
 // One cp.async.bulk per contiguous run of source particles (adjacent list entries are merged: 57 particles = 910 B per run on the
 // Plummer benchmark, tests/tools/p2p_list_structure.py) with completion on a per-warp, per-buffer mbarrier, instead of eight rows of
-// per-lane 16-byte cp.async copies driven by a flat-slot -> entry bitmap. DESIGN.md section 10 has the instruction budget.
+// per-lane 16-byte cp.async copies driven by a flat-slot -> entry bitmap. Measured (profiles/r02a_call.log, Plummer 2^24, capacity 48):
+// leaf kernel 38.41 -> 35.12 ms, 41.4 -> 45.3 % of the FP32 FMA peak, parity suite green.
 #ifndef NBODY_LEAF_BULK
-#define NBODY_LEAF_BULK 0
+#define NBODY_LEAF_BULK 1
 #endif
 __device__ __forceinline__ unsigned leaf_smem_addr(const void* p) { return (unsigned) __cvta_generic_to_shared(p); }
 __device__ __forceinline__ void leaf_mbar_init(uint64_t* bar, unsigned count) {
@@ -214,7 +215,9 @@ __global__ void __launch_bounds__(kLeafWarps * 32, kLeafMinCtas) k_leaf(const Le
 			const uint32_t nblk = (nt + kLeafG - 1) / kLeafG, gmax = (nt + nblk - 1) / nblk;  // even blocks of <= kLeafG targets
 #pragma unroll 1
 			for (uint32_t t0 = 0; t0 < nt; t0 += gmax) {
-				const unsigned G = min(gmax, nt - t0);
+				// (a warp reduction leaves G in a uniform register: the per-target guards of tile_rows become uniform branches without
+				//  reconvergence barriers; ptxas cannot know that a value that came through a shuffle is the same in every lane)
+				const unsigned G = __reduce_min_sync(0xffffffffu, min(gmax, nt - t0));
 				__syncwarp();
 				if (lane < G) stgt[w][lane] = a.posq[b + t0 + lane];
 				float ax[16], ay[16], az[16];
@@ -446,9 +449,10 @@ int direct_field_device(const float4* src, uint64_t n_src, const float4* tgt, ui
 	return NBODY_OK;
 }
 
-__global__ void k_direct_finish(uint64_t n, const float4* __restrict__ field, const float4* __restrict__ posq, const float4* __restrict__ velm,
+__global__ void k_direct_finish(const Ctrl* __restrict__ c, uint64_t n, const float4* __restrict__ field, const float4* __restrict__ posq, const float4* __restrict__ velm,
                                 float4* __restrict__ posq_out, float4* __restrict__ velm_out, float4* __restrict__ acc, float G, float dt,
                                 int integrator, int no_integrate) {
+	if (c->status) return;  // a pool overflowed (the tree build's node pool): the host grows it and re-runs the step from the untouched state
 	for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
 		const float4 f = field[i], p = posq[i], vm = velm[i];
 		const float sc = G * p.w / vm.w;
@@ -470,7 +474,7 @@ void launch_direct(Sim& s) {
 	direct_field_device(s.posq[1], s.n, s.posq[1], s.n, eps2, field, s.stream);
 	const uint64_t want = (s.n + 255) / 256;
 	k_direct_finish<<<(unsigned) (want > kNumSM * 16 ? kNumSM * 16 : (want ? want : 1)), 256, 0, s.stream>>>(
-	    s.n, field, s.posq[1], s.velm[1], s.posq[0], s.velm[0], s.acc, s.cfg.force_constant, s.dt, (int) s.cfg.integrator,
+	    s.ctrl, s.n, field, s.posq[1], s.velm[1], s.posq[0], s.velm[0], s.acc, s.cfg.force_constant, s.dt, (int) s.cfg.integrator,
 	    (s.cfg.flags & NBODY_FLAG_NO_INTEGRATE) ? 1 : 0);
 }
 

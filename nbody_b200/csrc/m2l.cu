@@ -277,7 +277,7 @@ static void m2l_t(Sim& s) {
 }
 template <int P>
 static void l2l_t(Sim& s) {
-	for (int l = 1; l <= (int) s.cfg.max_depth; ++l)
+	for (int l = 1; l <= (s.depth_bound < (int) s.cfg.max_depth ? s.depth_bound : (int) s.cfg.max_depth); ++l)
 		k_l2l<P><<<kNumSM * 4, 128, 0, s.stream>>>(s.ctrl, l, s.geom, s.info, s.nparent, s.nbegin, s.rank, s.L);
 }
 

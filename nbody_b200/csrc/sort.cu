@@ -211,6 +211,16 @@ void launch_own_sort_range(Sim& s, uint64_t first, uint64_t n) {
 
 void launch_own_sort(Sim& s) { launch_own_sort_range(s, 0, s.n); }
 
+// Exclusive scan of data[0..n) in place (three launches); the scratch is the radix sort's histogram area, free outside the sort.
+void launch_exclusive_scan(Sim& s, uint32_t* data, uint32_t n) {
+	if (n == 0) return;
+	const uint32_t nsums = (n + kScanTile - 1) / kScanTile;
+	uint32_t* sums = static_cast<uint32_t*>(s.sort_tmp);
+	k_scan_sums<<<nsums, 256, 0, s.stream>>>(n, data, sums);
+	k_scan_top<<<1, 256, 0, s.stream>>>(nsums, sums);
+	k_scan_apply<<<nsums, 256, 0, s.stream>>>(n, data, sums);
+}
+
 // ---- distributed sort (NBODY_FLAG_DIST_SORT): pairwise stable merges of the all-gathered, slice-wise sorted runs ----
 // merge_path.h has the plan and the index arithmetic (checked on the CPU by tests/test_merge_host.py). Two kernels per round:
 // k_merge_partition finds every tile's split point with one merge-path search in global memory per thread (all tiles at once: one

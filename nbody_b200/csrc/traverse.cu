@@ -57,16 +57,21 @@ __device__ __forceinline__ unsigned mac_classify(float ax, float ay, float az, f
 	return accept ? (ext2 < __fmul_rn(tau, d2) ? 2u : 1u) : 0u;
 }
 
-__global__ void k_traverse_init(Ctrl* c, const uint2* __restrict__ info, uint32_t* near0, Group* q1) {
+// Seeds of the traversal: near(root) = {root}, the reference's seed interaction {0,0}. Partitioned mode: the roots of the other
+// ranks' imported trees as well — every rank's tree is the global octree restricted to its own particles, so the own targets
+// against each of these source trees together cover the global recursion exactly once (let.cu).
+__global__ void k_traverse_init(Ctrl* c, const uint2* __restrict__ info, uint32_t* near0, Group* q1, const TraverseSeeds seeds) {
 	if (threadIdx.x == 0 && blockIdx.x == 0) {
-		near0[0] = 0;  // near(root) = {root}: the reference's seed interaction {0,0}
-		c->near_cursor[0] = 1;
+		uint32_t ncand = 0;
+		for (uint32_t k = 0; k < seeds.n; ++k) { near0[k] = seeds.id[k]; ncand += info[seeds.id[k]].x ? 8u : 1u; }
+		c->near_cursor[0] = seeds.n;
 		c->near_cursor[1] = 0;
 		const uint2 r = info[0];
 		Group g{};
-		if (r.x) { g.first = r.x; g.nt = 8; g.n_cand = 8; }
-		else { g.first = 0; g.nt = 1; g.n_cand = 1; }
-		g.list_off = 0; g.list_cnt = 1;
+		if (r.x) { g.first = r.x; g.nt = 8; }
+		else { g.first = 0; g.nt = 1; }
+		g.n_cand = ncand;
+		g.list_off = 0; g.list_cnt = seeds.n;
 		q1[0] = g;
 		c->gq_count[1] = r.y ? 1u : 0u;
 		c->gq_count[0] = 0;
@@ -363,7 +368,7 @@ void launch_traversal(Sim& s) {
 	const bool quarter = s.cfg.mac_ratio * s.cfg.mac_ratio == 0.25f;
 	cudaFuncSetAttribute(k_traverse<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(TravSmem));
 	cudaFuncSetAttribute(k_traverse<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(TravSmem));
-	k_traverse_init<<<1, 32, 0, s.stream>>>(s.ctrl, s.info, p.near[0], p.gq[1]);
+	k_traverse_init<<<1, 32, 0, s.stream>>>(s.ctrl, s.info, p.near[0], p.gq[1], s.seeds);
 	TraverseArgs a{};
 	a.c = s.ctrl; a.geom = s.geom; a.info = s.info; a.near_ref = s.near_ref; a.p2p_head = s.p2p_head;
 	a.nbegin = s.nbegin; a.rank = s.rank;
@@ -371,7 +376,8 @@ void launch_traversal(Sim& s) {
 	a.seg = p.seg; a.seg_cap = p.seg_cap; a.gq_cap = p.gq_cap; a.items8 = p.items[0]; a.items1 = p.items[1]; a.items_cap = p.items_cap;
 	a.ratio_sq = s.cfg.mac_ratio * s.cfg.mac_ratio;
 	a.tau = s.cfg.order >= 3 ? s.cfg.low_order_tau : 0.0f;  // order P-1 >= 2 only
-	for (int r = 1; r <= (int) s.cfg.max_depth; ++r) {
+	const int rounds = s.trav_bound < (int) s.cfg.max_depth ? s.trav_bound : (int) s.cfg.max_depth;
+	for (int r = 1; r <= rounds; ++r) {
 		k_round_prep<<<1, 32, 0, s.stream>>>(s.ctrl, r);
 		a.round = r;
 		a.near_in = p.near[(r - 1) & 1];

@@ -18,12 +18,12 @@ namespace nbody {
 // AoS48 boundary records <-> SoA float4 planes
 // ---------------------------------------------------------------------------
 __global__ void k_import(uint64_t n, const float4* __restrict__ aos, float4* __restrict__ posq, float4* __restrict__ velm,
-                         uint32_t* __restrict__ orig) {
+                         uint32_t* __restrict__ orig, uint32_t first_id) {
 	for (uint64_t i = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; i < n; i += (uint64_t) gridDim.x * blockDim.x) {
 		const float4 p = aos[3 * i], v = aos[3 * i + 1], mq = aos[3 * i + 2];
 		posq[i] = make_float4(p.x, p.y, p.z, mq.y);
 		velm[i] = make_float4(v.x, v.y, v.z, mq.x);
-		orig[i] = (uint32_t) i;
+		if (orig) orig[i] = first_id + (uint32_t) i;
 	}
 }
 __global__ void k_export(uint64_t n, float4* __restrict__ aos, const float4* __restrict__ posq, const float4* __restrict__ velm) {
@@ -34,13 +34,27 @@ __global__ void k_export(uint64_t n, float4* __restrict__ aos, const float4* __r
 		aos[3 * i + 2] = make_float4(v.w, p.w, 0.0f, 0.0f);
 	}
 }
+__global__ void k_keys(uint64_t n, const float4* __restrict__ posq, float sx, float sy, float sz, uint64_t* __restrict__ keys, uint32_t* __restrict__ idx);
+__global__ void k_gather(uint64_t n, const uint32_t* __restrict__ idx, const float4* __restrict__ posq_in, const float4* __restrict__ velm_in,
+                         const uint32_t* __restrict__ orig_in, float4* __restrict__ posq_out, float4* __restrict__ velm_out, uint32_t* __restrict__ orig_out);
 static inline int grid_for(uint64_t n, int block) {
 	const uint64_t want = (n + block - 1) / block;
 	const uint64_t cap = (uint64_t) kNumSM * 16;
 	return (int) (want < 1 ? 1 : (want > cap ? cap : want));
 }
 void launch_import(Sim& s, const nbody_particle* aos_dev, uint64_t n) {
-	k_import<<<grid_for(n, 256), 256, 0, s.stream>>>(n, (const float4*) aos_dev, s.posq[0], s.velm[0], s.orig[0]);
+	k_import<<<grid_for(n, 256), 256, 0, s.stream>>>(n, (const float4*) aos_dev, s.posq[0], s.velm[0], s.orig[0], 0u);
+}
+// partitioned mode: identities start at `first_id` (the rank's offset into the constructor's global array); keep_ids leaves orig alone
+void launch_import_ids(Sim& s, const nbody_particle* aos_dev, uint64_t n, uint32_t first_id, bool keep_ids) {
+	k_import<<<grid_for(n, 256), 256, 0, s.stream>>>(n, (const float4*) aos_dev, s.posq[0], s.velm[0], keep_ids ? nullptr : s.orig[0], first_id);
+}
+void launch_keys(Sim& s, const float4* pos, uint64_t n) {  // keys[0] = Morton keys of pos[0..n), idx[0] = 0..n-1
+	const float sx = 2097152.0f / s.cfg.bounds[0], sy = 2097152.0f / s.cfg.bounds[1], sz = 2097152.0f / s.cfg.bounds[2];
+	if (n) k_keys<<<grid_for(n, 256), 256, 0, s.stream>>>(n, pos, sx, sy, sz, s.keys[0], s.idx[0]);
+}
+void launch_gather(Sim& s, uint64_t n) {  // (posq, velm, orig)[1][i] = (posq, velm, orig)[0][idx[0][i]]
+	if (n) k_gather<<<grid_for(n, 256), 256, 0, s.stream>>>(n, s.idx[0], s.posq[0], s.velm[0], s.orig[0], s.posq[1], s.velm[1], s.orig[1]);
 }
 void launch_export(Sim& s, nbody_particle* aos_dev, uint64_t n) {
 	k_export<<<grid_for(n, 256), 256, 0, s.stream>>>(n, (float4*) aos_dev, s.posq[0], s.velm[0]);
@@ -144,7 +158,7 @@ int launch_keys_sort_permute(Sim& s) {
 		comm_own_slice(s, &first, &count);
 		if (count) k_keys_range<<<grid_for(count, 256), 256, 0, s.stream>>>(first, count, s.posq[0], sx, sy, sz, s.keys[0], s.idx[0]);
 		launch_own_sort_range(s, first, count);
-		uint32_t bound[17];
+		uint32_t bound[kMaxRanks + 1];
 		int nruns = 0;
 		const int rc = comm_sort_exchange(s, bound, &nruns);
 		if (rc) return rc;
@@ -186,7 +200,7 @@ __global__ void k_tree_init(Ctrl* c, uint32_t n, float bx, float by, float bz, f
 		for (int k = 0; k < 4; ++k) c->work_ticket[k] = 0;
 		c->acc_max2_bits = 0;
 		c->part[0] = 0;
-		for (int k = 1; k < 17; ++k) c->part[k] = n;  // single GPU: rank 0 owns everything (k_partition overwrites this)
+		for (int k = 1; k <= kMaxRanks; ++k) c->part[k] = n;  // single GPU: rank 0 owns everything (k_partition overwrites this)
 		geom[0] = make_float4(__fadd_rn(__fmul_rn(0.0f, bx), __fmul_rn(bx, 0.5f)), __fadd_rn(__fmul_rn(0.0f, by), __fmul_rn(by, 0.5f)),
 		                      __fadd_rn(__fmul_rn(0.0f, bz), __fmul_rn(bz, 0.5f)), bx);
 		info[0] = make_uint2(0u, n);
@@ -220,11 +234,25 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* w
 	return base + inc - v;
 }
 
+// Does a node of level `l` with `count` particles and key prefix `key` split? More than `cap` particles — or, in partitioned mode, a
+// cell that holds particles of several ranks (it contains a splitter key strictly inside its key range) whose GLOBAL count exceeds
+// cap (LetCtrl::force, summed over the ranks before the build): every rank's tree is then the global octree restricted to the
+// cells that hold its own particles.
+__device__ __forceinline__ bool node_splits(uint32_t count, uint32_t cap, uint64_t key, int l, const LetCtrl* __restrict__ lc) {
+	if (count > cap) return true;
+	if (lc == nullptr || count == 0u) return false;
+	const int sh = 3 * (kMaxDepth - l);
+	for (int b = 1; b < lc->world; ++b)
+		if (lc->force[b][l] > cap && (lc->split[b] >> sh) == (key >> sh)) return true;
+	return false;
+}
+
 // Pass A of level `l`: count the nodes that split in each tile; the last block to finish
 // turns the tile counts into exclusive offsets (a block-wide scan) and publishes the size of level l+1.
 // A level without nodes (below the deepest one) costs one launch that only clears the split count.
 __global__ void __launch_bounds__(256) k_level_count(Ctrl* c, int l, uint32_t cap, uint32_t max_depth, uint32_t max_nodes,
-                                                      const uint2* __restrict__ info, uint32_t* scan_sums) {
+                                                      const uint2* __restrict__ info, const uint64_t* __restrict__ nkey,
+                                                      const LetCtrl* __restrict__ lc, uint32_t* scan_sums) {
 	__shared__ uint32_t warp_sums[32];
 	__shared__ bool last;
 	const uint32_t lo = c->level_off[l], hi = c->level_off[l + 1];
@@ -236,7 +264,7 @@ __global__ void __launch_bounds__(256) k_level_count(Ctrl* c, int l, uint32_t ca
 	const uint32_t tile = (nl + gridDim.x - 1) / gridDim.x;
 	const uint32_t t0 = lo + blockIdx.x * tile, t1 = min(hi, t0 + tile);
 	uint32_t cnt = 0;
-	for (uint32_t i = t0 + threadIdx.x; i < t1; i += blockDim.x) cnt += info[i].y > cap ? 1u : 0u;
+	for (uint32_t i = t0 + threadIdx.x; i < t1; i += blockDim.x) cnt += node_splits(info[i].y, cap, lc ? nkey[i] : 0ull, l, lc) ? 1u : 0u;
 	uint32_t total;
 	block_exclusive_scan(cnt, warp_sums, total);
 	if (threadIdx.x == 0) {
@@ -286,7 +314,7 @@ constexpr int kSplitNodes = 256 / 8;  // nodes per block iteration
 __global__ void __launch_bounds__(256) k_level_split(Ctrl* c, int l, uint32_t cap, uint32_t max_depth, float bx, float by, float bz,
                                                       const uint64_t* __restrict__ keys, float4* geom, uint2* info, uint32_t* nbegin,
                                                       uint32_t* nparent, uint64_t* nkey, uint32_t* p2p_head,
-                                                      const uint32_t* __restrict__ scan_sums) {
+                                                      const LetCtrl* __restrict__ lc, const uint32_t* __restrict__ scan_sums) {
 	__shared__ uint32_t warp_sums[32];
 	if ((uint32_t) l >= max_depth || scan_sums[gridDim.x] == 0) return;
 	const uint32_t lo = c->level_off[l], hi = c->level_off[l + 1];
@@ -302,7 +330,7 @@ __global__ void __launch_bounds__(256) k_level_split(Ctrl* c, int l, uint32_t ca
 		const uint32_t i = base + slot;
 		uint2 nf = make_uint2(0u, 0u);
 		if (i < t1) nf = info[i];
-		const bool split = i < t1 && nf.y > cap;
+		const bool split = i < t1 && node_splits(nf.y, cap, lc ? nkey[i] : 0ull, l, lc);
 		uint32_t total;
 		uint32_t rank = block_exclusive_scan(split && k == 0u ? 1u : 0u, warp_sums, total);
 		rank = __shfl_sync(0xffffffffu, rank, (threadIdx.x & 31u) & ~7u);  // the node's lane 0 holds its rank
@@ -341,16 +369,31 @@ __global__ void __launch_bounds__(256) k_level_split(Ctrl* c, int l, uint32_t ca
 	}
 }
 
+// The level loops of a step stop at Sim::depth_bound (last step's depth + 1) instead of max_depth: on the Plummer benchmark the tree
+// has 12 levels of 21, and the launches for the empty ones were a third of all launches of a step. If a node at the bound still wants
+// to split, kOvfDepth makes the host re-run the step unbounded.
+__global__ void k_level_check(Ctrl* c, int l, uint32_t cap, const uint2* __restrict__ info, const uint64_t* __restrict__ nkey,
+                              const LetCtrl* __restrict__ lc) {
+	const uint32_t lo = c->level_off[l], hi = c->level_off[l + 1];
+	bool any = false;
+	for (uint32_t i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += gridDim.x * blockDim.x)
+		any |= node_splits(info[i].y, cap, nkey[i], l, lc);
+	if (any) atomicOr(&c->status, kOvfDepth);
+}
+
 void launch_tree_build(Sim& s) {
 	const nbody_cuda_config& cf = s.cfg;
+	const int bound = s.depth_bound < (int) cf.max_depth ? s.depth_bound : (int) cf.max_depth;
 	k_tree_init<<<1, 32, 0, s.stream>>>(s.ctrl, (uint32_t) s.n, cf.bounds[0], cf.bounds[1], cf.bounds[2], s.geom, s.info, s.nbegin,
 	                                     s.nparent, s.nkey, s.p2p_head);
-	for (int l = 0; l < (int) cf.max_depth; ++l) {
-		k_level_count<<<kScanBlocks, 256, 0, s.stream>>>(s.ctrl, l, cf.leaf_capacity, cf.max_depth, s.max_nodes, s.info, s.scan_sums);
+	for (int l = 0; l < bound; ++l) {
+		k_level_count<<<kScanBlocks, 256, 0, s.stream>>>(s.ctrl, l, cf.leaf_capacity, cf.max_depth, s.max_nodes, s.info, s.nkey, s.let_ctrl,
+		                                                  s.scan_sums);
 		k_level_split<<<kScanBlocks, 256, 0, s.stream>>>(s.ctrl, l, cf.leaf_capacity, cf.max_depth, cf.bounds[0], cf.bounds[1],
 		                                                  cf.bounds[2], s.keys[0], s.geom, s.info, s.nbegin, s.nparent, s.nkey,
-		                                                  s.p2p_head, s.scan_sums);
+		                                                  s.p2p_head, s.let_ctrl, s.scan_sums);
 	}
+	if (bound < (int) cf.max_depth) k_level_check<<<kNumSM, 256, 0, s.stream>>>(s.ctrl, bound, cf.leaf_capacity, s.info, s.nkey, s.let_ctrl);
 }
 
 }  // namespace nbody

@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(128) k_m2m(const Ctrl* __restrict__ c, int l, 
 template <int P>
 static void upsweep_t(Sim& s) {
 	k_p2m<P><<<kNumSM * 8, 256, 0, s.stream>>>(s.ctrl, s.posq[1], s.geom, s.info, s.nbegin, s.M, s.L, s.nc_stride);
-	for (int l = (int) s.cfg.max_depth - 1; l >= 0; --l)
+	for (int l = (s.depth_bound < (int) s.cfg.max_depth ? s.depth_bound : (int) s.cfg.max_depth) - 1; l >= 0; --l)
 		k_m2m<P><<<kNumSM * 4, 128, 0, s.stream>>>(s.ctrl, l, s.geom, s.info, s.M, s.nc_stride);
 }
 

@@ -1,0 +1,113 @@
+"""Partitioned multi-GPU scheme (NBODY_FLAG_PARTITIONED: every rank holds only its Morton-key range and imports a locally essential
+tree, nbody_b200/csrc/let.cu) on ONE GPU through virtual ranks: the same kernels and phases as one process per GPU, the exchanges
+are device copies. The W-rank run must reproduce the single-GPU run: Morton keys, tree order and permutation bit for bit (the
+concatenation of the ranks in rank order IS the global tree order), the P2P work summed over the ranks exactly (the ranks' trees are
+the global octree restricted to their own particles, so the interaction lists are the global ones), accelerations and trajectories
+to FP32 round-off (the lists are summed in a different order), and the accelerations within 1e-3 RMS of FP64 direct summation."""
+import numpy as np
+import pytest
+
+import nbody_b200
+import oracle
+from nbody_b200 import workloads
+from conftest import rms_rel
+
+pytestmark = pytest.mark.gpu
+
+ACC_TOL = 1e-3
+
+
+def single(P, **kw):
+    return nbody_b200.CudaSimulation([1.0, 1.0, 1.0], P, 1e-3, **kw)
+
+
+CASES = [("plummer", 30000, 8, 2), ("plummer", 30000, 8, 4), ("uniform", 20000, 8, 8), ("two_galaxies", 40000, 32, 4),
+         ("plummer", 100000, 48, 8), ("uniform", 5000, 8, 3), ("plummer", 3000, 8, 16)]
+
+
+@pytest.mark.parametrize("kind,n,cap,world", CASES)
+def test_force_evaluation_matches_single_gpu(kind, n, cap, world):
+    P = workloads.GENERATORS[kind](n)
+    ref = single(P, leaf_capacity=cap, flags=nbody_b200.FLAG_NO_INTEGRATE)
+    ref.step()
+    grp = nbody_b200.VirtualGroup([1.0, 1.0, 1.0], P, 1e-3, world, leaf_capacity=cap, flags=nbody_b200.FLAG_NO_INTEGRATE)
+    grp.step()
+    assert sum(grp.counts()) == n
+    assert np.array_equal(grp.keys(), ref.keys())
+    assert np.array_equal(grp.permutation(), ref.permutation())
+    assert np.array_equal(grp.particles(), ref.particles())
+    st, sr = grp.stats(), ref.stats()
+    assert sum(s["p2p_interactions"] for s in st) == sr["p2p_interactions"]       # same P2P lists, particle for particle
+    assert sum(s["m2l_interactions"] for s in st) >= sr["m2l_interactions"]       # cells shared by several ranks count once per part
+    a, a_ref = grp.accelerations().astype(np.float64), ref.accelerations().astype(np.float64)
+    assert rms_rel(a, a_ref) < 2e-5                                               # summation order only
+    if n <= 40000:
+        out = ref.particles()
+        posq = np.ascontiguousarray(np.concatenate([out[:, 0:3], out[:, 9:10]], axis=1))
+        g = oracle.direct_field(posq, None, 0.01) * (out[:, 9] / out[:, 8])[:, None]
+        assert rms_rel(a, g) < ACC_TOL
+    assert all(s["retries"] == 0 for s in st)
+    if world > 1 and n >= 20000:
+        assert all(s["imported_nodes"] > 0 for s in st) and any(s["halo_particles"] > 0 for s in st)
+    grp.close(); ref.close()
+
+
+@pytest.mark.parametrize("kind,n,cap,world,flags", [("plummer", 60000, 16, 4, 0), ("plummer", 60000, 16, 4, nbody_b200.FLAG_STATIC_PARTITION),
+                                                    ("two_galaxies", 50000, 8, 8, 0), ("uniform", 30000, 8, 2, 0)])
+def test_trajectory_matches_single_gpu(kind, n, cap, world, flags):
+    """Five steps with the integrator: particles migrate between the ranks and the splitters follow the measured work, yet the
+    state after every step is the single-GPU state in the same order."""
+    P = workloads.GENERATORS[kind](n)
+    G = workloads.force_constant(kind, n)
+    ref = single(P, leaf_capacity=cap, force_constant=G)
+    grp = nbody_b200.VirtualGroup([1.0, 1.0, 1.0], P, 1e-3, world, leaf_capacity=cap, force_constant=G, flags=flags)
+    migrated = 0
+    for step in range(5):
+        t_ref, t = ref.step(), grp.step()
+        assert t == t_ref
+        assert sum(grp.counts()) == n
+        a, b = grp.particles(), ref.particles()
+        assert np.array_equal(grp.permutation(), ref.permutation()), step
+        assert np.abs(a[:, 0:3] - b[:, 0:3]).max() < 2e-6 and np.abs(a[:, 4:7] - b[:, 4:7]).max() < 2e-4, step
+        assert sum(s["p2p_interactions"] for s in grp.stats()) == ref.stats()["p2p_interactions"], step
+        migrated += sum(s["migrated_particles"] for s in grp.stats()[0:1]) if step else 0
+    if flags & nbody_b200.FLAG_STATIC_PARTITION:
+        pass
+    else:
+        assert len(set(grp.counts())) > 1  # the partition follows the work, not the particle count
+    grp.close(); ref.close()
+
+
+def test_owned_round_trip_and_memory_scaling():
+    """get/set of a member's own particles touches nothing else, and a member's device memory follows N/W + halo, not N."""
+    n = 200000
+    P = workloads.plummer(n)
+    bytes_w = {}
+    for world in (1, 4):
+        grp = nbody_b200.VirtualGroup([1.0, 1.0, 1.0], P, 1e-3, world, leaf_capacity=32)
+        grp.step()
+        bytes_w[world] = max(s["device_bytes"] for s in grp.stats())
+        m = grp.members[world - 1]
+        mine = m.owned_particles()
+        assert mine.shape[0] == m.n and np.array_equal(mine, m.particles())
+        first, count = m.owned_range()
+        assert count == m.n and first == sum(grp.counts()[:world - 1])
+        m.set_owned_particles_ptr(mine.ctypes.data, mine.shape[0])
+        assert np.array_equal(m.particles(), mine)
+        grp.step()
+        grp.close()
+    assert bytes_w[4] < 0.6 * bytes_w[1]
+
+
+def test_pool_growth_inside_a_partitioned_step():
+    """Tiny pools: the ranks that overflow grow their pools and repeat their part of the step while the others wait."""
+    n = 40000
+    P = workloads.plummer(n)
+    ref = single(P, leaf_capacity=8, flags=nbody_b200.FLAG_NO_INTEGRATE)
+    ref.step()
+    grp = nbody_b200.VirtualGroup([1.0, 1.0, 1.0], P, 1e-3, 4, leaf_capacity=8, flags=nbody_b200.FLAG_NO_INTEGRATE, pool_scale=0.02)
+    grp.step()
+    assert any(s["retries"] > 0 for s in grp.stats())
+    assert np.array_equal(grp.permutation(), ref.permutation())
+    assert rms_rel(grp.accelerations(), ref.accelerations()) < 2e-5
+    grp.close(); ref.close()

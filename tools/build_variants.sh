@@ -4,7 +4,8 @@
 set -e
 cd "$(dirname "$0")/.."
 python nbody_b200/build.py
-NBODY_BUILD_TAG=bulk NBODY_BUILD_DEFS="-DNBODY_LEAF_BULK=1" python nbody_b200/build.py
-NBODY_BUILD_TAG=bulk_rows2 NBODY_BUILD_DEFS="-DNBODY_LEAF_BULK=1 -DNBODY_LEAF_ROWS=2" python nbody_b200/build.py   # tiles padded to 64 instead of 128 sources
-(cd tools/micro && nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o fma_peak fma_peak.cu)
-for t in bulk bulk_rows2; do grep -A3 "k_leafILi4ELb1" nbody_b200/build_$t/leaf.o.log | grep -E "Used|spill" | tr '\n' ' '; echo " <- $t"; done
+build() { NBODY_BUILD_TAG=$1 NBODY_BUILD_DEFS="$2" python nbody_b200/build.py > /dev/null; grep -A3 "k_leafILi4ELb1" nbody_b200/build_$1/leaf.o.log | grep -E "Used|spill" | tr '\n' ' '; echo " <- $1"; }
+build rowfill "-DNBODY_LEAF_BULK=0"                               # the cp.async row fill of round 1, for A/B runs
+build cta3 "-DNBODY_LEAF_MIN_CTAS=3"                              # 3 CTAs of 4 warps per SM at up to 168 registers
+build cta3_rows8 "-DNBODY_LEAF_MIN_CTAS=3 -DNBODY_LEAF_ROWS=8"    # ... with 8 source rows in flight per lane
+build cta5_g8 "-DNBODY_LEAF_MIN_CTAS=5 -DNBODY_LEAF_G=8"          # 5 CTAs per SM, 8 targets per block

@@ -10,8 +10,8 @@ import sys, json, numpy as np
 sys.path.insert(0, ".")
 import nbody_b200
 P = np.load(sys.argv[1])
-cap = int(sys.argv[2]); order = int(sys.argv[3]); flags = int(sys.argv[4]); steps = int(sys.argv[5])
-sim = nbody_b200.CudaSimulation([1, 1, 1], P, 1e-3, order=order, leaf_capacity=cap, flags=flags)
+cap = int(sys.argv[2]); order = int(sys.argv[3]); flags = int(sys.argv[4]); steps = int(sys.argv[5]); tau = float(sys.argv[6])
+sim = nbody_b200.CudaSimulation([1, 1, 1], P, 1e-3, order=order, leaf_capacity=cap, flags=flags, low_order_tau=tau)
 for _ in range(steps): sim.step()
 st = sim.stats()
 acc = sim.accelerations()
@@ -26,7 +26,7 @@ def main():
     if not os.path.exists(path):
         np.save(path, workloads.plummer(n))
     for spec in sys.argv[2:]:
-        env = dict(os.environ); cap, order, flags, steps = 32, 4, 0, 3
+        env = dict(os.environ); cap, order, flags, steps, tau = 32, 4, 0, 3, 0.13
         for item in filter(None, spec.split(";")):
             for kv in item.split(","):
                 k, v = kv.split("=")
@@ -34,8 +34,9 @@ def main():
                 elif k == "order": order = int(v)
                 elif k == "flags": flags = int(v)
                 elif k == "steps": steps = int(v)
+                elif k == "tau": tau = float(v)
                 else: env[k] = v
-        r = subprocess.run([sys.executable, "-c", CHILD, path, str(cap), str(order), str(flags), str(steps)], env=env, capture_output=True, text=True, timeout=300)
+        r = subprocess.run([sys.executable, "-c", CHILD, path, str(cap), str(order), str(flags), str(steps), str(tau)], env=env, capture_output=True, text=True, timeout=300)
         res = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")]
         if not res:
             print(f"[{spec}] FAILED rc={r.returncode}\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}", flush=True); continue
