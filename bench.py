@@ -51,7 +51,7 @@ def measured_peaks():
 def measured_traffic(kernel, args):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full
     capture of exactly this workload (profiles/r01k_traffic.json); None for any other workload."""
-    p = os.path.join(ROOT, "profiles", "r01k_traffic.json")
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
     try:
         with open(p) as f:
             d = json.load(f)
@@ -160,6 +160,15 @@ def reference_arm(args, rank, emit):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    # BASELINE config 1 exactly: the unmodified NaiveSimulation on ALL 4096 particles of the uniform cube, 10 steps
+    P1 = workloads.uniform_cube(4096)
+    G1 = workloads.force_constant("uniform", 4096)
+    run1 = (lambda steps: oracle.ref_naive_run(P1, G1, args.dt, steps)) if have_ref else (lambda steps: oracle.naive_step_as_written(P1, G1, args.dt, steps))
+    t0 = time.perf_counter()
+    run1(10)
+    dt1 = time.perf_counter() - t0
+    line["config1"] = {"workload": "uniform cube N=4096, 10 steps (BASELINE configs[0])", "value": 4096 * 10 / dt1, "unit": UNIT,
+                       "ms_per_step": 1e2 * dt1, "cores": 1, "kind": "reference" if have_ref else "port", "same_config_as_ours_config1": True}
     emit(line)
 
 
@@ -182,6 +191,13 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pool-scale", type=float, default=1.0)
     ap.add_argument("--flags", type=int, default=0, help="nbody_cuda_config.flags (e.g. 32 = NBODY_FLAG_NO_OVERLAP, for A/B runs)")
+    ap.add_argument("--scheme", default="auto", choices=["auto", "partitioned", "replicated"],
+                    help="multi-GPU scheme: partitioned = own particles + locally essential tree (NBODY_FLAG_PARTITIONED, the default for "
+                         "N > 1), replicated = round 1's replicated state and tree")
+    ap.add_argument("--tau", type=float, default=None, help="low_order_tau (adaptive-order M2L); default: the library's 0.13")
+    ap.add_argument("--no-accuracy", action="store_true", help="skip the accuracy check of the benched configuration")
+    ap.add_argument("--no-multi-check", action="store_true", help="N > 1: skip the comparison with a single-GPU run at N = 2^20")
+    ap.add_argument("--no-config1", action="store_true", help="skip BASELINE config 1 (uniform N = 4096, 10 steps) measured alongside")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -215,20 +231,25 @@ def main():
     # this rank's slice of the global particle set (weak in memory, strong in work: N is fixed)
     lo = n * rank // world
     hi = n * (rank + 1) // world
-    gen = workloads.GENERATORS[args.workload]
-    P = gen(hi - lo, start=lo, n_total=n) if args.workload == "plummer" else gen(hi - lo, start=lo) if args.workload == "uniform" else gen(n)
+    P = workloads.generate(args.workload, n, lo, hi - lo)
     host = torch.from_numpy(P).pin_memory()
     Pn = host.numpy()
+    partitioned = world > 1 and args.scheme != "replicated"
+    base_flags = args.flags | (nbody_b200.FLAG_PARTITIONED if partitioned else 0)
 
-    def make_sim(capacity):
-        cfgkw = dict(order=args.order, leaf_capacity=capacity, device=local_rank, pool_scale=args.pool_scale, flags=args.flags,
-                     force_constant=workloads.force_constant(args.workload, n))
+    def make_sim(capacity, particles=None, n_total=None, offset=None, flags=None, kind=None):
+        particles = Pn if particles is None else particles
+        n_total = n if n_total is None else n_total
+        cfgkw = dict(order=args.order, leaf_capacity=capacity, device=local_rank, pool_scale=args.pool_scale,
+                     flags=base_flags if flags is None else flags, force_constant=workloads.force_constant(kind or args.workload, n_total))
+        if args.tau is not None:
+            cfgkw["low_order_tau"] = args.tau
         if world == 1:
-            return nbody_b200.CudaSimulation([1.0, 1.0, 1.0], Pn, args.dt, **cfgkw)
+            return nbody_b200.CudaSimulation([1.0, 1.0, 1.0], particles, args.dt, **cfgkw)
         uid = [nbody_b200.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
-        return nbody_b200.CudaSimulation([1.0, 1.0, 1.0], Pn, args.dt, _distributed={
-            "unique_id": uid[0], "n_global": n, "global_offset": lo, "rank": rank, "world": world}, **cfgkw)
+        return nbody_b200.CudaSimulation([1.0, 1.0, 1.0], particles, args.dt, _distributed={
+            "unique_id": uid[0], "n_global": n_total, "global_offset": lo if offset is None else offset, "rank": rank, "world": world}, **cfgkw)
 
     def barrier():
         torch.cuda.synchronize()
@@ -280,7 +301,7 @@ def main():
     # also re-assembles the full state over NVLink when N > 1), the step, D2H of the rank's updated slice.
     first, count = sim.owned_range()
     # owned counts drift with the per-step rebalancing (a few leaves on the Plummer benchmark): room for +50 % on a multi-GPU run
-    out = torch.empty((max(count, 1) + ((n // world) // 2 if world > 1 else 0) + 1024, 12), dtype=torch.float32).pin_memory()
+    out = torch.empty((max(count, 1) + ((n // world) if world > 1 else 0) + 1024, 12), dtype=torch.float32).pin_memory()
     sim.owned_particles_into_ptr(out.data_ptr(), out.shape[0])  # warm the export path
     barrier()
     h2d = d2h = 0
@@ -304,6 +325,46 @@ def main():
            "d2h_bytes_per_step": int(d2h / args.e2e_steps), "ms_per_step": 1e3 * e2e_t / args.e2e_steps, "steps": args.e2e_steps}
 
     sim.close()
+
+    # ---- accuracy of the benched configuration: one force evaluation of the same workload, capacity, order and
+    # tau on the initial condition; rank 0 compares the accelerations of 65,536 of ITS particles with direct summation over ALL N
+    # sources (the all-pairs GPU kernel, FP32 with compensated tile sums; tests/test_gpu_parity.py checks that kernel against FP64)
+    accuracy = None
+    if not args.no_accuracy:
+        fsim = make_sim(args.leaf_capacity, flags=base_flags | nbody_b200.FLAG_NO_INTEGRATE)
+        fsim.step()
+        if partitioned or world == 1:
+            own, acc = fsim.particles(), fsim.accelerations()
+        else:
+            acc = fsim.accelerations()           # collective in the replicated scheme
+            f0, c0 = fsim.owned_range()
+            own, acc = fsim.particles()[f0:f0 + c0], acc[f0:f0 + c0]
+        fsim.close()
+        if rank == 0:
+            full = Pn if world == 1 else workloads.generate(args.workload, n)
+            src = np.ascontiguousarray(np.concatenate([full[:, 0:3], full[:, 9:10]], axis=1))
+            del full
+            ntg = min(65536, own.shape[0])
+            tg = np.linspace(0, own.shape[0] - 1, ntg).astype(np.int64)
+            tpos = np.ascontiguousarray(np.concatenate([own[tg, 0:3], own[tg, 9:10]], axis=1))
+            f, _ = nbody_b200.direct_field(src, tpos, 0.01, device=local_rank)
+            ref = f.astype(np.float64) * (workloads.force_constant(args.workload, n) * own[tg, 9] / own[tg, 8])[:, None]
+            err = float(np.sqrt(((acc[tg].astype(np.float64) - ref) ** 2).sum() / (ref ** 2).sum()))
+            accuracy = {"rms_rel": err, "targets": int(ntg), "sources": int(n), "bar": 1e-3,
+                        "what": "accelerations of one force evaluation of this configuration vs direct summation over all sources (GPU all-pairs kernel)"}
+        barrier()
+
+    # ---- N > 1: the multi-GPU step against a single-GPU run (same workload at N = 2^20, 3 steps): same tree order, same
+    # trajectories to FP32 round-off, the P2P work of the ranks sums to the single-GPU count exactly
+    multi_check = None
+    if world > 1 and not args.no_multi_check:
+        multi_check = multi_gpu_check(args, rank, world, local_rank, make_sim, partitioned, dist, torch)
+
+    # ---- BASELINE config 1 (the reference's own CPU-runnable case): uniform cube N = 4096, 10 steps, measured alongside so that one
+    # same-configuration ratio against --impl reference exists
+    config1 = None
+    if world == 1 and rank == 0 and not args.no_config1:
+        config1 = config1_ours(args, local_rank)
     ref_cap = None
     if args.leaf_capacity != 8 and not args.no_reference_capacity:
         # the same workload at the reference's hard-coded node capacity (src/open_cl_simulation.cpp:41-47), for the record
@@ -336,6 +397,8 @@ def main():
             "achieved": m2l_tf if dominant == "m2l" else p2p_tf, "peak": peak, "unit": "TFLOP/s",
             "frac": (m2l_tf if dominant == "m2l" else p2p_tf) / peak,
             "traffic": measured_traffic("k_m2l" if dominant == "m2l" else "k_leaf", args),
+            "traffic_source": "profiles/r02_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this "
+                              "kernel on this workload (not measured in this run; null for any other workload or N > 1)",
             "peak_source": f"148 SM x 128 lanes x 2 x {peaks['sm_max_mhz']} MHz ({peaks['source']}; FP32 FMA peak, derived)",
             "algorithmic_flops_per_unit": (f"{m2l_flops} per order-{args.order} M2L, {m2l_flops_lo} per order-{args.order - 1} M2L "
                                            f"({n_lo} of {counts['m2l_interactions']} run at the lower order)") if dominant == "m2l" else 20,
@@ -350,7 +413,8 @@ def main():
             "config": {"workload": f"{args.workload} sphere N={n}" if args.workload == "plummer" else f"{args.workload} N={n}",
                        "order": args.order, "leaf_capacity": args.leaf_capacity, "mac_ratio": 0.5, "softening": 0.01,
                        "integrator": "kick-drift", "l2_policy": "working set (>1 GB of lists and particle state per step) exceeds the 126 MB L2",
-                       "partition": "morton-range" if world > 1 else "single", "flags": args.flags,
+                       "partition": ("morton-range, partitioned state + locally essential tree" if partitioned else
+                                     "morton-range, replicated state" if world > 1 else "single"), "flags": base_flags,
                        "library": os.path.basename(nbody_b200.LIB_PATH)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": K * launches_per_step(sim, world),
             "roofline": roof,
@@ -359,6 +423,7 @@ def main():
                                 "all_pairs_config": p2p_micro},
             "m2l_fp32_tflops": m2l_tf, "reference_capacity": ref_cap,
             "stage_ms": stage_ms, "counts": counts,
+            "accuracy": accuracy, "multi_gpu_check": multi_check, "config1": config1,
         }
         if rank_ms is not None:
             line["per_rank_ms"] = {"columns": ["traverse", "m2l", "leaf", "comm"], "rows": rank_ms}
@@ -368,6 +433,90 @@ def main():
     sim.close()
     if world > 1:
         dist.destroy_process_group()
+    if rank == 0:
+        if accuracy is not None and not (accuracy["rms_rel"] <= accuracy["bar"]):
+            raise SystemExit(f"accuracy check failed: RMS relative error {accuracy['rms_rel']:.3e} > 1e-3")
+        if multi_check is not None and not multi_check["pass"]:
+            raise SystemExit(f"multi-GPU check failed: {multi_check}")
+
+
+def multi_gpu_check(args, rank, world, local_rank, make_sim, partitioned, dist, torch):
+    import nbody_b200
+    from nbody_b200 import workloads
+    n2, steps = 1 << 20, 3
+    lo, hi = n2 * rank // world, n2 * (rank + 1) // world
+    sim = make_sim(args.leaf_capacity, particles=workloads.generate(args.workload, n2, lo, hi - lo), n_total=n2, offset=lo)
+    sim.step()
+    first = (sim.permutation() if partitioned else sim.permutation()[slice(*(lambda f, c: (f, f + c))(*sim.owned_range()))],
+             sim.stats()["p2p_interactions"])
+    for _ in range(steps - 1):
+        sim.step()
+    st = sim.stats()
+    if partitioned:
+        mine, perm = sim.particles(), sim.permutation()
+    else:
+        f0, c0 = sim.owned_range()
+        full, fperm = sim.particles(), sim.permutation()
+        mine, perm = full[f0:f0 + c0], fperm[f0:f0 + c0]
+        h = torch.tensor([float(np.abs(full[:, 0:7]).sum(dtype=np.float64))], device="cuda", dtype=torch.float64)
+        hs = [torch.zeros_like(h) for _ in range(world)]
+        dist.all_gather(hs, h)
+    sim.close()
+    parts = [None] * world if rank == 0 else None
+    dist.gather_object((mine, perm, st["p2p_interactions"], st["m2l_interactions"], st["device_bytes"], first[0], first[1]), parts, dst=0)
+    res = None
+    if rank == 0:
+        got = np.concatenate([p[0] for p in parts])
+        gperm = np.concatenate([p[1] for p in parts])
+        ref = nbody_b200.CudaSimulation([1.0, 1.0, 1.0], workloads.generate(args.workload, n2), args.dt, order=args.order,
+                                        leaf_capacity=args.leaf_capacity, device=local_rank,
+                                        force_constant=workloads.force_constant(args.workload, n2),
+                                        **({"low_order_tau": args.tau} if args.tau is not None else {}))
+        ref.step()
+        rperm1, rp2p1 = ref.permutation(), int(ref.stats()["p2p_interactions"])
+        for _ in range(steps - 1):
+            ref.step()
+        r, rperm, rst = ref.particles(), ref.permutation(), ref.stats()
+        ref.close()
+        # first step (identical input): the same tree order, the same P2P work particle for particle
+        gperm1 = np.concatenate([p[5] for p in parts])
+        same_order = gperm1.shape == rperm1.shape and bool(np.array_equal(gperm1, rperm1))
+        p2p_sum = int(sum(p[6] for p in parts))
+        # after `steps` steps: the same trajectories by particle identity (the runs differ by FP32 round-off, so a particle that sits
+        # 1e-7 from a cell boundary may sort differently: the order itself is only compared on the first step)
+        complete = got.shape == r.shape and bool(np.array_equal(np.sort(gperm), np.arange(n2, dtype=np.uint32)))
+        ia, ib = np.argsort(gperm), np.argsort(rperm)
+        dx = float(np.abs(got[ia, 0:3] - r[ib, 0:3]).max()) if complete else float("inf")
+        dv = float(np.abs(got[ia, 4:7] - r[ib, 4:7]).max()) if complete else float("inf")
+        res = {"workload": f"{args.workload} N={n2}", "steps": steps, "ranks": world, "first_step_same_tree_order_as_1gpu": same_order,
+               "first_step_p2p_interactions_sum": p2p_sum, "first_step_p2p_interactions_1gpu": rp2p1,
+               "all_particles_present": complete, "max_abs_dx": dx, "max_abs_dv": dv,
+               "m2l_interactions_sum": int(sum(p[3] for p in parts)), "m2l_interactions_1gpu": int(rst["m2l_interactions"]),
+               "device_bytes_per_rank": [int(p[4]) for p in parts], "device_bytes_1gpu": int(rst["device_bytes"])}
+        ok = same_order and complete and dx < 1e-5 and dv < 1e-3 and p2p_sum == rp2p1
+        if not partitioned:
+            res["state_identical_on_all_ranks"] = all(abs(float(x) - float(hs[0])) <= 1e-9 * abs(float(hs[0])) for x in hs)
+            ok = ok and res["state_identical_on_all_ranks"]
+        res["pass"] = bool(ok)
+    return res
+
+
+def config1_ours(args, local_rank):
+    """BASELINE config 1 through the same library: uniform cube N = 4096, 10 steps (the FMM path, the reference's capacity 8)."""
+    import nbody_b200
+    from nbody_b200 import workloads
+    n1, steps = 4096, 10
+    P1 = workloads.uniform_cube(n1)
+    sim = nbody_b200.CudaSimulation([1.0, 1.0, 1.0], P1, args.dt, device=local_rank, force_constant=workloads.force_constant("uniform", n1))
+    for _ in range(3):
+        sim.step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        sim.step()
+    dt = time.perf_counter() - t0
+    sim.close()
+    return {"workload": "uniform cube N=4096, 10 steps (BASELINE configs[0])", "value": n1 * steps / dt, "unit": UNIT, "ms_per_step": 1e3 * dt / steps,
+            "note": "the FMM path at the library defaults (capacity 8, order 4); compare with config1 of --impl reference"}
 
 
 def launches_per_step(sim, world):

@@ -185,11 +185,12 @@ __global__ void k_let_fixup(const ImportTable t, uint32_t imp_base, uint32_t tot
 	}
 }
 
-__global__ void k_let_mark(const Ctrl* __restrict__ c, uint64_t p2p_cap, const uint2* __restrict__ p2p, uint32_t* __restrict__ hoff) {
+__global__ void k_let_mark(const Ctrl* __restrict__ c, uint64_t p2p_cap, const uint2* __restrict__ p2p, uint32_t total, uint32_t* __restrict__ hoff) {
+	if (c->status) return;  // a pool overflowed: the lists are incomplete (reserved but unwritten entries); the host grows the pool and repeats
 	const uint64_t n = c->p2p_cursor < p2p_cap ? c->p2p_cursor : p2p_cap;
 	for (uint64_t e = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; e < n; e += (uint64_t) gridDim.x * blockDim.x) {
 		const uint2 en = p2p[e];
-		if (en.x & kImported) hoff[en.x & ~kImported] = en.y;  // every writer stores the same count
+		if ((en.x & kImported) && (en.x & ~kImported) < total) hoff[en.x & ~kImported] = en.y;  // every writer stores the same count
 	}
 }
 
@@ -201,7 +202,7 @@ __global__ void k_let_fetch(Ctrl* c, LetCtrl* lc, const PeerTable peer, const Im
 	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
 	const uint32_t need = hoff[total];
 	if (blockIdx.x == 0 && threadIdx.x == 0) { lc->halo_count = need; if (need > halo_cap) atomicOr(&c->status, kOvfHalo); }
-	if (need > halo_cap) return;
+	if (need > halo_cap || (c->status & ~kOvfHalo)) return;
 	for (uint32_t base = warp * 32u; base < total; base += nwarps * 32u) {
 		const uint32_t i = base + lane;
 		uint32_t off = 0, cnt = 0, rb = 0;
@@ -222,7 +223,7 @@ __global__ void k_let_fetch(Ctrl* c, LetCtrl* lc, const PeerTable peer, const Im
 
 __global__ void k_let_translate(const Ctrl* __restrict__ c, uint64_t p2p_cap, uint2* __restrict__ p2p, const uint32_t* __restrict__ hoff,
                                 uint32_t halo_base) {
-	if (c->status & kOvfHalo) return;
+	if (c->status) return;
 	const uint64_t n = c->p2p_cursor < p2p_cap ? c->p2p_cursor : p2p_cap;
 	for (uint64_t e = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; e < n; e += (uint64_t) gridDim.x * blockDim.x) {
 		const uint32_t x = p2p[e].x;
@@ -520,7 +521,7 @@ int stage3(Sim& s, bool retry) {
 	NB_CUDA_CHECK(cudaEventRecord(L.ev[5], st));
 	// halo: which imported leaves do the P2P lists name -> slots behind the own particles -> fetch over NVLink -> point the entries at them
 	const uint32_t halo_base = (uint32_t) s.cap, halo_cap = (uint32_t) (s.src_cap - s.cap);
-	k_let_mark<<<kNumSM * 8, 256, 0, st>>>(s.ctrl, s.pools.p2p_cap, s.pools.p2p, L.imp_hoff);
+	k_let_mark<<<kNumSM * 8, 256, 0, st>>>(s.ctrl, s.pools.p2p_cap, s.pools.p2p, L.imp_total, L.imp_hoff);
 	launch_exclusive_scan(s, L.imp_hoff, L.imp_total + 1);
 	k_let_fetch<<<kNumSM * 8, 256, 0, st>>>(s.ctrl, s.let_ctrl, L.peer, L.imp, L.imp_total, L.imp_hoff, L.imp_rbegin, s.posq[1], halo_base, halo_cap);
 	k_let_translate<<<kNumSM * 8, 256, 0, st>>>(s.ctrl, s.pools.p2p_cap, s.pools.p2p, L.imp_hoff, halo_base);

@@ -99,15 +99,31 @@ def plummer(n, seed=42, start=0, n_total=None):
     return _plummer(n, seed, start, (0.5, 0.5, 0.5), 1.0 / 32.0, 0.45, 1.0, (0, 0, 0), n_total or n)
 
 
-def two_galaxies(n, seed=42):
-    """Two Plummer spheres of n/2 at x = 0.3 / 0.7 approaching at +-0.05 (config 4)."""
-    h = n // 2
-    a = _plummer(h, seed, 0, (0.3, 0.5, 0.5), 1.0 / 32.0, 0.28, 0.5, (0.05, 0, 0), h)
-    b = _plummer(n - h, seed + 1, h, (0.7, 0.5, 0.5), 1.0 / 32.0, 0.28, 0.5, (-0.05, 0, 0), n - h)
-    return np.concatenate([a, b], axis=0)
+def two_galaxies(n, seed=42, start=0, n_total=None):
+    """Two Plummer spheres of N/2 at x = 0.3 / 0.7 approaching at +-0.05 (config 4). With n_total, particles
+    [start, start + n) of the N = n_total set (ranks generate disjoint slices of one global set)."""
+    N = n_total or n
+    h = N // 2
+    lo, hi = start, start + n
+    na = max(0, min(hi, h) - lo)
+    nb = n - na
+    parts = []
+    if na:
+        parts.append(_plummer(na, seed, lo, (0.3, 0.5, 0.5), 1.0 / 32.0, 0.28, 0.5, (0.05, 0, 0), h))
+    if nb:
+        parts.append(_plummer(nb, seed + 1, max(lo, h), (0.7, 0.5, 0.5), 1.0 / 32.0, 0.28, 0.5, (-0.05, 0, 0), N - h))
+    return np.concatenate(parts, axis=0) if parts else np.zeros((0, PARTICLE_FLOATS), np.float32)
 
 
 GENERATORS = {"uniform": uniform_cube, "plummer": plummer, "two_galaxies": two_galaxies}
+
+
+def generate(kind, n_total, start=0, count=None):
+    """Particles [start, start + count) of the n_total-particle workload `kind`: every rank builds its own slice."""
+    count = n_total - start if count is None else count
+    if kind == "uniform":
+        return uniform_cube(count, start=start)
+    return GENERATORS[kind](count, start=start, n_total=n_total)
 
 
 def force_constant(kind, n):
