@@ -179,7 +179,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="plummer", choices=["plummer", "uniform", "two_galaxies"])
-    ap.add_argument("--n", type=int, default=1 << 24)
+    ap.add_argument("--n", "--particles", dest="n", type=int, default=1 << 24)
     ap.add_argument("--order", type=int, default=4)
     ap.add_argument("--leaf-capacity", type=int, default=48,
                     help="octree node capacity; the reference hard-codes 8 with a FIXME (src/open_cl_simulation.cpp:41-47), 48 is the B200 tuning")
@@ -196,6 +196,8 @@ def main():
                          "N > 1), replicated = round 1's replicated state and tree")
     ap.add_argument("--tau", type=float, default=None, help="low_order_tau (adaptive-order M2L); default: the library's 0.13")
     ap.add_argument("--no-accuracy", action="store_true", help="skip the accuracy check of the benched configuration")
+    ap.add_argument("--accuracy-targets", type=int, default=65536)
+    ap.add_argument("--slack-pct", type=int, default=0, help="partitioned mode: nbody_cuda_config.partition_slack_pct (0 = automatic)")
     ap.add_argument("--no-multi-check", action="store_true", help="N > 1: skip the comparison with a single-GPU run at N = 2^20")
     ap.add_argument("--no-config1", action="store_true", help="skip BASELINE config 1 (uniform N = 4096, 10 steps) measured alongside")
     args = ap.parse_args()
@@ -231,9 +233,13 @@ def main():
     # this rank's slice of the global particle set (weak in memory, strong in work: N is fixed)
     lo = n * rank // world
     hi = n * (rank + 1) // world
-    P = workloads.generate(args.workload, n, lo, hi - lo)
-    host = torch.from_numpy(P).pin_memory()
+    big = hi - lo > (1 << 26)                    # config 5 (2^27 particles per rank): no pinned staging, no end-to-end leg
+    host = torch.empty((hi - lo, 12), dtype=torch.float32)
+    if not big:
+        host = host.pin_memory()
     Pn = host.numpy()
+    for c0 in range(lo, hi, 1 << 23):            # in chunks: the generator's temporaries stay small at 2^27 particles per rank
+        Pn[c0 - lo:min(c0 + (1 << 23), hi) - lo] = workloads.generate(args.workload, n, c0, min(1 << 23, hi - c0))
     partitioned = world > 1 and args.scheme != "replicated"
     base_flags = args.flags | (nbody_b200.FLAG_PARTITIONED if partitioned else 0)
 
@@ -244,6 +250,8 @@ def main():
                      flags=base_flags if flags is None else flags, force_constant=workloads.force_constant(kind or args.workload, n_total))
         if args.tau is not None:
             cfgkw["low_order_tau"] = args.tau
+        if args.slack_pct:
+            cfgkw["partition_slack_pct"] = args.slack_pct
         if world == 1:
             return nbody_b200.CudaSimulation([1.0, 1.0, 1.0], particles, args.dt, **cfgkw)
         uid = [nbody_b200.comm_unique_id() if rank == 0 else None]
@@ -264,7 +272,7 @@ def main():
         barrier()
         if sampler is not None:
             sampler.start()
-        sums, cnts = {}, {}
+        sums, cnts, imb = {}, {}, []
         t0 = time.perf_counter()
         for _ in range(k):
             sim.step()
@@ -273,6 +281,7 @@ def main():
                     sums[key] = sums.get(key, 0.0) + v
                 else:
                     cnts[key] = v
+            imb.append(round(cnts.get("work_imbalance", 0.0), 4))
         barrier()
         dt = time.perf_counter() - t0
         dev_ms = sums.get("ms_total", 0.0)  # CUDA events on the solver's stream, first launch to last of every step
@@ -281,6 +290,7 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dt, dev_ms = float(tt[0].item()), float(tt[1].item())
         cnts["device_ms_per_step"] = dev_ms / k
+        cnts["work_imbalance_per_step"] = imb
         return dt, {key: v / k for key, v in sums.items()}, cnts
 
     sim = make_sim(args.leaf_capacity)
@@ -291,7 +301,8 @@ def main():
     K = args.steps
     rank_ms = None
     if world > 1:
-        mine = torch.tensor([stage_ms.get(k, 0.0) for k in ("ms_traverse", "ms_m2l", "ms_leaf", "ms_comm")], device="cuda", dtype=torch.float64)
+        RANK_COLS = ("ms_sort", "ms_tree", "ms_upsweep", "ms_traverse", "ms_m2l", "ms_l2l", "ms_leaf", "ms_comm", "ms_import", "ms_halo", "ms_balance", "ms_total")
+        mine = torch.tensor([stage_ms.get(k, 0.0) for k in RANK_COLS], device="cuda", dtype=torch.float64)
         allm = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(allm, mine)
         rank_ms = [[round(float(x), 2) for x in t] for t in allm]
@@ -300,13 +311,15 @@ def main():
     # every step: H2D of this rank's slice of the state from pinned host memory (set_owned_particles, which
     # also re-assembles the full state over NVLink when N > 1), the step, D2H of the rank's updated slice.
     first, count = sim.owned_range()
-    # owned counts drift with the per-step rebalancing (a few leaves on the Plummer benchmark): room for +50 % on a multi-GPU run
-    out = torch.empty((max(count, 1) + ((n // world) if world > 1 else 0) + 1024, 12), dtype=torch.float32).pin_memory()
-    sim.owned_particles_into_ptr(out.data_ptr(), out.shape[0])  # warm the export path
+    e2e_steps = 0 if big else args.e2e_steps
+    # owned counts drift with the per-step rebalancing (a few leaves on the Plummer benchmark): room for +100 % on a multi-GPU run
+    out = torch.empty(((max(count, 1) + ((n // world) if world > 1 else 0) + 1024) if e2e_steps else 16, 12), dtype=torch.float32).pin_memory()
+    if e2e_steps:
+        sim.owned_particles_into_ptr(out.data_ptr(), out.shape[0])  # warm the export path
     barrier()
     h2d = d2h = 0
     t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
+    for _ in range(e2e_steps):
         first, count = sim.owned_range()
         sim.set_owned_particles_ptr(out.data_ptr(), count)
         h2d += 48 * count
@@ -321,8 +334,10 @@ def main():
         mx = tt.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = tt.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         e2e_t, h2d, d2h = float(mx[0]), float(sm[1]), float(sm[2])
-    e2e = {"value": n * args.e2e_steps / e2e_t, "unit": UNIT, "h2d_bytes_per_step": int(h2d / args.e2e_steps),
-           "d2h_bytes_per_step": int(d2h / args.e2e_steps), "ms_per_step": 1e3 * e2e_t / args.e2e_steps, "steps": args.e2e_steps}
+    e2e = {"value": n * e2e_steps / e2e_t, "unit": UNIT, "h2d_bytes_per_step": int(h2d / max(e2e_steps, 1)),
+           "d2h_bytes_per_step": int(d2h / max(e2e_steps, 1)), "ms_per_step": 1e3 * e2e_t / max(e2e_steps, 1), "steps": e2e_steps}
+    if not e2e_steps:
+        e2e["skipped"] = "more than 2^26 particles per rank: the end-to-end leg would pin > 12 GB of host memory per rank"
 
     sim.close()
 
@@ -341,14 +356,16 @@ def main():
             own, acc = fsim.particles()[f0:f0 + c0], acc[f0:f0 + c0]
         fsim.close()
         if rank == 0:
-            full = Pn if world == 1 else workloads.generate(args.workload, n)
-            src = np.ascontiguousarray(np.concatenate([full[:, 0:3], full[:, 9:10]], axis=1))
-            del full
-            ntg = min(65536, own.shape[0])
+            ntg = min(args.accuracy_targets, own.shape[0])
             tg = np.linspace(0, own.shape[0] - 1, ntg).astype(np.int64)
             tpos = np.ascontiguousarray(np.concatenate([own[tg, 0:3], own[tg, 9:10]], axis=1))
-            f, _ = nbody_b200.direct_field(src, tpos, 0.01, device=local_rank)
-            ref = f.astype(np.float64) * (workloads.force_constant(args.workload, n) * own[tg, 9] / own[tg, 8])[:, None]
+            f = np.zeros((ntg, 3), np.float64)
+            chunk = 1 << 25                      # the sources in chunks (the field is linear in them): the full set need not fit anywhere
+            for c0 in range(0, n, chunk):
+                part = Pn[c0:c0 + chunk] if world == 1 else workloads.generate(args.workload, n, c0, min(chunk, n - c0))
+                src = np.ascontiguousarray(np.concatenate([part[:, 0:3], part[:, 9:10]], axis=1))
+                f += nbody_b200.direct_field(src, tpos, 0.01, device=local_rank)[0]
+            ref = f * (workloads.force_constant(args.workload, n) * own[tg, 9] / own[tg, 8])[:, None]
             err = float(np.sqrt(((acc[tg].astype(np.float64) - ref) ** 2).sum() / (ref ** 2).sum()))
             accuracy = {"rms_rel": err, "targets": int(ntg), "sources": int(n), "bar": 1e-3,
                         "what": "accelerations of one force evaluation of this configuration vs direct summation over all sources (GPU all-pairs kernel)"}
@@ -426,7 +443,7 @@ def main():
             "accuracy": accuracy, "multi_gpu_check": multi_check, "config1": config1,
         }
         if rank_ms is not None:
-            line["per_rank_ms"] = {"columns": ["traverse", "m2l", "leaf", "comm"], "rows": rank_ms}
+            line["per_rank_ms"] = {"columns": [c[3:] for c in RANK_COLS], "rows": rank_ms}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args)
         emit(line)

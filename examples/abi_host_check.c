@@ -34,7 +34,7 @@ int main(int argc, char** argv) {
 	CHECK(sizeof(nbody_particle) == 48);
 	CHECK(sizeof(nbody_cuda_config) == 92);
 	CHECK(sizeof(nbody_checkpoint_header) == 152);
-	CHECK(sizeof(nbody_cuda_stats) == 12 * 8 + 10 * 4 + 3 * 8);
+	CHECK(sizeof(nbody_cuda_stats) == 12 * 8 + 10 * 4 + 3 * 8 + 4 * 4);
 
 	nbody_cuda_default_config(&cfg);
 	CHECK(cfg.abi_version == NBODY_CUDA_ABI_VERSION && cfg.leaf_capacity == 8 && cfg.order == 4 && cfg.max_depth == 21);

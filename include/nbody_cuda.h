@@ -97,7 +97,9 @@ typedef struct nbody_cuda_config {
 	float time_step_eta;
 	float time_step_min;
 	float time_step_max;
-	uint32_t _reserved[3];
+	uint32_t partition_slack_pct; /* partitioned mode: room for own particles = (100 + this) % of N / ranks (migration and rebalancing change a
+	                                 rank's count); 0 = automatic (50 % up to 16M particles per rank, less above) */
+	uint32_t _reserved[2];
 } nbody_cuda_config;
 
 /* per-step statistics (tracing/metrics hook) */
@@ -119,6 +121,10 @@ typedef struct nbody_cuda_stats {
 	uint64_t halo_particles;     /* other ranks' particles fetched for the P2P lists of the last step */
 	uint64_t imported_nodes;     /* nodes of the other ranks' trees held as sources */
 	uint64_t migrated_particles; /* particles that arrived from other ranks at the start of the last step */
+	float ms_import;             /* the parts of ms_comm: all-gather of the ranks' trees (node counts, then the node records over NCCL) */
+	float ms_halo;               /*   halo: mark the imported leaves the P2P lists name, prefix sum, NVLink fetch, list fix-up */
+	float ms_balance;            /*   end of step: work times and next step's splitters */
+	float _pad;
 } nbody_cuda_stats;
 
 typedef struct nbody_cuda_sim nbody_cuda_sim; /* opaque; single-threaded use */

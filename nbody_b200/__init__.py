@@ -41,7 +41,7 @@ class Config(C.Structure):
                 ("softening", C.c_float), ("mac_ratio", C.c_float), ("leaf_capacity", C.c_uint32), ("max_depth", C.c_uint32),
                 ("order", C.c_uint32), ("integrator", C.c_uint32), ("flags", C.c_uint32), ("device", C.c_int32),
                 ("pool_scale", C.c_float), ("low_order_tau", C.c_float), ("time_step_eta", C.c_float), ("time_step_min", C.c_float),
-                ("time_step_max", C.c_float), ("_reserved", C.c_uint32 * 3)]
+                ("time_step_max", C.c_float), ("partition_slack_pct", C.c_uint32), ("_reserved", C.c_uint32 * 2)]
 
 
 class CheckpointHeader(C.Structure):
@@ -56,7 +56,8 @@ class Stats(C.Structure):
                                           "m2l_interactions_low", "p2p_entries", "p2p_interactions", "near_entries", "retries", "device_bytes")] + \
                [(k, C.c_float) for k in ("ms_total", "ms_sort", "ms_tree", "ms_upsweep", "ms_traverse", "ms_m2l", "ms_l2l",
                                          "ms_leaf", "ms_comm", "work_imbalance")] + \
-               [(k, C.c_uint64) for k in ("halo_particles", "imported_nodes", "migrated_particles")]
+               [(k, C.c_uint64) for k in ("halo_particles", "imported_nodes", "migrated_particles")] + \
+               [(k, C.c_float) for k in ("ms_import", "ms_halo", "ms_balance", "_pad")]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if not k.startswith("_")}

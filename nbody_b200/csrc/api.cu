@@ -40,9 +40,9 @@ void dev_free(Sim& s, T*& p, size_t count) {
 	if (p) { cudaFree(p); s.device_bytes -= std::max<size_t>(count, 1) * sizeof(T); p = nullptr; }
 }
 
-// Source-side arrays (geometry, child / count record, first particle, multipole: what a node is read for as a SOURCE) have room for
-// `src_nodes` >= max_nodes entries: in partitioned mode the other ranks' trees are imported behind the own tree. Everything a node
-// carries as a TARGET (local expansion, list heads, parent, key) exists for the own tree only.
+// Source-side arrays (geometry, child / count record, first particle: what the traversal reads of a node as a SOURCE) have room for
+// `src_nodes` >= max_nodes entries: in partitioned mode the other ranks' trees are imported behind the own tree. Expansions and
+// everything a node carries as a TARGET (list heads, parent, key) exist for the own tree only.
 int alloc_nodes(Sim& s, uint32_t max_nodes, uint32_t src_nodes) {
 	if (src_nodes < max_nodes) src_nodes = max_nodes;
 	s.max_nodes = max_nodes;
@@ -51,7 +51,7 @@ int alloc_nodes(Sim& s, uint32_t max_nodes, uint32_t src_nodes) {
 	if ((rc = dev_alloc(s, s.geom, src_nodes))) return rc;
 	if ((rc = dev_alloc(s, s.info, src_nodes))) return rc;
 	if ((rc = dev_alloc(s, s.nbegin, src_nodes))) return rc;
-	if ((rc = dev_alloc(s, s.M, (size_t) src_nodes * s.nc_stride))) return rc;
+	if ((rc = dev_alloc(s, s.M, (size_t) max_nodes * s.nc_stride))) return rc;
 	if ((rc = dev_alloc(s, s.nparent, max_nodes))) return rc;
 	if ((rc = dev_alloc(s, s.nkey, max_nodes))) return rc;
 	if ((rc = dev_alloc(s, s.L, (size_t) max_nodes * s.nc_stride))) return rc;
@@ -61,7 +61,7 @@ int alloc_nodes(Sim& s, uint32_t max_nodes, uint32_t src_nodes) {
 }
 void free_nodes(Sim& s) {
 	const size_t m = s.max_nodes, sn = s.src_nodes;
-	dev_free(s, s.geom, sn); dev_free(s, s.info, sn); dev_free(s, s.nbegin, sn); dev_free(s, s.M, sn * s.nc_stride);
+	dev_free(s, s.geom, sn); dev_free(s, s.info, sn); dev_free(s, s.nbegin, sn); dev_free(s, s.M, m * s.nc_stride);
 	dev_free(s, s.nparent, m); dev_free(s, s.nkey, m);
 	dev_free(s, s.L, m * s.nc_stride); dev_free(s, s.near_ref, m); dev_free(s, s.p2p_head, m);
 }
@@ -261,7 +261,7 @@ int create_common(const nbody_cuda_config* cfg, uint64_t n, Sim** out, uint64_t 
 		return fail(NBODY_ERR_CUDA);
 	}
 	std::memset(s->ctrl_host, 0, sizeof(Ctrl));
-	const double sc = s->cfg.pool_scale, dn = (double) cap;
+	const double sc = s->cfg.pool_scale, dn = (double) n;  // (partitioned mode: n = the rank's initial share; the pools grow on demand)
 	// node budget: ~0.35-0.6 nodes per particle at capacity 8 (measured with the oracle); fewer for larger leaves
 	const double per_particle = std::min(1.25, 10.0 / (double) s->cfg.leaf_capacity);
 	const uint32_t nodes0 = (uint32_t) clamp32(sc * (per_particle * dn + 65536));

@@ -123,7 +123,7 @@ struct Sim {
 
 	// octree, level-major; the 8 children of a split node are contiguous
 	uint32_t max_nodes = 0;      // capacity of the own tree
-	uint32_t src_nodes = 0;      // allocated length of the source-side arrays geom / info / nbegin / M (>= max_nodes; partitioned mode:
+	uint32_t src_nodes = 0;      // allocated length of the source-side arrays geom / info / nbegin (>= max_nodes; partitioned mode:
 	                             // the other ranks' trees are imported at ids [max_nodes, src_nodes))
 	int depth_bound = kMaxDepth; // the level loops of a step run to this depth (last step's depth + 1; kOvfDepth re-runs unbounded)
 	TraverseSeeds seeds;
@@ -135,6 +135,7 @@ struct Sim {
 	uint64_t* nkey = nullptr;    // key prefix
 	float* M = nullptr;          // multipoles, nc_stride floats per node
 	float* L = nullptr;          // locals (pure derivatives), nc_stride floats per node
+	float* Mimp = nullptr;       // partitioned mode: multipole orders 0..P-1 of the imported nodes the M2L lists name (let.cu)
 	uint2* near_ref = nullptr;   // per target node: {offset, count} of its near list in the current round's pool
 	uint32_t* p2p_head = nullptr;  // per node: head of its P2P segment chain (0xffffffff = none)
 	uint32_t* scan_sums = nullptr; // kScanBlocks + 1

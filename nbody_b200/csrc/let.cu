@@ -68,6 +68,11 @@ struct XSlot {
 	uint32_t straddle[kMaxRanks][kNumLevels];  // X2: local count of the depth-d cell that straddles splitter b
 	unsigned long long own_ns;                 // X4: device time of the stages whose cost follows the partition
 	uint64_t cand[kMaxRanks + 1];              // X5: key at the wanted boundary position k, if this rank owns that position
+	// the rank's compact multipole export (orders 0..P-1 per own node): where the others fetch the multipoles their M2L lists name.
+	// Written by the host when the buffer is (re)allocated; `gen` tells the readers to map it again.
+	cudaIpcMemHandle_t mexp_handle;
+	unsigned long long mexp_ptr;               // virtual ranks: the pointer itself
+	uint32_t mexp_gen, _pad;
 	uint64_t sample[kSample];                  // creation: evenly spaced sample of the sorted keys
 };
 
@@ -83,6 +88,7 @@ struct PullArgs {
 	int world;
 };
 struct ImportTable { uint32_t off[kMaxRanks + 1]; int world; };  // imported node i belongs to rank s: off[s] <= i < off[s+1]
+struct MexpTable { const float* p[kMaxRanks]; };
 struct CountTable { uint32_t n[kMaxRanks]; };
 
 }  // namespace
@@ -99,7 +105,13 @@ struct Let {
 	void* mapped[3 * kMaxRanks] = {};
 	uint32_t* imp_rbegin = nullptr;  // per imported node: first particle in its owner's sorted array
 	uint32_t* imp_hoff = nullptr;    // per imported node (+1): halo particles before it; before the scan: its count if a P2P list names it
+	uint32_t* imp_mflag = nullptr;   // per imported node: named by an M2L list of this step
 	uint32_t imp_alloc = 0;
+	float* mexp = nullptr;           // own nodes' multipoles, orders 0..P-1, compact: what the other ranks fetch from
+	uint32_t mexp_cap = 0, mexp_gen = 0;
+	MexpTable peer_mexp{};           // the other ranks' exports (mapped through cudaIpc, or the members' pointers)
+	void* mexp_mapped[kMaxRanks] = {};
+	uint32_t mexp_seen[kMaxRanks] = {};
 	uint32_t counts[kMaxRanks] = {}; // particles per rank in the current step
 	uint32_t nodes[kMaxRanks] = {};
 	ImportTable imp{};
@@ -231,6 +243,40 @@ __global__ void k_let_translate(const Ctrl* __restrict__ c, uint64_t p2p_cap, ui
 	}
 }
 
+// Own multipoles -> compact export: the first MS floats (orders 0..P-1) of every record.
+__global__ void k_let_pack_m(const Ctrl* __restrict__ c, const float4* __restrict__ M4, int s4, float4* __restrict__ E4, int ms4, uint32_t cap) {
+	const uint32_t n = c->n_nodes < cap ? c->n_nodes : cap;
+	const uint64_t total = (uint64_t) n * ms4;
+	for (uint64_t t = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; t < total; t += (uint64_t) gridDim.x * blockDim.x) {
+		const uint32_t node = (uint32_t) (t / ms4), j = (uint32_t) (t - (uint64_t) node * ms4);
+		E4[t] = M4[(size_t) node * s4 + j];
+	}
+}
+
+__global__ void k_let_mark_m(const Ctrl* __restrict__ c, uint64_t m2l_cap, const uint32_t* __restrict__ m2l_id, uint32_t imp_base, uint32_t total,
+                             uint32_t* __restrict__ mflag) {
+	if (c->status) return;
+	const uint64_t n = c->m2l_cursor < m2l_cap ? c->m2l_cursor : m2l_cap;
+	for (uint64_t e = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; e < n; e += (uint64_t) gridDim.x * blockDim.x) {
+		const uint32_t id = m2l_id[e];
+		if (id >= imp_base && id - imp_base < total) mflag[id - imp_base] = 1u;
+	}
+}
+
+// The multipoles the M2L lists name, from their owners' exports (peer memory: NVLink loads), into the local array the M2L kernel reads.
+__global__ void k_let_fetch_m(const Ctrl* __restrict__ c, const MexpTable peer, const ImportTable t, uint32_t total, const uint32_t* __restrict__ mflag,
+                              float4* __restrict__ Mimp4, int ms4) {
+	if (c->status) return;
+	const uint64_t n = (uint64_t) total * ms4;
+	for (uint64_t q = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; q < n; q += (uint64_t) gridDim.x * blockDim.x) {
+		const uint32_t i = (uint32_t) (q / ms4), j = (uint32_t) (q - (uint64_t) i * ms4);
+		if (!mflag[i]) continue;
+		int s = 0;
+		while (s + 1 < t.world && i >= t.off[s + 1]) ++s;
+		Mimp4[q] = reinterpret_cast<const float4*>(peer.p[s])[(size_t) (i - t.off[s]) * ms4 + j];
+	}
+}
+
 __global__ void k_stamp(unsigned long long* dst) {
 	unsigned long long t;
 	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -344,39 +390,40 @@ int ensure_import_room(Sim& s, uint32_t need, uint32_t own_nodes) {
 	if (s.src_nodes - s.max_nodes < need) {
 		const uint64_t want = (uint64_t) s.max_nodes + need + need / 4 + 1024;
 		if (want > 0x7fffffffull) { set_error("partitioned mode: more than 2^31 nodes on one rank"); return NBODY_ERR_CAPACITY; }
-		float4* geom = nullptr; uint2* info = nullptr; uint32_t* nbegin = nullptr; float* M = nullptr;
-		const size_t st = (size_t) s.nc_stride;
+		float4* geom = nullptr; uint2* info = nullptr; uint32_t* nbegin = nullptr;
 		if (cudaMalloc((void**) &geom, want * sizeof(float4)) != cudaSuccess || cudaMalloc((void**) &info, want * sizeof(uint2)) != cudaSuccess ||
-		    cudaMalloc((void**) &nbegin, want * 4) != cudaSuccess || cudaMalloc((void**) &M, want * st * 4) != cudaSuccess) {
-			cudaFree(geom); cudaFree(info); cudaFree(nbegin); cudaFree(M);
+		    cudaMalloc((void**) &nbegin, want * 4) != cudaSuccess) {
+			cudaFree(geom); cudaFree(info); cudaFree(nbegin);
 			set_error("partitioned mode: no memory for the imported trees");
 			return NBODY_ERR_CUDA;
 		}
 		NB_CUDA_CHECK(cudaMemcpyAsync(geom, s.geom, own_nodes * sizeof(float4), cudaMemcpyDeviceToDevice, s.stream));
 		NB_CUDA_CHECK(cudaMemcpyAsync(info, s.info, own_nodes * sizeof(uint2), cudaMemcpyDeviceToDevice, s.stream));
 		NB_CUDA_CHECK(cudaMemcpyAsync(nbegin, s.nbegin, own_nodes * 4, cudaMemcpyDeviceToDevice, s.stream));
-		NB_CUDA_CHECK(cudaMemcpyAsync(M, s.M, own_nodes * st * 4, cudaMemcpyDeviceToDevice, s.stream));
 		NB_CUDA_CHECK(cudaStreamSynchronize(s.stream));
-		cudaFree(s.geom); cudaFree(s.info); cudaFree(s.nbegin); cudaFree(s.M);
-		s.device_bytes += (want - s.src_nodes) * (sizeof(float4) + sizeof(uint2) + 4 + st * 4);
-		s.geom = geom; s.info = info; s.nbegin = nbegin; s.M = M;
+		cudaFree(s.geom); cudaFree(s.info); cudaFree(s.nbegin);
+		s.device_bytes += (want - s.src_nodes) * (sizeof(float4) + sizeof(uint2) + 4);
+		s.geom = geom; s.info = info; s.nbegin = nbegin;
 		s.src_nodes = (uint32_t) want;
 	}
 	if (L.imp_alloc < need + 1) {
 		const uint32_t want = need + need / 4 + 1024;
-		if (L.imp_rbegin) { cudaFree(L.imp_rbegin); cudaFree(L.imp_hoff); s.device_bytes -= (uint64_t) L.imp_alloc * 8; }
-		L.imp_rbegin = L.imp_hoff = nullptr;
-		if (cudaMalloc((void**) &L.imp_rbegin, (size_t) want * 4) != cudaSuccess || cudaMalloc((void**) &L.imp_hoff, (size_t) want * 4) != cudaSuccess) {
+		const size_t per = 12 + (size_t) coef_stride((int) s.cfg.order - 1) * 4;  // rbegin, hoff, mflag, Mimp record
+		if (L.imp_rbegin) { cudaFree(L.imp_rbegin); cudaFree(L.imp_hoff); cudaFree(L.imp_mflag); cudaFree(s.Mimp); s.device_bytes -= (uint64_t) L.imp_alloc * per; }
+		L.imp_rbegin = L.imp_hoff = L.imp_mflag = nullptr; s.Mimp = nullptr;
+		if (cudaMalloc((void**) &L.imp_rbegin, (size_t) want * 4) != cudaSuccess || cudaMalloc((void**) &L.imp_hoff, (size_t) want * 4) != cudaSuccess ||
+		    cudaMalloc((void**) &L.imp_mflag, (size_t) want * 4) != cudaSuccess || cudaMalloc((void**) &s.Mimp, (size_t) want * (per - 12)) != cudaSuccess) {
 			set_error("partitioned mode: no memory for the import tables");
 			return NBODY_ERR_CUDA;
 		}
 		L.imp_alloc = want;
-		s.device_bytes += (uint64_t) want * 8;
+		s.device_bytes += (uint64_t) want * per;
 	}
 	return NBODY_OK;
 }
 
-// X3, second half: every rank's tree (source side: geometry, child/count record, first particle, multipole) lands behind the own tree.
+// X3, second half: every rank's tree as the traversal reads it (geometry, child/count record, first particle: 28 bytes per node) lands
+// behind the own tree. The multipoles do not travel here: after the traversal each rank fetches exactly the ones its M2L lists name.
 int exchange_trees(Sim** m, int nm) {
 	Let& L0 = *m[0]->let;
 	const int W = L0.world;
@@ -387,18 +434,16 @@ int exchange_trees(Sim** m, int nm) {
 			for (int s = 0; s < nm; ++s) {
 				if (s == d || L.nodes[s] == 0) continue;
 				const Sim& S = *m[s];
-				const size_t at = (size_t) D.max_nodes + L.imp.off[s], cnt = L.nodes[s], st = (size_t) D.nc_stride;
+				const size_t at = (size_t) D.max_nodes + L.imp.off[s], cnt = L.nodes[s];
 				NB_CUDA_CHECK(cudaMemcpyAsync(D.geom + at, S.geom, cnt * sizeof(float4), cudaMemcpyDeviceToDevice, D.stream));
 				NB_CUDA_CHECK(cudaMemcpyAsync(D.info + at, S.info, cnt * sizeof(uint2), cudaMemcpyDeviceToDevice, D.stream));
 				NB_CUDA_CHECK(cudaMemcpyAsync(D.nbegin + at, S.nbegin, cnt * 4, cudaMemcpyDeviceToDevice, D.stream));
-				NB_CUDA_CHECK(cudaMemcpyAsync(D.M + at * st, S.M, cnt * st * 4, cudaMemcpyDeviceToDevice, D.stream));
 			}
 		}
 		return NBODY_OK;
 	}
 	Sim& D = *m[0];
 	const Let& L = *D.let;
-	const size_t st = (size_t) D.nc_stride;
 	NB_NCCL_CHECK(g_nccl.GroupStart());
 	for (int s = 0; s < W; ++s) {
 		const size_t cnt = L.nodes[s];
@@ -407,7 +452,6 @@ int exchange_trees(Sim** m, int nm) {
 		NB_NCCL_CHECK(g_nccl.Broadcast(D.geom + at, D.geom + at, cnt * sizeof(float4), ncclChar, s, L.comm, D.stream));
 		NB_NCCL_CHECK(g_nccl.Broadcast(D.info + at, D.info + at, cnt * sizeof(uint2), ncclChar, s, L.comm, D.stream));
 		NB_NCCL_CHECK(g_nccl.Broadcast(D.nbegin + at, D.nbegin + at, cnt * 4, ncclChar, s, L.comm, D.stream));
-		NB_NCCL_CHECK(g_nccl.Broadcast(D.M + at * st, D.M + at * st, cnt * st * 4, ncclChar, s, L.comm, D.stream));
 	}
 	NB_NCCL_CHECK(g_nccl.GroupEnd());
 	return NBODY_OK;
@@ -462,12 +506,41 @@ int phase2a(Sim& s) {
 	return NBODY_OK;
 }
 
+// The compact multipole export holds max_nodes records; (re)allocated with the node arrays, its handle published through the slot.
+int ensure_export(Sim& s) {
+	Let& L = *s.let;
+	if (L.mexp && L.mexp_cap == s.max_nodes) return NBODY_OK;
+	const size_t rec = (size_t) coef_stride((int) s.cfg.order - 1) * 4;
+	if (L.mexp) { cudaFree(L.mexp); s.device_bytes -= (uint64_t) L.mexp_cap * rec; L.mexp = nullptr; }
+	if (cudaMalloc((void**) &L.mexp, (size_t) s.max_nodes * rec) != cudaSuccess) { set_error("partitioned mode: no memory for the multipole export"); return NBODY_ERR_CUDA; }
+	L.mexp_cap = s.max_nodes;
+	s.device_bytes += (uint64_t) L.mexp_cap * rec;
+	XSlot& h = L.xhost[L.rank];  // staging: only these fields of the own slot are host-written
+	std::memset(&h.mexp_handle, 0, sizeof(h.mexp_handle));
+	if (!L.virt && cudaIpcGetMemHandle(&h.mexp_handle, L.mexp) != cudaSuccess) {
+		set_error(std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(cudaGetLastError()));
+		return NBODY_ERR_CUDA;
+	}
+	h.mexp_ptr = (unsigned long long) (uintptr_t) L.mexp;
+	h.mexp_gen = ++L.mexp_gen;
+	XSlot* d = L.xbuf + L.rank;
+	NB_CUDA_CHECK(cudaMemcpyAsync(&d->mexp_handle, &h.mexp_handle, sizeof(h.mexp_handle), cudaMemcpyHostToDevice, s.stream));
+	NB_CUDA_CHECK(cudaMemcpyAsync(&d->mexp_ptr, &h.mexp_ptr, sizeof(h.mexp_ptr), cudaMemcpyHostToDevice, s.stream));
+	NB_CUDA_CHECK(cudaMemcpyAsync(&d->mexp_gen, &h.mexp_gen, sizeof(h.mexp_gen), cudaMemcpyHostToDevice, s.stream));
+	NB_CUDA_CHECK(cudaStreamSynchronize(s.stream));  // the staging words live in the pinned mirror the next read-back overwrites
+	return NBODY_OK;
+}
+
 int build_tree(Sim& s) {
 	Let& L = *s.let;
 	NB_CUDA_CHECK(cudaEventRecord(L.ev[1], s.stream));
 	launch_tree_build(s);
 	NB_CUDA_CHECK(cudaEventRecord(L.ev[2], s.stream));
-	if (!(s.cfg.flags & NBODY_FLAG_DIRECT)) launch_upsweep(s);
+	launch_upsweep(s);
+	int rc = ensure_export(s);
+	if (rc) return rc;
+	const int ms4 = coef_stride((int) s.cfg.order - 1) / 4;
+	k_let_pack_m<<<kNumSM * 4, 256, 0, s.stream>>>(s.ctrl, reinterpret_cast<const float4*>(s.M), s.nc_stride / 4, reinterpret_cast<float4*>(L.mexp), ms4, L.mexp_cap);
 	k_let_publish<<<1, 1, 0, s.stream>>>(s.ctrl, L.xbuf + L.rank);
 	NB_CUDA_CHECK(cudaEventRecord(L.ev[3], s.stream));
 	return NBODY_OK;
@@ -498,6 +571,21 @@ int plan_import(Sim& s) {
 	if (total > 0x7ffffff0ull) { set_error("partitioned mode: more than 2^31 imported nodes"); return NBODY_ERR_CAPACITY; }
 	L.imp_total = (uint32_t) total;
 	s.trav_bound = (int) deepest - 1 > 0 ? (int) deepest - 1 : 1;
+	for (int q = 0; q < W; ++q) {  // the other ranks' multipole exports: map again when a rank has reallocated its buffer
+		const XSlot& x = L.xhost[q];
+		if (q == L.rank) { L.peer_mexp.p[q] = L.mexp; continue; }
+		if (x.mexp_gen == L.mexp_seen[q] && L.peer_mexp.p[q]) continue;
+		if (L.virt) L.peer_mexp.p[q] = reinterpret_cast<const float*>((uintptr_t) x.mexp_ptr);
+		else {
+			if (L.mexp_mapped[q]) { cudaIpcCloseMemHandle(L.mexp_mapped[q]); L.mexp_mapped[q] = nullptr; }
+			void* p = nullptr;
+			const cudaError_t e = cudaIpcOpenMemHandle(&p, x.mexp_handle, cudaIpcMemLazyEnablePeerAccess);
+			if (e != cudaSuccess) { set_error(std::string("cudaIpcOpenMemHandle (multipoles of rank ") + std::to_string(q) + "): " + cudaGetErrorString(e)); return NBODY_ERR_CUDA; }
+			L.mexp_mapped[q] = p;
+			L.peer_mexp.p[q] = static_cast<const float*>(p);
+		}
+		L.mexp_seen[q] = x.mexp_gen;
+	}
 	return ensure_import_room(s, L.imp_total, L.nodes[L.rank]);
 }
 
@@ -507,7 +595,7 @@ int stage3(Sim& s, bool retry) {
 	cudaStream_t st = s.stream;
 	if (retry) {
 		k_reset_lists<<<kNumSM * 4, 256, 0, st>>>(s.ctrl, s.p2p_head);
-		if (!(s.cfg.flags & NBODY_FLAG_DIRECT)) launch_upsweep(s);  // P2M also clears the local expansions the failed attempt accumulated into
+		launch_upsweep(s);  // P2M also clears the local expansions the failed attempt accumulated into
 		NB_CUDA_CHECK(cudaMemsetAsync(L.imp_hoff, 0, ((size_t) L.imp_total + 1) * 4, st));
 	} else {
 		k_let_fixup<<<grid_of((uint64_t) L.imp_total + 1, 256), 256, 0, st>>>(L.imp, s.max_nodes, L.imp_total, s.info, s.nbegin, L.imp_rbegin, L.imp_hoff);
@@ -525,6 +613,13 @@ int stage3(Sim& s, bool retry) {
 	launch_exclusive_scan(s, L.imp_hoff, L.imp_total + 1);
 	k_let_fetch<<<kNumSM * 8, 256, 0, st>>>(s.ctrl, s.let_ctrl, L.peer, L.imp, L.imp_total, L.imp_hoff, L.imp_rbegin, s.posq[1], halo_base, halo_cap);
 	k_let_translate<<<kNumSM * 8, 256, 0, st>>>(s.ctrl, s.pools.p2p_cap, s.pools.p2p, L.imp_hoff, halo_base);
+	// ... and the multipoles: which imported nodes do the M2L lists name -> fetch orders 0..P-1 of exactly those from their owners
+	if (L.imp_total) {
+		const int ms4 = coef_stride((int) s.cfg.order - 1) / 4;
+		NB_CUDA_CHECK(cudaMemsetAsync(L.imp_mflag, 0, (size_t) L.imp_total * 4, st));
+		k_let_mark_m<<<kNumSM * 8, 256, 0, st>>>(s.ctrl, s.pools.m2l_cap, s.pools.m2l_id, s.max_nodes, L.imp_total, L.imp_mflag);
+		k_let_fetch_m<<<kNumSM * 8, 256, 0, st>>>(s.ctrl, L.peer_mexp, L.imp, L.imp_total, L.imp_mflag, reinterpret_cast<float4*>(s.Mimp), ms4);
+	}
 	NB_CUDA_CHECK(cudaEventRecord(L.ev[6], st));
 	launch_m2l(s);
 	NB_CUDA_CHECK(cudaEventRecord(L.ev[7], st));
@@ -558,7 +653,8 @@ void fill_stats(Sim& s) {
 	t.near_entries = c.stat_near; t.device_bytes = s.device_bytes;
 	auto ms = [&](int a, int b) { float v = 0; cudaEventElapsedTime(&v, L.ev[a], L.ev[b]); return v; };
 	t.ms_sort = ms(0, 1); t.ms_tree = ms(1, 2); t.ms_upsweep = ms(2, 3); t.ms_traverse = ms(4, 5); t.ms_m2l = ms(6, 7); t.ms_l2l = ms(7, 8);
-	t.ms_leaf = ms(8, 9); t.ms_comm = ms(3, 4) + ms(5, 6) + ms(9, 10); t.ms_total = ms(0, 10);
+	t.ms_leaf = ms(8, 9); t.ms_import = ms(3, 4); t.ms_halo = ms(5, 6); t.ms_balance = ms(9, 10);
+	t.ms_comm = t.ms_import + t.ms_halo + t.ms_balance; t.ms_total = ms(0, 10);
 	float mx = 0.0f, sum = 0.0f;
 	for (int q = 0; q < L.world; ++q) { const float w = (float) L.xhost[q].own_ns * 1e-6f; mx = std::max(mx, w); sum += w; }
 	t.work_imbalance = sum > 0.0f ? mx * L.world / sum - 1.0f : 0.0f;
@@ -734,6 +830,10 @@ void let_destroy(Sim& s) {
 	if (s.let_ctrl) cudaFree(s.let_ctrl);
 	if (L->imp_rbegin) cudaFree(L->imp_rbegin);
 	if (L->imp_hoff) cudaFree(L->imp_hoff);
+	if (L->imp_mflag) cudaFree(L->imp_mflag);
+	if (s.Mimp) { cudaFree(s.Mimp); s.Mimp = nullptr; }
+	for (void* p : L->mexp_mapped) if (p) cudaIpcCloseMemHandle(p);
+	if (L->mexp) cudaFree(L->mexp);
 	for (auto& e : L->ev) if (e) cudaEventDestroy(e);
 	if (L->virt && L->rank != 0) s.stream = nullptr;  // the group's stream belongs to member 0
 	delete L;
@@ -750,13 +850,16 @@ int let_step(Sim& s) {
 static void let_room(const nbody_cuda_config* cfg, uint64_t n_global, int world, uint64_t n_local, uint64_t* cap, uint64_t* halo) {
 	const double sc = cfg->pool_scale > 0 ? cfg->pool_scale : 1.0;
 	const uint64_t share = (n_global + world - 1) / world;
-	*cap = std::max<uint64_t>(n_local, (uint64_t) (sc * 1.5 * (double) share)) + 4096;
-	*halo = world > 1 ? (uint64_t) (sc * 2.0 * (double) share) + 262144 : 16;
+	// automatic slack: 50 % up to 2^24 particles per rank, shrinking above (a large rank's share moves by a smaller fraction per step)
+	const double slack = cfg->partition_slack_pct ? 0.01 * cfg->partition_slack_pct : 0.5 * std::min(1.0, 16777216.0 / (double) std::max<uint64_t>(share, 1));
+	*cap = std::max<uint64_t>(n_local, (uint64_t) (sc * (1.0 + slack) * (double) share)) + 4096;
+	*halo = world > 1 ? (uint64_t) (sc * std::min(2.0, 4.0 * (slack + 0.05)) * (double) share) + 262144 : 16;
 }
 
 int let_create_distributed(const nbody_cuda_config* cfg, const nbody_particle* local_particles, uint64_t n_local, uint64_t n_global,
                            uint64_t global_offset, int rank, int world, const uint8_t* id, nbody_cuda_sim** out) {
 	if (n_global > 0xfffffff0ull) { set_error("particle identities are 32-bit: at most 2^32-16 particles in total"); return NBODY_ERR_INVALID; }
+	if (cfg->flags & NBODY_FLAG_DIRECT) { set_error("NBODY_FLAG_DIRECT (all-pairs validation path) is not available in partitioned mode"); return NBODY_ERR_INVALID; }
 	uint64_t cap = 0, halo = 0;
 	let_room(cfg, n_global, world, n_local, &cap, &halo);
 	if (cap + halo >= 0x7ffffff0ull) { set_error("partitioned mode: more than 2^31 particles (own + halo) on one rank"); return NBODY_ERR_INVALID; }
@@ -828,6 +931,7 @@ extern "C" {
 int nbody_cuda_create_group(const nbody_cuda_config* cfg, const nbody_particle* particles, uint64_t n, int world, nbody_cuda_sim** sims_out) {
 	if (!cfg || !particles || !sims_out) { set_error("NULL argument"); return NBODY_ERR_INVALID; }
 	if (world < 1 || world > kMaxRanks) { set_error("bad world size (1..16 ranks)"); return NBODY_ERR_INVALID; }
+	if (cfg->flags & NBODY_FLAG_DIRECT) { set_error("NBODY_FLAG_DIRECT (all-pairs validation path) is not available in partitioned mode"); return NBODY_ERR_INVALID; }
 	for (int r = 0; r < world; ++r) sims_out[r] = nullptr;
 	Sim* m[kMaxRanks] = {};
 	auto fail = [&](int code) { for (int r = world - 1; r >= 0; --r) if (m[r]) release(m[r]); return code; };

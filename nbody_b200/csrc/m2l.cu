@@ -81,7 +81,7 @@ template <int P, int NT>
 __global__ void __launch_bounds__(NT == 8 ? 256 : 32, NT == 8 ? 2 : 16)
 k_m2l(Ctrl* __restrict__ c, const Group* __restrict__ items, uint32_t items_cap, const float4* __restrict__ geom,
       const float* __restrict__ M, float* __restrict__ L, const uint32_t* __restrict__ m2l_id, const uint8_t* __restrict__ m2l_mask,
-      const uint8_t* __restrict__ m2l_mask_lo, float eps2) {
+      const uint8_t* __restrict__ m2l_mask_lo, float eps2, uint32_t imp_base, const float* __restrict__ Mimp) {
 	using E = Expansion<P>;
 	using SH = M2LShared<P, NT>;
 	constexpr int CH = SH::CH;
@@ -95,6 +95,9 @@ k_m2l(Ctrl* __restrict__ c, const Group* __restrict__ items, uint32_t items_cap,
 	const unsigned lt_mask = (1u << lane) - 1u;
 	const uint32_t n_items = min(c->items_count[NT == 8 ? 0 : 1], items_cap);
 	const float4* M4 = reinterpret_cast<const float4*>(M);
+	// partitioned mode: ids >= imp_base are nodes of other ranks' trees; the multipoles the lists name were fetched from their owners
+	// into Mimp, MS floats (orders 0..P-1, all a field-only M2L reads) per imported node (let.cu)
+	const float4* Mi4 = reinterpret_cast<const float4*>(Mimp);
 	for (;;) {
 		__syncthreads();  // everyone is done with the previous item (and with S.item)
 		if (tid == 0) S.item = atomicAdd(&c->work_ticket[NT == 8 ? 0 : 1], 1u);
@@ -125,7 +128,10 @@ k_m2l(Ctrl* __restrict__ c, const Group* __restrict__ items, uint32_t items_cap,
 #pragma unroll
 			for (int r = 0; r < MS4; ++r) {
 				const uint32_t piece = tid + r * CH, slot = piece / MS4, j = piece - slot * MS4;
-				if (slot < ns) cp_async16(dst + piece, M4 + (size_t) ids[slot] * S4 + j);
+				if (slot < ns) {
+					const uint32_t id = ids[slot];
+					cp_async16(dst + piece, id < imp_base ? M4 + (size_t) id * S4 + j : Mi4 + (size_t) (id - imp_base) * MS4 + j);
+				}
 			}
 			if (tid < ns) cp_async16(&S.sgeom[buf][tid], geom + ids[tid]);
 			cp_async_commit();
@@ -270,10 +276,11 @@ static void m2l_t(Sim& s) {
 	const float eps2 = s.cfg.softening * s.cfg.softening;
 	cudaFuncSetAttribute(k_m2l<P, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(M2LShared<P, 8>));
 	cudaFuncSetAttribute(k_m2l<P, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(M2LShared<P, 1>));
+	const uint32_t imp_base = s.let ? s.max_nodes : 0xffffffffu;
 	k_m2l<P, 8><<<kNumSM * 2, 256, sizeof(M2LShared<P, 8>), s.stream>>>(s.ctrl, s.pools.items[0], s.pools.items_cap, s.geom, s.M, s.L,
-	                                                                  s.pools.m2l_id, s.pools.m2l_mask, s.pools.m2l_mask_lo, eps2);
+	                                                                  s.pools.m2l_id, s.pools.m2l_mask, s.pools.m2l_mask_lo, eps2, imp_base, s.Mimp);
 	k_m2l<P, 1><<<kNumSM * 16, 32, sizeof(M2LShared<P, 1>), s.stream>>>(s.ctrl, s.pools.items[1], s.pools.items_cap, s.geom, s.M, s.L,
-	                                                                  s.pools.m2l_id, s.pools.m2l_mask, s.pools.m2l_mask_lo, eps2);
+	                                                                  s.pools.m2l_id, s.pools.m2l_mask, s.pools.m2l_mask_lo, eps2, imp_base, s.Mimp);
 }
 template <int P>
 static void l2l_t(Sim& s) {

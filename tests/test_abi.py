@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts():
     assert C.sizeof(nbody_b200.Config) == 4 + 16 + 4 * 4 + 4 * 6 + 4 + 7 * 4   # 92 bytes, mirrors nbody_cuda_config
-    assert C.sizeof(nbody_b200.Stats) == 12 * 8 + 10 * 4 + 3 * 8
+    assert C.sizeof(nbody_b200.Stats) == 12 * 8 + 10 * 4 + 3 * 8 + 4 * 4
     cfg = nbody_b200.default_config()
     assert cfg.abi_version == 1 and cfg.leaf_capacity == 8 and cfg.order == 4 and cfg.max_depth == 21
     assert abs(cfg.softening - 0.01) < 1e-9 and abs(cfg.mac_ratio - 0.5) < 1e-9 and cfg.force_constant == 1.0
