@@ -95,7 +95,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -103,7 +103,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append([time.perf_counter()] + [x.strip() for x in line.split(",")])
+
+    def mark(self):
+        """Start of the timed region: samples before this were taken under the (identical) warm-up load."""
+        self.t_mark = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
@@ -113,18 +117,23 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        t_mark = getattr(self, "t_mark", 0.0)
+        timed = [r for r in self.rows if r[0] >= t_mark]
+        # a timed region of a few steps at 8 GPUs lasts ~0.1 s: when it holds fewer than 3 samples, the samples of the warm-up steps
+        # (the same step, the same load, immediately before) are used as well, and the line says so
+        use, window = (timed, "timed region") if len(timed) >= 3 else (self.rows, "warm-up + timed region (timed region too short for 3 samples)")
+        sm, mx, reasons = [], [], set()
+        for r in use:
             try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
+                sm.append(float(r[1])); mx.append(float(r[2]))
                 for k, nm in enumerate(names):
-                    if r[3 + k].lower().startswith("active"):
+                    if r[4 + k].lower().startswith("active"):
                         reasons.add(nm)
             except Exception:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "samples_in_timed_region": len(timed), "window": window, "reasons": sorted(reasons)}
 
 
 def reference_arm(args, rank, emit):
@@ -267,11 +276,14 @@ def main():
 
     def timed_steps(sim, warm, k, sampler=None):
         """`warm` untimed steps, then exactly k steps between barriers; returns (seconds [max over ranks], per-step stage ms, counts)."""
+        if sampler is not None:
+            sampler.start()
+            time.sleep(0.4)  # nvidia-smi needs a moment to produce its first sample
         for _ in range(warm):
             sim.step()
         barrier()
         if sampler is not None:
-            sampler.start()
+            sampler.mark()
         sums, cnts, imb = {}, {}, []
         t0 = time.perf_counter()
         for _ in range(k):
@@ -297,6 +309,14 @@ def main():
     sampler = ClockSampler(local_rank)
     elapsed, stage_ms, counts = timed_steps(sim, max(args.warmup, 3), args.steps, sampler)
     clocks = sampler.stop()
+    if world > 1:  # every rank samples its own GPU: eight GPUs under load at once need not hold the clock one GPU holds alone
+        allc = [None] * world
+        dist.all_gather_object(allc, {"sm_mhz": clocks["sm_mhz"], "samples": clocks["samples"], "reasons": clocks["reasons"]})
+        clocks["per_rank"] = allc
+        known = [c["sm_mhz"] for c in allc if c["sm_mhz"] is not None]
+        if known:
+            clocks["sm_mhz_min_over_ranks"] = min(known)
+        clocks["reasons"] = sorted(set(r for c in allc for r in c["reasons"]))
     value = n * args.steps / elapsed
     K = args.steps
     rank_ms = None
@@ -433,7 +453,7 @@ def main():
                        "partition": ("morton-range, partitioned state + locally essential tree" if partitioned else
                                      "morton-range, replicated state" if world > 1 else "single"), "flags": base_flags,
                        "library": os.path.basename(nbody_b200.LIB_PATH)},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": K * launches_per_step(sim, world),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": K * launches_per_step(sim, world, counts.get("n_levels"), partitioned),
             "roofline": roof,
             "p2p_fp32_tflops": {"tree_p2p_kernel": p2p_tf, "tree_p2p_frac_of_peak": p2p_tf / peak,
                                 "all_pairs_kernel": p2p_micro["tflops"], "all_pairs_frac_of_peak": p2p_micro["tflops"] / peak,
@@ -536,18 +556,28 @@ def config1_ours(args, local_rank):
             "note": "the FMM path at the library defaults (capacity 8, order 4); compare with config1 of --impl reference"}
 
 
-def launches_per_step(sim, world):
-    """Kernels of ours launched by one step() (matches the ncu launch lists under profiles/: 174 on one GPU at max_depth 21)."""
+def launches_per_step(sim, world, n_levels=None, partitioned=False):
+    """Kernels of ours launched by one step() (matches the ncu launch list profiles/r02*_launches_*.csv: 121 on one GPU for a tree of
+    12 levels). The level loops run to last step's depth + 1, bounded by max_depth."""
     d = int(sim.config.max_depth)
+    b = min(d, int(n_levels)) if n_levels else d
     sort = 8 * 5                 # per 8-bit pass: histogram, three scan kernels, scatter
-    if world > 1 and (int(sim.config.flags) & 64):
-        sort += 2 * (world - 1).bit_length()   # NBODY_FLAG_DIST_SORT: the same passes over the rank's slice, then log2(world) merge rounds of two kernels
-    tree = 1 + 2 * d             # init, per level (count, split)
-    upsweep = 1 + d              # P2M, per level M2M
-    traversal = 1 + 2 * d        # init, per round (prep, traverse)
-    far = 2 + d                  # two M2L launches, per level L2L
-    multi = 2 if world > 1 else 0  # partition snap, velocity half of the gather
-    return 1 + sort + 1 + tree + upsweep + traversal + far + 1 + multi   # + keys, gather, leaf kernel
+    tree = 1 + 2 * b + (1 if b < d else 0)   # init, per level (count, split), the depth check
+    upsweep = 1 + b              # P2M, per level M2M
+    traversal = 1 + 2 * b        # init, per round (prep, traverse)
+    far = 2 + b                  # two M2L launches, per level L2L
+    base = 1 + sort + 1 + tree + upsweep + traversal + far + 1   # + keys, gather, leaf kernel
+    if world == 1:
+        return base
+    if partitioned:
+        merge = 2 * (world - 1).bit_length()
+        # cuts, pull, keys, merge rounds, straddle, force, gather, export pack, publish, fix-up, 2 stamps, halo (mark, 3 scan kernels,
+        # fetch, translate), multipole mark + fetch, finish, rebalance, adopt
+        return base + 1 + 1 + 1 + merge + 1 + 1 + 1 + 1 + 1 + 1 + 2 + 6 + 2 + 1 + 1 + 1
+    multi = 2                    # partition snap, velocity half of the gather
+    if int(sim.config.flags) & 64:
+        multi += 2 * (world - 1).bit_length()   # NBODY_FLAG_DIST_SORT: merge rounds of two kernels
+    return base + multi
 
 
 def cpu_baseline(args):

@@ -40,6 +40,8 @@ void dev_free(Sim& s, T*& p, size_t count) {
 	if (p) { cudaFree(p); s.device_bytes -= std::max<size_t>(count, 1) * sizeof(T); p = nullptr; }
 }
 
+uint64_t clamp32(double v) { return (uint64_t) std::min(v, 4294967295.0); }
+
 // Source-side arrays (geometry, child / count record, first particle: what the traversal reads of a node as a SOURCE) have room for
 // `src_nodes` >= max_nodes entries: in partitioned mode the other ranks' trees are imported behind the own tree. Expansions and
 // everything a node carries as a TARGET (list heads, parent, key) exist for the own tree only.
@@ -94,7 +96,6 @@ PoolPlan current_plan(const Sim& s) {
 	return PoolPlan{p.near_cap, p.p2p_cap, p.m2l_cap, p.seg_cap, p.gq_cap, p.items_cap};
 }
 
-uint64_t clamp32(double v) { return (uint64_t) std::min(v, 4294967295.0); }
 
 void free_all(Sim* s) {
 	if (!s) return;
@@ -146,24 +147,26 @@ int run_pipeline(Sim& s, bool retry) {
 	cudaStream_t st = s.stream;
 	const bool direct = (s.cfg.flags & NBODY_FLAG_DIRECT) != 0;
 	const bool keep_sort = retry && s.comm && (s.cfg.flags & NBODY_FLAG_DIST_SORT) && !(s.cfg.flags & NBODY_FLAG_CUB_SORT);
+	NvtxRange step_range("nbody step");
 	NB_CUDA_CHECK(cudaEventRecord(s.ev[0], st));
-	int rc = keep_sort ? NBODY_OK : launch_keys_sort_permute(s);
+	int rc = NBODY_OK;
+	{ NvtxRange r("keys + sort + gather"); rc = keep_sort ? NBODY_OK : launch_keys_sort_permute(s); }
 	if (rc) return rc;
 	NB_CUDA_CHECK(cudaEventRecord(s.ev[1], st));
-	launch_tree_build(s);
+	{ NvtxRange r("octree build"); launch_tree_build(s); }
 	NB_CUDA_CHECK(cudaEventRecord(s.ev[2], st));
 	if (s.comm && (rc = comm_partition(s))) return rc;
 	if (!direct) {
-		launch_upsweep(s);
+		{ NvtxRange r("P2M + M2M"); launch_upsweep(s); }
 		NB_CUDA_CHECK(cudaEventRecord(s.ev[3], st));
-		launch_traversal(s);
+		{ NvtxRange r("dual-tree traversal"); launch_traversal(s); }
 		NB_CUDA_CHECK(cudaEventRecord(s.ev[4], st));
-		launch_m2l(s);
+		{ NvtxRange r("M2L"); launch_m2l(s); }
 		NB_CUDA_CHECK(cudaEventRecord(s.ev[5], st));
-		launch_l2l(s);
+		{ NvtxRange r("L2L"); launch_l2l(s); }
 		if (s.comm) { if ((rc = comm_wait_velocities(s))) return rc; launch_gather_velocities(s); }
 		NB_CUDA_CHECK(cudaEventRecord(s.ev[6], st));
-		launch_leaf(s);
+		{ NvtxRange r("P2P + L2P + integrator"); launch_leaf(s); }
 	} else {
 		for (int k = 3; k <= 5; ++k) NB_CUDA_CHECK(cudaEventRecord(s.ev[k], st));
 		if (s.comm) { if ((rc = comm_wait_velocities(s))) return rc; launch_gather_velocities(s); }

@@ -6,6 +6,8 @@
 #include <cstdio>
 #include <string>
 
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX 3: the ranges cost nothing unless a tool (nsys, ncu --nvtx) is attached
+
 #include "../../include/nbody_cuda.h"
 #include "expansion.cuh"
 
@@ -155,6 +157,14 @@ struct Sim {
 	uint64_t device_bytes = 0;
 	bool lists_valid = false;
 	bool acc_partial = false;  // distributed: `acc` holds only this rank's slice until comm_exchange_acc()
+};
+
+// ---- tracing hook: one NVTX range per stage of a step, around the stage's launches -------------------------
+struct NvtxRange {
+	explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+	~NvtxRange() { nvtxRangePop(); }
+	NvtxRange(const NvtxRange&) = delete;
+	NvtxRange& operator=(const NvtxRange&) = delete;
 };
 
 // ---- error plumbing ---------------------------------------------------------

@@ -425,6 +425,7 @@ int ensure_import_room(Sim& s, uint32_t need, uint32_t own_nodes) {
 // X3, second half: every rank's tree as the traversal reads it (geometry, child/count record, first particle: 28 bytes per node) lands
 // behind the own tree. The multipoles do not travel here: after the traversal each rank fetches exactly the ones its M2L lists name.
 int exchange_trees(Sim** m, int nm) {
+	NvtxRange r("partitioned: all-gather of the trees");
 	Let& L0 = *m[0]->let;
 	const int W = L0.world;
 	if (L0.virt) {
@@ -461,6 +462,7 @@ int exchange_trees(Sim** m, int nm) {
 // phases (each enqueues on the member's stream; the driver below places the exchanges between them)
 // ---------------------------------------------------------------------------------------------------------------------------
 int phase1(Sim& s) {
+	NvtxRange r("partitioned: keys + sort + cuts");
 	Let& L = *s.let;
 	NB_CUDA_CHECK(cudaEventRecord(L.ev[0], s.stream));
 	launch_keys(s, s.posq[0], s.n);
@@ -471,6 +473,7 @@ int phase1(Sim& s) {
 }
 
 int phase2a(Sim& s) {
+	NvtxRange nvtx("partitioned: pull migrants + merge");
 	Let& L = *s.let;
 	const int W = L.world, r = L.rank;
 	PullArgs pa{};
@@ -532,6 +535,7 @@ int ensure_export(Sim& s) {
 }
 
 int build_tree(Sim& s) {
+	NvtxRange r("partitioned: octree + upsweep + export");
 	Let& L = *s.let;
 	NB_CUDA_CHECK(cudaEventRecord(L.ev[1], s.stream));
 	launch_tree_build(s);
@@ -590,6 +594,7 @@ int plan_import(Sim& s) {
 }
 
 int stage3(Sim& s, bool retry) {
+	NvtxRange r("partitioned: traversal + halo + M2L + L2L + P2P");
 	Let& L = *s.let;
 	const int W = L.world;
 	cudaStream_t st = s.stream;
