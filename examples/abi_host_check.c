@@ -38,6 +38,9 @@ int main(int argc, char** argv) {
 
 	nbody_cuda_default_config(&cfg);
 	CHECK(cfg.abi_version == NBODY_CUDA_ABI_VERSION && cfg.leaf_capacity == 8 && cfg.order == 4 && cfg.max_depth == 21);
+	nbody_cuda_tuned_config(&cfg);
+	CHECK(cfg.abi_version == NBODY_CUDA_ABI_VERSION && cfg.leaf_capacity == 48 && cfg.order == 4 && cfg.mac_ratio == 0.5f);
+	nbody_cuda_default_config(&cfg);
 	CHECK(cfg.time_step == 0.001f && cfg.softening == 0.01f && cfg.mac_ratio == 0.5f && cfg.time_step_eta == 0.0f);
 
 	/* the variable-time-step rule: off by default, eta * sqrt(softening / a_max) clamped otherwise */

@@ -49,12 +49,17 @@ class CudaSimulation final : public Simulation<device::scalar_t, device::vector_
 public:
 	// Mirrors OpenClSimulation(bounds, particles, timeStep, log); `config` (optional) overrides the
 	// reference's compile-time constants (MAC ratio, softening, capacity, ...), see nbody_cuda_config.
+	// Without `config`: the reference's constants with the B200-tuned node capacity (nbody_cuda_tuned_config: 48 instead of the
+	// reference's provisional 8; same accuracy, 2.7x the speed). Pass nbody_cuda_default_config() for capacity 8.
+	// NOTE on the integrator: the default is kick-drift (x += v_new dt), NaiveSimulation's rule (src/naive_simulation.cpp:28-42);
+	// OpenClSimulation integrates x += v_old dt (src/open_cl_simulation.cpp:602-607): set config->integrator = NBODY_EXPLICIT_EULER
+	// to reproduce that trajectory (the two differ by a dt^2 per step).
 	CudaSimulation(device::vector_t bounds, std::vector<Particle> particles, Scalar timeStep, std::ostream& log,
 	               const nbody_cuda_config* config = nullptr)
 	    : _log(log), _time(0.0f) {
 		static_assert(sizeof(Particle) == sizeof(nbody_particle), "Particle must be the 48-byte boundary record");
 		nbody_cuda_config cfg;
-		if (config) cfg = *config; else nbody_cuda_default_config(&cfg);
+		if (config) cfg = *config; else nbody_cuda_tuned_config(&cfg);
 		for (int k = 0; k < 4; ++k) cfg.bounds[k] = bounds[k];
 		cfg.time_step = timeStep;
 		_log << "Creating the CUDA simulation (" << particles.size() << " particles).\n";
@@ -68,7 +73,9 @@ public:
 		check(nbody_cuda_checkpoint_load(checkpointPath.c_str(), config, &_sim));
 		check(nbody_cuda_get_time(_sim, &_time, nullptr));
 	}
-	// One rank of a multi-GPU run (one process or thread per GPU, Morton-range partition, NCCL):
+	// One rank of a multi-GPU run (one process per GPU, Morton-range partition). Without `config`: the
+	// partitioned scheme (NBODY_FLAG_PARTITIONED: the rank holds only its own particles and imports a locally essential tree;
+	// particles() / permutation() then return THIS rank's particles, in tree order; ranks in rank order = the global tree order).
 	// `particles` is THIS rank's contiguous slice of the global set, `globalOffset` the index of its first particle and
 	// `uniqueId` the 128 bytes nbody_cuda_comm_unique_id() returned on rank 0. Collective: every rank constructs at once.
 	CudaSimulation(device::vector_t bounds, std::vector<Particle> particles, Scalar timeStep, std::ostream& log,
@@ -76,7 +83,7 @@ public:
 	               const nbody_cuda_config* config = nullptr)
 	    : _log(log), _time(0.0f) {
 		nbody_cuda_config cfg;
-		if (config) cfg = *config; else nbody_cuda_default_config(&cfg);
+		if (config) cfg = *config; else { nbody_cuda_tuned_config(&cfg); cfg.flags |= NBODY_FLAG_PARTITIONED; }
 		for (int k = 0; k < 4; ++k) cfg.bounds[k] = bounds[k];
 		cfg.time_step = timeStep;
 		_log << "Creating rank " << rank << " of " << world << " of the CUDA simulation (" << particles.size() << " of " << globalCount << " particles).\n";
@@ -110,8 +117,8 @@ public:
 		return p;
 	}
 
-	// Multi-GPU: the slice [first, first + count) of the tree-ordered particle array this rank owns after the last step, and
-	// just those particles (particles() returns the whole, replicated state on every rank).
+	// Multi-GPU: the slice [first, first + count) of the global tree-ordered particle array this rank owns after the last step, and
+	// just those particles (partitioned scheme: the same as particles(); replicated scheme: particles() returns the whole state).
 	void ownedRange(std::uint64_t& first, std::uint64_t& count) const { check(nbody_cuda_owned_range(_sim, &first, &count)); }
 	std::vector<Particle> ownedParticles() const {
 		std::uint64_t first = 0, count = 0;

@@ -22,7 +22,7 @@ FLAG_KEEP_LISTS, FLAG_NO_INTEGRATE, FLAG_DIRECT, FLAG_CUB_SORT, FLAG_STATIC_PART
 FLAG_PARTITIONED = 128
 
 EXPORTED_SYMBOLS = [
-    "nbody_cuda_default_config", "nbody_cuda_create", "nbody_cuda_destroy", "nbody_cuda_set_particles", "nbody_cuda_step",
+    "nbody_cuda_default_config", "nbody_cuda_tuned_config", "nbody_cuda_create", "nbody_cuda_destroy", "nbody_cuda_set_particles", "nbody_cuda_step",
     "nbody_cuda_num_particles", "nbody_cuda_get_particles", "nbody_cuda_get_permutation", "nbody_cuda_get_accelerations",
     "nbody_cuda_get_keys", "nbody_cuda_get_tree", "nbody_cuda_get_lists", "nbody_cuda_get_expansions", "nbody_cuda_get_stats",
     "nbody_cuda_direct_field", "nbody_cuda_sort_runs", "nbody_cuda_comm_unique_id", "nbody_cuda_create_distributed", "nbody_cuda_owned_range",
@@ -87,6 +87,8 @@ def load_library():
     vp, u64, u32 = C.c_void_p, C.c_uint64, C.c_uint32
     L.nbody_cuda_default_config.argtypes = [C.POINTER(Config)]
     L.nbody_cuda_default_config.restype = None
+    L.nbody_cuda_tuned_config.argtypes = [C.POINTER(Config)]
+    L.nbody_cuda_tuned_config.restype = None
     L.nbody_cuda_create.argtypes = [C.POINTER(Config), vp, u64, C.POINTER(vp)]
     L.nbody_cuda_destroy.argtypes = [vp]
     L.nbody_cuda_destroy.restype = None

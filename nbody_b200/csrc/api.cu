@@ -352,6 +352,11 @@ void nbody_cuda_default_config(nbody_cuda_config* cfg) {
 	cfg->low_order_tau = 0.13f;
 }
 
+void nbody_cuda_tuned_config(nbody_cuda_config* cfg) {
+	nbody_cuda_default_config(cfg);
+	cfg->leaf_capacity = 48;
+}
+
 int nbody_cuda_create(const nbody_cuda_config* cfg, const nbody_particle* particles, uint64_t n, nbody_cuda_sim** out) {
 	if (!out || !particles) { set_error("NULL argument"); return NBODY_ERR_INVALID; }
 	*out = nullptr;

@@ -35,6 +35,26 @@ def test_cpp_driver_runs_and_writes_reference_style_csv(tmp_path, driver_exe):
     assert "M2L" in r.stdout
 
 
+@pytest.mark.parametrize("distribution", ["plummer", "two-galaxies"])
+def test_cpp_driver_distributions(tmp_path, driver_exe, distribution):
+    """--distribution: the clustered models of BASELINE configs 3 and 4 from the C++ driver, at the reference's
+    node capacity (--capacity 8) and at the wrapper's tuned default."""
+    for extra in ([], ["--capacity", "8"]):
+        csv = str(tmp_path / f"p{len(extra)}.csv")
+        r = subprocess.run([driver_exe, "--n", "30000", "--steps", "2", "--csv", csv, "--csv-max", "30000", "--quiet", "--distribution", distribution] + extra,
+                           capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stderr
+        rows = np.array([[float(v) for v in line.split(",")] for line in open(csv).read().strip().splitlines()])
+        xyz = rows[:, 1:].reshape(2, -1, 3)
+        assert xyz.shape[1] == 30000 and np.all(np.isfinite(xyz)) and xyz.min() > 0.0 and xyz.max() < 1.0
+        centre = xyz[0].mean(axis=0)
+        assert np.abs(centre - 0.5).max() < 0.02                      # both models are centred in the box
+        spread_x = xyz[0][:, 0].std()
+        assert (spread_x > 0.15) == (distribution == "two-galaxies")  # two clumps at x = 0.3 / 0.7 against one at 0.5
+    r = subprocess.run([driver_exe, "--distribution", "ring"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 2 and "unknown distribution" in r.stderr
+
+
 def test_cpp_driver_checkpoint_restart_and_variable_step(tmp_path, driver_exe):
     def rows(path):
         return np.array([[float(v) for v in line.split(",")] for line in open(path).read().strip().splitlines()])

@@ -338,9 +338,7 @@ def test_full_size_plummer_16m_properties():
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("NBODY_TEST_EXPERIMENTAL") != "1", reason="distributed-sort kernels have not run on hardware yet: "
-                    "set NBODY_TEST_EXPERIMENTAL=1 (tools/gpu_call_r02a.sh does); becomes unconditional once it has passed on a B200")
-@pytest.mark.parametrize("n,nruns", [(1, 1), (5000, 2), (70001, 3), (300000, 8), (1 << 21, 16)])
+@pytest.mark.parametrize("n,nruns", [(1, 1), (5000, 2), (70001, 3), (300000, 8), (1 << 21, 16)])  # (first green on a B200: profiles/r02a_call.log)
 def test_distributed_sort_pipeline_equals_stable_sort(n, nruns):
     """nbody_cuda_sort_runs = what NBODY_FLAG_DIST_SORT does on the device (slice radix sorts + pairwise merge rounds), on one GPU:
     the stable sort of all keys for any boundaries — the oracle's std::stable_sort, ties included."""
