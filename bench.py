@@ -235,6 +235,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_cpus(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -452,7 +453,7 @@ def main():
                        "integrator": "kick-drift", "l2_policy": "working set (>1 GB of lists and particle state per step) exceeds the 126 MB L2",
                        "partition": ("morton-range, partitioned state + locally essential tree" if partitioned else
                                      "morton-range, replicated state" if world > 1 else "single"), "flags": base_flags,
-                       "library": os.path.basename(nbody_b200.LIB_PATH)},
+                       "library": os.path.basename(nbody_b200.LIB_PATH), "cpu_binding": numa},
             "clocks": clocks, "e2e": e2e, "gpu_launches": K * launches_per_step(sim, world, counts.get("n_levels"), partitioned),
             "roofline": roof,
             "p2p_fp32_tflops": {"tree_p2p_kernel": p2p_tf, "tree_p2p_frac_of_peak": p2p_tf / peak,
@@ -475,6 +476,24 @@ def main():
             raise SystemExit(f"accuracy check failed: RMS relative error {accuracy['rms_rel']:.3e} > 1e-3")
         if multi_check is not None and not multi_check["pass"]:
             raise SystemExit(f"multi-GPU check failed: {multi_check}")
+
+
+def bind_to_gpu_cpus(index):
+    """One process per GPU: run on the CPU cores NVML reports as local to this GPU, so that the pinned staging buffers of the
+    end-to-end leg (first touch) live on the GPU's own NUMA node — what any MPI launcher's rank binding does; torchrun does not."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if word >> b & 1]
+        cpus = [c for c in cpus if c in os.sched_getaffinity(0)]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return {"cpus": f"{cpus[0]}-{cpus[-1]}", "count": len(cpus)}
+    except Exception as e:  # no NVML, no permission: run unbound
+        return {"unbound": str(e)[:80]}
+    return None
 
 
 def multi_gpu_check(args, rank, world, local_rank, make_sim, partitioned, dist, torch):

@@ -59,6 +59,7 @@ int alloc_nodes(Sim& s, uint32_t max_nodes, uint32_t src_nodes) {
 	if ((rc = dev_alloc(s, s.L, (size_t) max_nodes * s.nc_stride))) return rc;
 	if ((rc = dev_alloc(s, s.near_ref, max_nodes))) return rc;
 	if ((rc = dev_alloc(s, s.p2p_head, max_nodes))) return rc;
+	if ((rc = dev_alloc(s, s.leaf_items, max_nodes))) return rc;
 	return NBODY_OK;
 }
 void free_nodes(Sim& s) {
@@ -66,6 +67,7 @@ void free_nodes(Sim& s) {
 	dev_free(s, s.geom, sn); dev_free(s, s.info, sn); dev_free(s, s.nbegin, sn); dev_free(s, s.M, m * s.nc_stride);
 	dev_free(s, s.nparent, m); dev_free(s, s.nkey, m);
 	dev_free(s, s.L, m * s.nc_stride); dev_free(s, s.near_ref, m); dev_free(s, s.p2p_head, m);
+	dev_free(s, s.leaf_items, m);
 }
 
 struct PoolPlan { uint64_t near, p2p, m2l; uint32_t seg, gq, items; };

@@ -25,6 +25,7 @@ enum : uint32_t {
 	kOvfHalo = 256u    // partitioned mode: the halo particles do not fit behind the own particles
 };
 constexpr int kMaxRanks = 16;
+constexpr uint32_t kImported = 0x80000000u;  // partitioned mode: a first-particle index with this bit names an imported leaf, not a particle
 
 // One work item of the traversal / of the M2L kernel: `nt` sibling targets
 // (8 = the children of one parent, 1 = a carried childless node) that share one
@@ -58,6 +59,7 @@ struct Ctrl {
 	unsigned long long stat_m2l_inter, stat_m2l_low, stat_p2p_entries, stat_p2p_inter, stat_near, stat_leaves;
 	uint32_t work_ticket[4];             // dynamic work distribution of the persistent kernels
 	uint32_t part[kMaxRanks + 1];        // distributed: rank r owns particles [part[r], part[r+1]) of the tree-ordered array
+	uint32_t n_leaf_items;               // entries of the compacted leaf list (k_leaf_items; small trees only)
 	uint32_t acc_max2_bits;              // variable time step: bits of max |a|^2 over this rank's slice (k_acc_max; non-negative floats order like uints)
 };
 
@@ -129,6 +131,8 @@ struct Sim {
 	                             // the other ranks' trees are imported at ids [max_nodes, src_nodes))
 	int depth_bound = kMaxDepth; // the level loops of a step run to this depth (last step's depth + 1; kOvfDepth re-runs unbounded)
 	TraverseSeeds seeds;
+	uint32_t* imp_hoff = nullptr;   // partitioned mode (let.cu): per imported leaf, its particle count once a P2P list names it ...
+	uint32_t* imp_mflag = nullptr;  // ... and per imported node, whether an M2L list names it: both marked by the traversal as it writes the lists
 	int trav_bound = kMaxDepth;  // rounds of the traversal (partitioned mode: the deepest tree of any rank; otherwise depth_bound)
 	float4* geom = nullptr;      // centre xyz, dimensions.x
 	uint2* info = nullptr;       // {first child (0 = childless), particle count}
@@ -140,6 +144,7 @@ struct Sim {
 	float* Mimp = nullptr;       // partitioned mode: multipole orders 0..P-1 of the imported nodes the M2L lists name (let.cu)
 	uint2* near_ref = nullptr;   // per target node: {offset, count} of its near list in the current round's pool
 	uint32_t* p2p_head = nullptr;  // per node: head of its P2P segment chain (0xffffffff = none)
+	uint32_t* leaf_items = nullptr;  // compacted list of the slice's non-empty leaves (the leaf kernel's tickets on small trees)
 	uint32_t* scan_sums = nullptr; // kScanBlocks + 1
 
 	Pools pools;

@@ -112,6 +112,7 @@ struct LeafArgs {
 	int integrator, no_integrate;
 	int rank;                     // this rank's slice of the tree-ordered particle array: [c->part[rank], c->part[rank+1])
 	int reverse;                  // hand the leaves out from the deepest level upwards
+	const uint32_t* items;        // the non-empty leaves of the slice in node order (k_leaf_items), or nullptr: tickets are chunks of node ids
 	unsigned long long* stat_inter;
 	unsigned long long* stat_leaves;
 };
@@ -163,6 +164,30 @@ __device__ __forceinline__ void transpose_reduce16(float (&v)[16], unsigned lane
 	v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
+// The compacted leaf list for small trees: every non-empty childless node of this rank's slice, in node (level-major, Morton) order up
+// to warp granularity (one atomic per 32 nodes), so neighbouring leaves are still worked on at the same time.
+__global__ void __launch_bounds__(256) k_leaf_items(Ctrl* c, int rank, const uint2* __restrict__ info, const uint32_t* __restrict__ nbegin,
+                                                     uint32_t* __restrict__ items, uint32_t items_cap) {
+	if (c->status) return;
+	const uint32_t n_nodes = c->n_nodes, own_first = c->part[rank], own_end = c->part[rank + 1];
+	const unsigned lane = threadIdx.x & 31u;
+	const uint32_t stride = gridDim.x * blockDim.x;
+	for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n_nodes; base += stride) {
+		const uint32_t node = base + lane;
+		bool leaf = false;
+		if (node < n_nodes) {
+			const uint2 nf = info[node];
+			const uint32_t b = nbegin[node];
+			leaf = nf.x == 0u && nf.y != 0u && b >= own_first && b < own_end;
+		}
+		const unsigned m = __ballot_sync(0xffffffffu, leaf);
+		uint32_t at = 0;
+		if (lane == 0 && m) at = atomicAdd(&c->n_leaf_items, (uint32_t) __popc(m));
+		at = __shfl_sync(0xffffffffu, at, 0) + __popc(m & ((1u << lane) - 1u));
+		if (leaf && at < items_cap) items[at] = node;
+	}
+}
+
 // Leaves are handed out kLeafChunk node ids at a time by an atomic ticket, so the grid is exactly the resident set.
 // A leaf's source list is a chain of segments of {first particle, count} entries. The sources stream through two
 // 256-particle tiles per warp: the flat particle range of up to 32 entries (one per lane) is cut at exactly one
@@ -190,16 +215,16 @@ __global__ void __launch_bounds__(kLeafWarps * 32, kLeafMinCtas) k_leaf(const Le
 	__syncwarp();
 #endif
 	if (a.c->status) return;  // a pool overflowed: the host grows it and re-runs the step; leave the state untouched
-	const uint32_t n_nodes = a.c->n_nodes;
+	const uint32_t n_nodes = a.c->n_nodes, n_items = a.c->n_leaf_items;
 	const uint32_t own_first = a.c->part[a.rank], own_end = a.c->part[a.rank + 1];
 	const unsigned le_mask = (2u << lane) - 1u;  // bits 0..lane
 	unsigned long long inter = 0, leaves = 0;
 #pragma unroll 1
 	for (;;) {
 		uint32_t chunk = 0;
-		if (lane == 0) chunk = atomicAdd(&a.c->work_ticket[3], (uint32_t) kLeafChunk);
+		if (lane == 0) chunk = atomicAdd(&a.c->work_ticket[3], a.items ? 1u : (uint32_t) kLeafChunk);
 		chunk = __shfl_sync(0xffffffffu, chunk, 0);
-		if (chunk >= n_nodes) break;
+		if (chunk >= (a.items ? n_items : n_nodes)) break;
 		// a.reverse (developer switch NBODY_LEAF_REVERSE=1): tickets run from the END of the level-major node array, so that the deepest
 		// levels (the dense regions: full leaves, the longest source lists) start first. Measured slower both on one GPU (34.8 against
 		// 34.0 ms at 2^24) and on a rank's 1/8 share (5.28 against 5.20 ms): the kernel has no tail worth removing — run alone on one GPU,
@@ -207,9 +232,19 @@ __global__ void __launch_bounds__(kLeafWarps * 32, kLeafMinCtas) k_leaf(const Le
 		if (a.reverse) chunk = (n_nodes - 1u - chunk) & ~(uint32_t) (kLeafChunk - 1);
 		uint2 nf_l = make_uint2(1u, 0u);
 		uint32_t b_l = 0;
-		if (lane < (unsigned) kLeafChunk && chunk + lane < n_nodes) { nf_l = a.info[chunk + lane]; b_l = a.nbegin[chunk + lane]; }
-		// childless, non-empty, and inside this rank's slice
-		unsigned todo = __ballot_sync(0xffffffffu, nf_l.x == 0u && nf_l.y != 0u && b_l >= own_first && b_l < own_end);
+		unsigned todo;
+		if (a.items) {
+			// small problems (a rank's share of a multi-GPU run): one ticket = one leaf of the compacted leaf list (k_leaf_items). Chunks of
+			// 8 node ids are sibling groups, i.e. 8 neighbouring leaves of similar weight: with only ~9 such tickets per warp on a 1/8
+			// share of the benchmark the kernel ended in a long tail (4.98 ms against 4.40 ms, profiles/r02k_summary.md)
+			chunk = a.items[chunk];
+			if (lane == 0) { nf_l = a.info[chunk]; b_l = a.nbegin[chunk]; }
+			todo = 1u;
+		} else {
+			if (lane < (unsigned) kLeafChunk && chunk + lane < n_nodes) { nf_l = a.info[chunk + lane]; b_l = a.nbegin[chunk + lane]; }
+			// childless, non-empty, and inside this rank's slice
+			todo = __ballot_sync(0xffffffffu, nf_l.x == 0u && nf_l.y != 0u && b_l >= own_first && b_l < own_end);
+		}
 #pragma unroll 1
 		while (todo) {
 			const int kk = __ffs(todo) - 1;
@@ -389,6 +424,16 @@ void launch_leaf(Sim& s) {
 	a.rank = s.rank;
 	static const char* env = std::getenv("NBODY_LEAF_REVERSE");
 	a.reverse = env ? std::atoi(env) != 0 : 0;
+	// ticket granularity: leaves on small trees (fewer than 2^19 nodes at the last step: ~27 chunk tickets per warp), node chunks on
+	// large ones (where the compacted list costs 2 %: 34.8 against 34.0 ms at 2^24 on one GPU). NBODY_LEAF_ITEMS=0/1 overrides.
+	static const char* env_items = std::getenv("NBODY_LEAF_ITEMS");
+	const uint32_t last_nodes = s.steps_done ? s.ctrl_host->n_nodes : (uint32_t) (s.n / 12 + 1);
+	const bool items = env_items ? std::atoi(env_items) != 0 : last_nodes < (1u << 19);
+	a.items = nullptr;
+	if (items && !a.reverse) {
+		a.items = s.leaf_items;
+		k_leaf_items<<<kNumSM * 4, 256, 0, s.stream>>>(s.ctrl, s.rank, s.info, s.nbegin, s.leaf_items, s.max_nodes);
+	}
 	a.stat_inter = &s.ctrl->stat_p2p_inter; a.stat_leaves = &s.ctrl->stat_leaves;
 	switch (s.cfg.order) {
 		case 2: leaf_t<2>(s, a); break;

@@ -58,12 +58,12 @@ namespace {
 constexpr int kSample = 512;                 // keys per rank for the initial splitters
 constexpr uint64_t kKeyEnd = 1ull << 63;      // one past the largest Morton key
 constexpr uint64_t kNoKey = ~0ull;
-constexpr uint32_t kImported = 0x80000000u;   // tag of a first-particle index that names an imported leaf instead of a particle
 
 // What a rank publishes in the small all-gathers (one slot per rank, always sent whole).
 struct XSlot {
 	uint32_t cut[kMaxRanks + 1];               // X1: position of splitter d in this rank's sorted keys
 	uint32_t n_nodes, n_levels, status;        // X3 / X4
+	uint32_t node_cap;                         // X3: capacity of the own tree's arrays
 	uint32_t acc_max2_bits;                    // X4 (variable time step)
 	uint32_t straddle[kMaxRanks][kNumLevels];  // X2: local count of the depth-d cell that straddles splitter b
 	unsigned long long own_ns;                 // X4: device time of the stages whose cost follows the partition
@@ -115,7 +115,8 @@ struct Let {
 	uint32_t counts[kMaxRanks] = {}; // particles per rank in the current step
 	uint32_t nodes[kMaxRanks] = {};
 	ImportTable imp{};
-	uint32_t imp_total = 0;
+	uint32_t imp_total = 0, imp_slot = 0;
+	bool gather_ok = true;           // every rank's own arrays hold a whole slot: the trees travel by plain all-gather
 	uint64_t global_first = 0;
 	cudaEvent_t ev[12] = {};
 	uint64_t pulled = 0;             // particles that arrived from other ranks in the last step
@@ -177,8 +178,8 @@ __global__ void k_let_force(const XSlot* __restrict__ xb, LetCtrl* lc) {
 	}
 }
 
-__global__ void k_let_publish(const Ctrl* __restrict__ c, XSlot* slot) {
-	slot->n_nodes = c->n_nodes; slot->n_levels = c->n_levels; slot->status = c->status;
+__global__ void k_let_publish(const Ctrl* __restrict__ c, uint32_t node_cap, XSlot* slot) {
+	slot->n_nodes = c->n_nodes; slot->n_levels = c->n_levels; slot->status = c->status; slot->node_cap = node_cap;
 }
 
 // Imported trees: child pointers are relative to the owner's array -> rebase; the first-particle index is kept aside (it addresses
@@ -194,15 +195,6 @@ __global__ void k_let_fixup(const ImportTable t, uint32_t imp_base, uint32_t tot
 		if (nf.x) { nf.x += imp_base + t.off[s]; info[imp_base + i] = nf; }
 		rbegin[i] = nbegin[imp_base + i];
 		nbegin[imp_base + i] = kImported | i;
-	}
-}
-
-__global__ void k_let_mark(const Ctrl* __restrict__ c, uint64_t p2p_cap, const uint2* __restrict__ p2p, uint32_t total, uint32_t* __restrict__ hoff) {
-	if (c->status) return;  // a pool overflowed: the lists are incomplete (reserved but unwritten entries); the host grows the pool and repeats
-	const uint64_t n = c->p2p_cursor < p2p_cap ? c->p2p_cursor : p2p_cap;
-	for (uint64_t e = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; e < n; e += (uint64_t) gridDim.x * blockDim.x) {
-		const uint2 en = p2p[e];
-		if ((en.x & kImported) && (en.x & ~kImported) < total) hoff[en.x & ~kImported] = en.y;  // every writer stores the same count
 	}
 }
 
@@ -250,16 +242,6 @@ __global__ void k_let_pack_m(const Ctrl* __restrict__ c, const float4* __restric
 	for (uint64_t t = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; t < total; t += (uint64_t) gridDim.x * blockDim.x) {
 		const uint32_t node = (uint32_t) (t / ms4), j = (uint32_t) (t - (uint64_t) node * ms4);
 		E4[t] = M4[(size_t) node * s4 + j];
-	}
-}
-
-__global__ void k_let_mark_m(const Ctrl* __restrict__ c, uint64_t m2l_cap, const uint32_t* __restrict__ m2l_id, uint32_t imp_base, uint32_t total,
-                             uint32_t* __restrict__ mflag) {
-	if (c->status) return;
-	const uint64_t n = c->m2l_cursor < m2l_cap ? c->m2l_cursor : m2l_cap;
-	for (uint64_t e = blockIdx.x * (uint64_t) blockDim.x + threadIdx.x; e < n; e += (uint64_t) gridDim.x * blockDim.x) {
-		const uint32_t id = m2l_id[e];
-		if (id >= imp_base && id - imp_base < total) mflag[id - imp_base] = 1u;
 	}
 }
 
@@ -340,6 +322,7 @@ __global__ void k_reset_lists(Ctrl* c, uint32_t* __restrict__ p2p_head) {
 		c->stat_m2l_inter = c->stat_m2l_low = c->stat_p2p_entries = c->stat_p2p_inter = c->stat_near = c->stat_leaves = 0;
 		for (int k = 0; k < 4; ++k) c->work_ticket[k] = 0;
 		c->acc_max2_bits = 0;
+		c->n_leaf_items = 0;
 	}
 }
 
@@ -445,7 +428,16 @@ int exchange_trees(Sim** m, int nm) {
 	}
 	Sim& D = *m[0];
 	const Let& L = *D.let;
-	NB_NCCL_CHECK(g_nccl.GroupStart());
+	if (L.gather_ok) {
+		const size_t slot = L.imp_slot, at = D.max_nodes;
+		NB_NCCL_CHECK(g_nccl.GroupStart());
+		NB_NCCL_CHECK(g_nccl.AllGather(D.geom, D.geom + at, slot * sizeof(float4), ncclChar, L.comm, D.stream));
+		NB_NCCL_CHECK(g_nccl.AllGather(D.info, D.info + at, slot * sizeof(uint2), ncclChar, L.comm, D.stream));
+		NB_NCCL_CHECK(g_nccl.AllGather(D.nbegin, D.nbegin + at, slot * 4, ncclChar, L.comm, D.stream));
+		NB_NCCL_CHECK(g_nccl.GroupEnd());
+		return NBODY_OK;
+	}
+	NB_NCCL_CHECK(g_nccl.GroupStart());  // fallback: one rank's tree is larger than another rank's arrays
 	for (int s = 0; s < W; ++s) {
 		const size_t cnt = L.nodes[s];
 		if (cnt == 0) continue;
@@ -545,7 +537,7 @@ int build_tree(Sim& s) {
 	if (rc) return rc;
 	const int ms4 = coef_stride((int) s.cfg.order - 1) / 4;
 	k_let_pack_m<<<kNumSM * 4, 256, 0, s.stream>>>(s.ctrl, reinterpret_cast<const float4*>(s.M), s.nc_stride / 4, reinterpret_cast<float4*>(L.mexp), ms4, L.mexp_cap);
-	k_let_publish<<<1, 1, 0, s.stream>>>(s.ctrl, L.xbuf + L.rank);
+	k_let_publish<<<1, 1, 0, s.stream>>>(s.ctrl, s.max_nodes, L.xbuf + L.rank);
 	NB_CUDA_CHECK(cudaEventRecord(L.ev[3], s.stream));
 	return NBODY_OK;
 }
@@ -562,16 +554,20 @@ int phase2b(Sim& s) {
 int plan_import(Sim& s) {
 	Let& L = *s.let;
 	const int W = L.world;
-	uint64_t total = 0;
-	uint32_t deepest = 1;
+	// every rank's tree gets a slot of `maxc` nodes behind the own tree (the own slot stays unused): equal slots make the exchange
+	// three plain all-gathers instead of 3 W grouped broadcasts
+	uint32_t deepest = 1, maxc = 0;
 	L.imp.world = W;
+	L.gather_ok = true;
 	for (int q = 0; q < W; ++q) {
 		L.nodes[q] = L.xhost[q].n_nodes;
 		deepest = std::max(deepest, L.xhost[q].n_levels);
-		L.imp.off[q] = (uint32_t) total;
-		if (q != L.rank) total += L.nodes[q];
+		maxc = std::max(maxc, L.nodes[q]);
 	}
-	L.imp.off[W] = (uint32_t) total;
+	for (int q = 0; q < W; ++q) if (L.xhost[q].node_cap < maxc) L.gather_ok = false;  // (a sender reads maxc records of its own arrays)
+	const uint64_t total = (uint64_t) W * maxc;
+	for (int q = 0; q <= W; ++q) L.imp.off[q] = (uint32_t) ((uint64_t) q * maxc);
+	L.imp_slot = maxc;
 	if (total > 0x7ffffff0ull) { set_error("partitioned mode: more than 2^31 imported nodes"); return NBODY_ERR_CAPACITY; }
 	L.imp_total = (uint32_t) total;
 	s.trav_bound = (int) deepest - 1 > 0 ? (int) deepest - 1 : 1;
@@ -605,6 +601,8 @@ int stage3(Sim& s, bool retry) {
 	} else {
 		k_let_fixup<<<grid_of((uint64_t) L.imp_total + 1, 256), 256, 0, st>>>(L.imp, s.max_nodes, L.imp_total, s.info, s.nbegin, L.imp_rbegin, L.imp_hoff);
 	}
+	if (L.imp_total) NB_CUDA_CHECK(cudaMemsetAsync(L.imp_mflag, 0, (size_t) L.imp_total * 4, st));
+	s.imp_hoff = L.imp_hoff; s.imp_mflag = L.imp_mflag;
 	s.seeds.n = 1; s.seeds.id[0] = 0;
 	for (int q = 0; q < W; ++q)
 		if (q != L.rank && L.nodes[q] && L.counts[q]) s.seeds.id[s.seeds.n++] = s.max_nodes + L.imp.off[q];
@@ -614,15 +612,12 @@ int stage3(Sim& s, bool retry) {
 	NB_CUDA_CHECK(cudaEventRecord(L.ev[5], st));
 	// halo: which imported leaves do the P2P lists name -> slots behind the own particles -> fetch over NVLink -> point the entries at them
 	const uint32_t halo_base = (uint32_t) s.cap, halo_cap = (uint32_t) (s.src_cap - s.cap);
-	k_let_mark<<<kNumSM * 8, 256, 0, st>>>(s.ctrl, s.pools.p2p_cap, s.pools.p2p, L.imp_total, L.imp_hoff);
-	launch_exclusive_scan(s, L.imp_hoff, L.imp_total + 1);
+	launch_exclusive_scan(s, L.imp_hoff, L.imp_total + 1);  // (the traversal stored every named imported leaf's count there)
 	k_let_fetch<<<kNumSM * 8, 256, 0, st>>>(s.ctrl, s.let_ctrl, L.peer, L.imp, L.imp_total, L.imp_hoff, L.imp_rbegin, s.posq[1], halo_base, halo_cap);
 	k_let_translate<<<kNumSM * 8, 256, 0, st>>>(s.ctrl, s.pools.p2p_cap, s.pools.p2p, L.imp_hoff, halo_base);
 	// ... and the multipoles: which imported nodes do the M2L lists name -> fetch orders 0..P-1 of exactly those from their owners
 	if (L.imp_total) {
 		const int ms4 = coef_stride((int) s.cfg.order - 1) / 4;
-		NB_CUDA_CHECK(cudaMemsetAsync(L.imp_mflag, 0, (size_t) L.imp_total * 4, st));
-		k_let_mark_m<<<kNumSM * 8, 256, 0, st>>>(s.ctrl, s.pools.m2l_cap, s.pools.m2l_id, s.max_nodes, L.imp_total, L.imp_mflag);
 		k_let_fetch_m<<<kNumSM * 8, 256, 0, st>>>(s.ctrl, L.peer_mexp, L.imp, L.imp_total, L.imp_mflag, reinterpret_cast<float4*>(s.Mimp), ms4);
 	}
 	NB_CUDA_CHECK(cudaEventRecord(L.ev[6], st));

@@ -114,6 +114,10 @@ struct TraverseArgs {
 	float ratio_sq;
 	float tau;
 	int round;
+	// partitioned mode: imported nodes have ids >= imp_base; the lists' imported leaves / nodes are marked for the halo and multipole fetch
+	uint32_t imp_base;
+	uint32_t* imp_hoff;
+	uint32_t* imp_mflag;
 };
 
 // Sized so that 4 CTAs fit in the 228 KB of an SM: sizeof(TravSmem) + 1 KB reserve <= 57 KB (static_assert below).
@@ -145,7 +149,7 @@ __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, unsigned lane, ui
 	return inc - v;
 }
 
-template <bool QUARTER>
+template <bool QUARTER, bool LET>
 __global__ void __launch_bounds__(kTravThreads) k_traverse(const TraverseArgs a) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	TravSmem& S = *reinterpret_cast<TravSmem*>(smem_raw);
@@ -296,7 +300,9 @@ __global__ void __launch_bounds__(kTravThreads) k_traverse(const TraverseArgs a)
 						if (mn >> lane & 1u) a.near_out[S.off[1][t] + S.running[1][t] + S.pre[0][t][b] + __popc(mn & lt_mask)] = S.cid[s];
 						if (mp >> lane & 1u) {
 							const uint32_t src = S.cid[s];
-							a.p2p[S.off[2][t] + S.running[2][t] + S.pre[1][t][b] + __popc(mp & lt_mask)] = make_uint2(a.nbegin[src], a.info[src].y);
+							const uint2 en = make_uint2(a.nbegin[src], a.info[src].y);
+							a.p2p[S.off[2][t] + S.running[2][t] + S.pre[1][t][b] + __popc(mp & lt_mask)] = en;
+							if (LET && (en.x & kImported)) a.imp_hoff[en.x & ~kImported] = en.y;  // (only imported leaves carry the tag; every writer stores the same count)
 						}
 					}
 					for (uint32_t b = w; b < nb; b += 8) {
@@ -305,7 +311,9 @@ __global__ void __launch_bounds__(kTravThreads) k_traverse(const TraverseArgs a)
 							unsigned am = 0, al = 0;
 							for (uint32_t tt = 0; tt < nt; ++tt) { am |= (S.bal[0][tt][b] >> lane & 1u) << tt; al |= (S.bal[3][tt][b] >> lane & 1u) << tt; }
 							const uint32_t pos = S.off[0][0] + S.running[0][0] + S.upre[b] + __popc(u & lt_mask);
-							a.m2l_id[pos] = S.cid[32 * b + lane];
+							const uint32_t mid = S.cid[32 * b + lane];
+							a.m2l_id[pos] = mid;
+							if (LET && mid >= a.imp_base) a.imp_mflag[mid - a.imp_base] = 1u;
 							a.m2l_mask[pos] = (uint8_t) am;
 							a.m2l_mask_lo[pos] = (uint8_t) al;
 						}
@@ -366,8 +374,9 @@ __global__ void __launch_bounds__(kTravThreads) k_traverse(const TraverseArgs a)
 void launch_traversal(Sim& s) {
 	Pools& p = s.pools;
 	const bool quarter = s.cfg.mac_ratio * s.cfg.mac_ratio == 0.25f;
-	cudaFuncSetAttribute(k_traverse<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(TravSmem));
-	cudaFuncSetAttribute(k_traverse<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(TravSmem));
+	const bool let = s.let != nullptr && s.imp_hoff != nullptr && s.imp_mflag != nullptr;
+	auto kernel = quarter ? (let ? k_traverse<true, true> : k_traverse<true, false>) : (let ? k_traverse<false, true> : k_traverse<false, false>);
+	cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(TravSmem));
 	k_traverse_init<<<1, 32, 0, s.stream>>>(s.ctrl, s.info, p.near[0], p.gq[1], s.seeds);
 	TraverseArgs a{};
 	a.c = s.ctrl; a.geom = s.geom; a.info = s.info; a.near_ref = s.near_ref; a.p2p_head = s.p2p_head;
@@ -376,6 +385,7 @@ void launch_traversal(Sim& s) {
 	a.seg = p.seg; a.seg_cap = p.seg_cap; a.gq_cap = p.gq_cap; a.items8 = p.items[0]; a.items1 = p.items[1]; a.items_cap = p.items_cap;
 	a.ratio_sq = s.cfg.mac_ratio * s.cfg.mac_ratio;
 	a.tau = s.cfg.order >= 3 ? s.cfg.low_order_tau : 0.0f;  // order P-1 >= 2 only
+	a.imp_base = s.let ? s.max_nodes : 0xffffffffu; a.imp_hoff = s.imp_hoff; a.imp_mflag = s.imp_mflag;
 	const int rounds = s.trav_bound < (int) s.cfg.max_depth ? s.trav_bound : (int) s.cfg.max_depth;
 	for (int r = 1; r <= rounds; ++r) {
 		k_round_prep<<<1, 32, 0, s.stream>>>(s.ctrl, r);
@@ -384,8 +394,7 @@ void launch_traversal(Sim& s) {
 		a.near_out = p.near[r & 1];
 		a.q_in = p.gq[r & 1];
 		a.q_out = p.gq[(r + 1) & 1];
-		if (quarter) k_traverse<true><<<kNumSM * 5, kTravThreads, sizeof(TravSmem), s.stream>>>(a);
-		else k_traverse<false><<<kNumSM * 5, kTravThreads, sizeof(TravSmem), s.stream>>>(a);
+		kernel<<<kNumSM * 5, kTravThreads, sizeof(TravSmem), s.stream>>>(a);
 	}
 }
 

@@ -199,6 +199,7 @@ __global__ void k_tree_init(Ctrl* c, uint32_t n, float bx, float by, float bz, f
 		c->stat_m2l_inter = c->stat_m2l_low = c->stat_p2p_entries = c->stat_p2p_inter = c->stat_near = c->stat_leaves = 0;
 		for (int k = 0; k < 4; ++k) c->work_ticket[k] = 0;
 		c->acc_max2_bits = 0;
+		c->n_leaf_items = 0;
 		c->part[0] = 0;
 		for (int k = 1; k <= kMaxRanks; ++k) c->part[k] = n;  // single GPU: rank 0 owns everything (k_partition overwrites this)
 		geom[0] = make_float4(__fadd_rn(__fmul_rn(0.0f, bx), __fmul_rn(bx, 0.5f)), __fadd_rn(__fmul_rn(0.0f, by), __fmul_rn(by, 0.5f)),
