@@ -130,6 +130,11 @@ int validate(const nbody_cuda_config* cfg, uint64_t n) {
 	if (cfg->max_depth < 1 || cfg->max_depth > (uint32_t) kMaxDepth) { set_error("max_depth must be in [1,21]"); return NBODY_ERR_INVALID; }
 	if (cfg->leaf_capacity < 1) { set_error("leaf_capacity must be >= 1"); return NBODY_ERR_INVALID; }
 	if (!(cfg->softening >= 0) || !(cfg->mac_ratio > 0)) { set_error("softening must be >= 0 and mac_ratio > 0"); return NBODY_ERR_INVALID; }
+	if (cfg->softening > 0 && !(cfg->softening * cfg->softening >= 1.17549435e-38f)) {
+		// the softened kernels use rsqrt.approx.ftz: a denormal eps^2 would flush to zero and turn every particle's self term into 0 * inf
+		set_error("softening^2 is denormal: use 0 (unsoftened kernels) or a softening >= 1.1e-19");
+		return NBODY_ERR_INVALID;
+	}
 	if (cfg->integrator > 1) { set_error("unknown integrator"); return NBODY_ERR_INVALID; }
 	if (!(cfg->low_order_tau >= 0)) { set_error("low_order_tau must be >= 0"); return NBODY_ERR_INVALID; }
 	if (!(cfg->time_step_eta >= 0) || !(cfg->time_step_min >= 0) || !(cfg->time_step_max >= 0) ||

@@ -178,6 +178,11 @@ int nbody_cuda_checkpoint_write(const char* path, const nbody_checkpoint_header*
 int nbody_cuda_checkpoint_save(nbody_cuda_sim* sim, const char* path) {
 	Sim* s = reinterpret_cast<Sim*>(sim);
 	if (!s || !path) { set_error("NULL argument"); return NBODY_ERR_INVALID; }
+	if (s->let) {
+		set_error("checkpoint_save: a rank of a partitioned run holds only its own particles; save them per rank with "
+		          "nbody_cuda_get_owned_particles + nbody_cuda_get_permutation (the checkpoint format is single-rank)");
+		return NBODY_ERR_STATE;
+	}
 	std::vector<nbody_particle> particles(s->n);
 	std::vector<uint32_t> orig(s->n);
 	int rc = nbody_cuda_get_particles(sim, particles.data(), s->n);
@@ -200,8 +205,19 @@ int nbody_cuda_checkpoint_load(const char* path, const nbody_cuda_config* cfg, n
 	std::vector<nbody_particle> particles(h.n_particles);
 	std::vector<uint32_t> orig(h.n_particles);
 	if ((rc = nbody_cuda_checkpoint_read(path, particles.data(), orig.data(), h.n_particles))) return rc;
+	{  // the stored identities must be a permutation of [0, n): callers index with them (P[inverse]), a foreign file must not get that far
+		std::vector<uint8_t> seen(h.n_particles, 0);
+		for (uint64_t i = 0; i < h.n_particles; ++i) {
+			if (orig[i] >= h.n_particles || seen[orig[i]]) {
+				set_error(std::string("checkpoint '") + path + "': the stored particle identities are not a permutation of [0, n)");
+				return NBODY_ERR_INVALID;
+			}
+			seen[orig[i]] = 1;
+		}
+	}
 	nbody_cuda_config use = cfg ? *cfg : h.config;
 	if (!cfg) use.device = -1;  // the ordinal of the writing process means nothing here
+	use.flags &= ~(uint32_t) NBODY_FLAG_PARTITIONED;  // (a single-rank object)
 	nbody_cuda_sim* sim = nullptr;
 	if ((rc = nbody_cuda_create(&use, particles.data(), h.n_particles, &sim))) return rc;
 	Sim* s = reinterpret_cast<Sim*>(sim);

@@ -231,6 +231,9 @@ float comm_work_imbalance(const Sim& s) {
 // rank gives NaN everywhere.
 int comm_all_max(Sim& s, float* value) {
 	Comm& cm = *s.comm;
+	// the velocity broadcasts of this step may still be in flight on the second stream, possibly on the SAME communicator:
+	// two collectives of one communicator must not overlap, so the compute stream is ordered behind them first
+	{ const int rcw = comm_wait_velocities(s); if (rcw) return rcw; }
 	cm.red_host[cm.rank] = *value;
 	NB_CUDA_CHECK(cudaMemcpyAsync(cm.red_dev + cm.rank, cm.red_host + cm.rank, sizeof(float), cudaMemcpyHostToDevice, s.stream));
 	NB_NCCL_CHECK(g_nccl.AllGather(cm.red_dev + cm.rank, cm.red_dev, 1, ncclFloat, cm.comm, s.stream));
@@ -244,6 +247,7 @@ int comm_all_max(Sim& s, float* value) {
 
 int comm_exchange_acc(Sim& s) {
 	if (!s.acc_partial) return NBODY_OK;
+	{ const int rcw = comm_wait_velocities(s); if (rcw) return rcw; }  // (see comm_all_max)
 	int rc = exchange(s, s.acc, sizeof(float4));
 	if (rc) return rc;
 	s.acc_partial = false;

@@ -13,6 +13,22 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
 
 
+def pytest_collection_modifyitems(config, items):
+    """Tests marked `gpu` are skipped (not failed) on a box without a CUDA device: the product has no CPU fallback to fall back on.
+    `-m gpu` on the GPU box runs them all; a plain `pytest` on the authoring container stays green."""
+    try:
+        import torch
+        have = torch.cuda.is_available()
+    except Exception:
+        have = False
+    if have:
+        return
+    skip = pytest.mark.skip(reason="needs a CUDA device (B200): the product has no CPU fallback")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 def sorted_system(P, bounds=(1.0, 1.0, 1.0), capacity=8, max_depth=21):
     """Oracle view of one particle set: keys, stable order, tree, sorted (x,y,z,q)."""
     import oracle

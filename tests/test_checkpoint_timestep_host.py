@@ -11,6 +11,7 @@ import pytest
 
 import nbody_b200
 import oracle
+from nbody_b200 import workloads
 
 GOLDEN = 0x9E3779B97F4A7C15
 MASK = (1 << 64) - 1
@@ -178,3 +179,21 @@ def test_oracle_adaptive_run_is_consistent():
     Qf, tf, dtf, _ = oracle.direct_step_adaptive(P, G, 0.01, 1e-3, 0.0, 0.0, 0.0, 3)
     Qr, tr = oracle.direct_step(P, G, 0.01, 1e-3, 3, 0)
     assert np.array_equal(Qf, Qr) and tf == tr and np.all(dtf == np.float32(1e-3))
+
+
+def test_load_refuses_identities_that_are_not_a_permutation(tmp_path):
+    """nbody_cuda_checkpoint_write accepts any identity array; nbody_cuda_checkpoint_load must not hand out-of-range or
+    duplicated identities to callers that index with them. The check runs before any device is touched."""
+    P = workloads.uniform_cube(64)
+    for bad in (np.zeros(64, np.uint32), np.arange(64, dtype=np.uint32) + 1, np.r_[np.arange(63), 1000].astype(np.uint32)):
+        path = str(tmp_path / "bad.ckp")
+        nbody_b200.checkpoint_write(path, P, bad)
+        with pytest.raises(nbody_b200.NbodyCudaError) as e:
+            nbody_b200.CudaSimulation.from_checkpoint(path)
+        assert "not a permutation" in str(e.value)
+
+
+def test_denormal_softening_is_rejected():
+    with pytest.raises(nbody_b200.NbodyCudaError) as e:
+        nbody_b200.CudaSimulation([1, 1, 1], workloads.uniform_cube(8), 1e-3, softening=1e-30)
+    assert "denormal" in str(e.value)

@@ -307,12 +307,14 @@ def test_large_uniform_1m_against_gpu_direct_subsample():
 
 
 def test_full_size_plummer_16m_properties():
-    """BASELINE config 3 at full size (Plummer N = 2^24) through size-independent properties: sorted keys, a valid
-    permutation, accelerations within 1e-3 RMS of direct summation on a 65,536-target subsample (GPU all-pairs kernel with
-    compensated sums, cross-checked against the FP64 oracle on 128 targets), and vanishing net force."""
+    """BASELINE config 3 at full size (Plummer N = 2^24) AT THE BENCHED SETTINGS (bench.py: leaf capacity 48, order 4, default
+    low_order_tau) through size-independent properties: sorted keys, a valid permutation, accelerations within 1e-3 RMS of direct
+    summation on a 65,536-target subsample (GPU all-pairs kernel with compensated sums, cross-checked against the FP64 oracle on
+    128 targets), and vanishing net force."""
     n = 1 << 24
     P = workloads.plummer(n)
-    sim = make_sim(P, leaf_capacity=32)
+    sim = make_sim(P, leaf_capacity=48, order=4)
+    assert abs(sim.config.low_order_tau - 0.13) < 1e-6
     sim.step()
     st = sim.stats()
     assert st["retries"] == 0 and st["n_leaves"] > 0 and st["m2l_interactions"] > st["m2l_interactions_low"] > 0

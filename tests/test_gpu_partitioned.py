@@ -118,3 +118,34 @@ def test_pool_growth_inside_a_partitioned_step():
     assert np.array_equal(grp.permutation(), ref.permutation())
     assert rms_rel(grp.accelerations(), ref.accelerations()) < 1.5e-4
     grp.close(); ref.close()
+
+
+def test_variable_time_step_and_edge_cases():
+    """The variable time step in partitioned mode (the largest acceleration is a maximum over the ranks' slots), a group of one rank,
+    more ranks than make sense for the particle count (ranks that own next to nothing), and the calls a member must refuse."""
+    n = 20000
+    P = workloads.plummer(n)
+    kw = dict(leaf_capacity=8, time_step_eta=0.01)
+    ref = single(P, **kw)
+    grp = nbody_b200.VirtualGroup([1.0, 1.0, 1.0], P, 1e-3, 4, **kw)
+    for step in range(3):
+        ref.step(); grp.step()
+        a, b = grp.members[0].time_step(), ref.time_step()
+        assert abs(a["last"] / b["last"] - 1) < 1e-4 and abs(a["next"] / b["next"] - 1) < 1e-3 and abs(a["acc_max"] / b["acc_max"] - 1) < 1e-3, (step, a, b)
+        assert all(m.time_step()["next"] == a["next"] for m in grp.members)           # every rank derives the same step, bit for bit
+    assert grp.members[0].time_step()["next"] < 1e-3                                  # the rule did take over
+    with pytest.raises(nbody_b200.NbodyCudaError):
+        grp.members[1].step()                                                        # members step through the group
+    grp.close(); ref.close()
+    for world, n2 in ((1, 3000), (16, 300)):
+        P2 = workloads.uniform_cube(n2)
+        r2 = single(P2, flags=nbody_b200.FLAG_NO_INTEGRATE)
+        r2.step()
+        g2 = nbody_b200.VirtualGroup([1.0, 1.0, 1.0], P2, 1e-3, world, flags=nbody_b200.FLAG_NO_INTEGRATE)
+        g2.step()
+        assert sum(g2.counts()) == n2 and np.array_equal(g2.permutation(), r2.permutation())
+        assert sum(s["p2p_interactions"] for s in g2.stats()) == r2.stats()["p2p_interactions"]
+        assert rms_rel(g2.accelerations(), r2.accelerations()) < 1.5e-4
+        g2.close(); r2.close()
+    with pytest.raises(nbody_b200.NbodyCudaError):
+        nbody_b200.VirtualGroup([1.0, 1.0, 1.0], P, 1e-3, 2, flags=nbody_b200.FLAG_DIRECT)   # the all-pairs path is single-GPU only
