@@ -105,3 +105,22 @@ def test_two_gpu_step_matches_single_gpu():
                         "--master-port", "29656", os.path.join(ROOT, "tools", "mg_check.py"), "100000", "4", "plummer", "0.05"],
                        capture_output=True, text=True, timeout=300)
     assert "MG_CHECK PASS" in r.stdout and "time steps agree: True" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_two_gpu_partitioned_step_matches_single_gpu():
+    """The partitioned scheme with one process per GPU (cudaIpc peer mappings + NCCL), through bench.py's own checks: accuracy of
+    the force evaluation against direct summation, and the 2-rank run against a single-GPU run (tree order, P2P work, trajectories)."""
+    import json
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (the one-GPU box covers the scheme through virtual ranks: tests/test_gpu_partitioned.py)")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29656", os.path.join(ROOT, "bench.py"), "--gpus", "2", "--particles", "400000", "--steps", "2", "--warmup", "3",
+                        "--no-cpu-baseline", "--no-reference-capacity", "--e2e-steps", "1"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert d["n_gpus"] == 2 and "partitioned" in d["config"]["partition"]
+    assert d["accuracy"]["rms_rel"] < 1e-3
+    c = d["multi_gpu_check"]
+    assert c["pass"] and c["first_step_same_tree_order_as_1gpu"] and c["first_step_p2p_interactions_sum"] == c["first_step_p2p_interactions_1gpu"]
+    assert max(c["device_bytes_per_rank"]) < c["device_bytes_1gpu"]
