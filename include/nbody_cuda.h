@@ -81,7 +81,7 @@ typedef struct nbody_cuda_config {
 	float mac_ratio;        /* NODE_APPROX_RATIO, src/interaction.cl:3-5; default 0.5 */
 	uint32_t leaf_capacity; /* octree node capacity, src/open_cl_simulation.cpp:41-47; default 8 */
 	uint32_t max_depth;     /* <= 21 */
-	uint32_t order;         /* expansion order P in {2,3,4}; default 4 */
+	uint32_t order;         /* expansion order P in {2,3,4,5}; default 4 (5: 56 coefficients, the M2L kernel then runs one CTA per SM at 254 registers) */
 	uint32_t integrator;    /* NBODY_KICK_DRIFT (default) | NBODY_EXPLICIT_EULER */
 	uint32_t flags;
 	int32_t device;         /* CUDA device ordinal; -1 = current */

@@ -126,7 +126,7 @@ int validate(const nbody_cuda_config* cfg, uint64_t n) {
 	if (cfg->abi_version != NBODY_CUDA_ABI_VERSION) { set_error("abi_version mismatch"); return NBODY_ERR_INVALID; }
 	if (n == 0 || n > 0xfffffff0ull) { set_error("particle count must be in [1, 2^32-16)"); return NBODY_ERR_INVALID; }
 	if (!(cfg->bounds[0] > 0 && cfg->bounds[1] > 0 && cfg->bounds[2] > 0)) { set_error("bounds must be positive"); return NBODY_ERR_INVALID; }
-	if (cfg->order < 2 || cfg->order > 4) { set_error("order must be 2, 3 or 4"); return NBODY_ERR_INVALID; }
+	if (cfg->order < 2 || cfg->order > 5) { set_error("order must be 2, 3, 4 or 5"); return NBODY_ERR_INVALID; }
 	if (cfg->max_depth < 1 || cfg->max_depth > (uint32_t) kMaxDepth) { set_error("max_depth must be in [1,21]"); return NBODY_ERR_INVALID; }
 	if (cfg->leaf_capacity < 1) { set_error("leaf_capacity must be >= 1"); return NBODY_ERR_INVALID; }
 	if (!(cfg->softening >= 0) || !(cfg->mac_ratio > 0)) { set_error("softening must be >= 0 and mac_ratio > 0"); return NBODY_ERR_INVALID; }

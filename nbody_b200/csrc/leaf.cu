@@ -438,6 +438,7 @@ void launch_leaf(Sim& s) {
 	switch (s.cfg.order) {
 		case 2: leaf_t<2>(s, a); break;
 		case 3: leaf_t<3>(s, a); break;
+		case 5: leaf_t<5>(s, a); break;
 		default: leaf_t<4>(s, a); break;
 	}
 }

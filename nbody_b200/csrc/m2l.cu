@@ -78,7 +78,7 @@ struct M2LShared {
 // Inside a chunk each warp first compacts the slots its target accepts into two dense lists
 // (order P and order P-1), then all 32 lanes work through each list.
 template <int P, int NT>
-__global__ void __launch_bounds__(NT == 8 ? 256 : 32, NT == 8 ? 2 : 16)
+__global__ void __launch_bounds__(NT == 8 ? 256 : 32, NT == 8 ? (P <= 4 ? 2 : 1) : (P <= 4 ? 16 : 8))
 k_m2l(Ctrl* __restrict__ c, const Group* __restrict__ items, uint32_t items_cap, const float4* __restrict__ geom,
       const float* __restrict__ M, float* __restrict__ L, const uint32_t* __restrict__ m2l_id, const uint8_t* __restrict__ m2l_mask,
       const uint8_t* __restrict__ m2l_mask_lo, float eps2, uint32_t imp_base, const float* __restrict__ Mimp) {
@@ -277,9 +277,9 @@ static void m2l_t(Sim& s) {
 	cudaFuncSetAttribute(k_m2l<P, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(M2LShared<P, 8>));
 	cudaFuncSetAttribute(k_m2l<P, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(M2LShared<P, 1>));
 	const uint32_t imp_base = s.let ? s.max_nodes : 0xffffffffu;
-	k_m2l<P, 8><<<kNumSM * 2, 256, sizeof(M2LShared<P, 8>), s.stream>>>(s.ctrl, s.pools.items[0], s.pools.items_cap, s.geom, s.M, s.L,
+	k_m2l<P, 8><<<kNumSM * (P <= 4 ? 2 : 1), 256, sizeof(M2LShared<P, 8>), s.stream>>>(s.ctrl, s.pools.items[0], s.pools.items_cap, s.geom, s.M, s.L,
 	                                                                  s.pools.m2l_id, s.pools.m2l_mask, s.pools.m2l_mask_lo, eps2, imp_base, s.Mimp);
-	k_m2l<P, 1><<<kNumSM * 16, 32, sizeof(M2LShared<P, 1>), s.stream>>>(s.ctrl, s.pools.items[1], s.pools.items_cap, s.geom, s.M, s.L,
+	k_m2l<P, 1><<<kNumSM * (P <= 4 ? 16 : 8), 32, sizeof(M2LShared<P, 1>), s.stream>>>(s.ctrl, s.pools.items[1], s.pools.items_cap, s.geom, s.M, s.L,
 	                                                                  s.pools.m2l_id, s.pools.m2l_mask, s.pools.m2l_mask_lo, eps2, imp_base, s.Mimp);
 }
 template <int P>
@@ -292,6 +292,7 @@ void launch_m2l(Sim& s) {
 	switch (s.cfg.order) {
 		case 2: m2l_t<2>(s); break;
 		case 3: m2l_t<3>(s); break;
+		case 5: m2l_t<5>(s); break;
 		default: m2l_t<4>(s); break;
 	}
 }
@@ -299,6 +300,7 @@ void launch_l2l(Sim& s) {
 	switch (s.cfg.order) {
 		case 2: l2l_t<2>(s); break;
 		case 3: l2l_t<3>(s); break;
+		case 5: l2l_t<5>(s); break;
 		default: l2l_t<4>(s); break;
 	}
 }

@@ -103,6 +103,7 @@ void launch_upsweep(Sim& s) {
 	switch (s.cfg.order) {
 		case 2: upsweep_t<2>(s); break;
 		case 3: upsweep_t<3>(s); break;
+		case 5: upsweep_t<5>(s); break;
 		default: upsweep_t<4>(s); break;
 	}
 }

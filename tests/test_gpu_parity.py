@@ -67,7 +67,7 @@ def test_keys_tree_lists_bit_exact(kind, n, cap):
 
 @pytest.mark.parametrize("kind,n,order,tau", [("uniform", 20000, 4, None), ("plummer", 20000, 4, None), ("plummer", 20000, 4, 0.0),
                                                ("uniform", 20000, 4, 0.0), ("plummer", 20000, 3, None), ("plummer", 20000, 3, 0.0),
-                                               ("uniform", 20000, 2, None)])
+                                               ("uniform", 20000, 2, None), ("plummer", 20000, 5, 0.0), ("uniform", 20000, 5, None)])
 def test_expansions_and_accelerations(kind, n, order, tau):
     """tau = 0.0 (and order 2, which has no lower order): every pair at order P — the device must reproduce the oracle's
     expansions coefficient by coefficient. tau = None: the default adaptive-order M2L (pairs with ext2 < 0.13 d2 may run at
@@ -106,8 +106,10 @@ def test_expansions_and_accelerations(kind, n, order, tau):
         assert rms_rel(L[ne][:, 1:], Lf_d) <= 1.05 * rms_rel(La_d, Lf_d) + EXP_TOL
         assert rms_rel(acc, g_full * scale) <= 1.05 * rms_rel(g_fmm, g_full) + 2e-6
         assert err <= rms_rel(g_fmm[tg], gd) + 1e-5                   # no error beyond the adaptive method's
-    if order == 4:
+    if order >= 4:
         assert err < ACC_TOL
+    if order == 5 and tau_eff == 0.0:
+        assert err < 1e-4                                             # one order more: 2.1e-4 -> below 1e-4 on the Plummer model
     sim.close()
 
 
