@@ -205,6 +205,7 @@ __global__ void __launch_bounds__(kLeafWarps * 32, kLeafMinCtas) k_leaf(const Le
 	const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
 #if NBODY_LEAF_BULK
 	__shared__ __align__(8) uint64_t sbar[kLeafWarps][2];  // one mbarrier per warp and tile buffer; a single arrival (lane 0) + the copied bytes
+	__shared__ uint2 sent[kLeafWarps][32];                  // the batch of list entries in flight for the tile after next (cp.async)
 	unsigned bar_parity = 0u;                               // bit b: the phase parity the next wait on buffer b expects
 	if (lane == 0) {
 		leaf_mbar_init(&sbar[w][0], 1u);
@@ -277,6 +278,23 @@ __global__ void __launch_bounds__(kLeafWarps * 32, kLeafMinCtas) k_leaf(const Le
 					if (e0 + lane < sg.cnt) ent = a.p2p[sg.off + e0 + lane];
 					return true;
 				};
+#if NBODY_LEAF_BULK
+				// The same for the batch after next, but through shared memory with cp.async: the entries are not needed before the next
+				// tile has been evaluated, and a register-destination load this far ahead made the warp wait for it at the very next
+				// instruction that touched its scoreboard (4.8 % of the kernel's stall samples, profiles/r02b_ncu_k_leaf_source.csv.gz).
+				auto fetch_async = [&]() -> bool {
+					while (e0 >= sg.cnt) {
+						if (si == END) return false;
+						sg = a.seg[si]; si = sg.next; e0 = 0;
+					}
+					if (e0 + lane < sg.cnt) {
+						const unsigned sa = leaf_smem_addr(&sent[w][lane]);
+						asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(a.p2p + (sg.off + e0 + lane)) : "memory");
+					} else sent[w][lane] = make_uint2(0u, 0u);
+					leaf_cp_async_commit();
+					return true;
+				};
+#endif
 				// Cut one tile off the flat particle range of `ent`, issue its fill and advance the cursor.
 				auto stage = [&](const uint2& ent, float4* tile, uint32_t& fill) {
 					const uint32_t nvalid = min(32u, sg.cnt - e0);
@@ -336,18 +354,28 @@ __global__ void __launch_bounds__(kLeafWarps * 32, kLeafMinCtas) k_leaf(const Le
 				uint2 ent_cur = make_uint2(0u, 0u), ent_nxt = make_uint2(0u, 0u);
 				uint32_t fill_cur = 0;
 				int cur = 0;
+#if NBODY_LEAF_BULK
+				bool pending = false;  // a batch of entries is in flight into sent[w]
+#endif
 				bool has_cur = fetch(ent_cur);
 				if (has_cur) stage(ent_cur, sbuf[w][0], fill_cur);
 				bool has_nxt = has_cur && fetch(ent_nxt);
 #pragma unroll 1
 				while (has_cur) {
 					uint32_t fill_nxt = 0;
+#if NBODY_LEAF_BULK
+					if (has_nxt) {
+						if (pending) { leaf_cp_async_wait0(); ent_nxt = sent[w][lane]; pending = false; }  // issued one tile ago
+						stage(ent_nxt, sbuf[w][cur ^ 1], fill_nxt);
+					}
+					const bool has_nn = has_nxt && fetch_async();  // entries of the batch after next: in flight during the math
+					pending = has_nn;
+#else
 					if (has_nxt) stage(ent_nxt, sbuf[w][cur ^ 1], fill_nxt);
-#if !NBODY_LEAF_BULK
 					else leaf_cp_async_commit();  // empty group keeps the wait_group arithmetic uniform
-#endif
 					uint2 ent_nn = make_uint2(0u, 0u);
 					const bool has_nn = has_nxt && fetch(ent_nn);  // entries of the batch after next: in flight during the math
+#endif
 #if NBODY_LEAF_BULK
 					leaf_mbar_wait(&sbar[w][cur], (bar_parity >> cur) & 1u);
 					bar_parity ^= 1u << cur;
@@ -356,7 +384,10 @@ __global__ void __launch_bounds__(kLeafWarps * 32, kLeafMinCtas) k_leaf(const Le
 #endif
 					tile_rows<SOFT>(G, sbuf[w][cur], (fill_cur + 31u) >> 5, lane, stgt[w], a.eps2, ax, ay, az);
 					nsrc += fill_cur;
-					ent_nxt = ent_nn; fill_cur = fill_nxt; has_cur = has_nxt; has_nxt = has_nn;
+#if !NBODY_LEAF_BULK
+					ent_nxt = ent_nn;
+#endif
+					fill_cur = fill_nxt; has_cur = has_nxt; has_nxt = has_nn;
 					cur ^= 1;
 				}
 #if !NBODY_LEAF_BULK
