@@ -54,6 +54,9 @@ __device__ __forceinline__ void leaf_cp_async_wait0() { asm volatile("cp.async.w
 #ifndef NBODY_LEAF_BULK
 #define NBODY_LEAF_BULK 1
 #endif
+#ifndef NBODY_LEAF_FLAT
+#define NBODY_LEAF_FLAT 0   // 1: the leaf's segment chain is read as one flat entry range (tiles run across segment ends); measured, see DESIGN.md section 10
+#endif
 __device__ __forceinline__ unsigned leaf_smem_addr(const void* p) { return (unsigned) __cvta_generic_to_shared(p); }
 __device__ __forceinline__ void leaf_mbar_init(uint64_t* bar, unsigned count) {
 	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(leaf_smem_addr(bar)), "r"(count) : "memory");
@@ -254,6 +257,15 @@ __global__ void __launch_bounds__(kLeafWarps * 32, kLeafMinCtas) k_leaf(const Le
 			const uint32_t nt = __shfl_sync(0xffffffffu, nf_l.y, kk), b = __shfl_sync(0xffffffffu, b_l, kk);
 			++leaves;
 			const float4 g = a.geom[node];
+#if NBODY_LEAF_FLAT
+			uint32_t seg_off_l = 0u, seg_beg_l = 0xffffffffu, E = 0u, nseg = 0u;
+			for (uint32_t sj = a.p2p_head[node]; sj != END && nseg < 32u; ++nseg) {
+				const Segment sgm = a.seg[sj];
+				if (lane == nseg) { seg_off_l = sgm.off; seg_beg_l = E; }
+				E += sgm.cnt;
+				sj = sgm.next;
+			}
+#endif
 			const uint32_t nblk = (nt + kLeafG - 1) / kLeafG, gmax = (nt + nblk - 1) / nblk;  // even blocks of <= kLeafG targets
 #pragma unroll 1
 			for (uint32_t t0 = 0; t0 < nt; t0 += gmax) {
@@ -269,6 +281,23 @@ __global__ void __launch_bounds__(kLeafWarps * 32, kLeafMinCtas) k_leaf(const Le
 				// ---- cursor over the segment chain: entry e0 of segment sg, of which `skip` particles are consumed ----
 				uint32_t si = a.p2p_head[node], e0 = 0, skip = 0;
 				Segment sg; sg.off = 0; sg.cnt = 0; sg.next = END;
+#if NBODY_LEAF_FLAT
+				auto flat_addr = [&](uint32_t gidx) -> uint32_t {
+					uint32_t addr = 0u;
+					for (uint32_t j = 0; j < nseg; ++j) {
+						const uint32_t bj = __shfl_sync(0xffffffffu, seg_beg_l, j), oj = __shfl_sync(0xffffffffu, seg_off_l, j);
+						if (gidx >= bj) addr = oj + (gidx - bj);
+					}
+					return addr;
+				};
+				auto fetch = [&](uint2& ent) -> bool {
+					if (e0 >= E) return false;
+					const uint32_t ad = flat_addr(e0 + lane);
+					ent = make_uint2(0u, 0u);
+					if (e0 + lane < E) ent = a.p2p[ad];
+					return true;
+				};
+#else
 				auto fetch = [&](uint2& ent) -> bool {  // the (up to) 32 entries at the cursor, lane l holds entry l; warp-uniform result
 					while (e0 >= sg.cnt) {
 						if (si == END) return false;
@@ -278,11 +307,20 @@ __global__ void __launch_bounds__(kLeafWarps * 32, kLeafMinCtas) k_leaf(const Le
 					if (e0 + lane < sg.cnt) ent = a.p2p[sg.off + e0 + lane];
 					return true;
 				};
+#endif
 #if NBODY_LEAF_BULK
 				// The same for the batch after next, but through shared memory with cp.async: the entries are not needed before the next
 				// tile has been evaluated, and a register-destination load this far ahead made the warp wait for it at the very next
 				// instruction that touched its scoreboard (4.8 % of the kernel's stall samples, profiles/r02b_ncu_k_leaf_source.csv.gz).
 				auto fetch_async = [&]() -> bool {
+#if NBODY_LEAF_FLAT
+					if (e0 >= E) return false;
+					const uint32_t ad = flat_addr(e0 + lane);
+					if (e0 + lane < E) {
+						const unsigned sa = leaf_smem_addr(&sent[w][lane]);
+						asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(a.p2p + ad) : "memory");
+					} else sent[w][lane] = make_uint2(0u, 0u);
+#else
 					while (e0 >= sg.cnt) {
 						if (si == END) return false;
 						sg = a.seg[si]; si = sg.next; e0 = 0;
@@ -291,13 +329,18 @@ __global__ void __launch_bounds__(kLeafWarps * 32, kLeafMinCtas) k_leaf(const Le
 						const unsigned sa = leaf_smem_addr(&sent[w][lane]);
 						asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(a.p2p + (sg.off + e0 + lane)) : "memory");
 					} else sent[w][lane] = make_uint2(0u, 0u);
+#endif
 					leaf_cp_async_commit();
 					return true;
 				};
 #endif
 				// Cut one tile off the flat particle range of `ent`, issue its fill and advance the cursor.
 				auto stage = [&](const uint2& ent, float4* tile, uint32_t& fill) {
+#if NBODY_LEAF_FLAT
+					const uint32_t nvalid = min(32u, E - e0);
+#else
 					const uint32_t nvalid = min(32u, sg.cnt - e0);
+#endif
 					const uint32_t sk = lane == 0u ? skip : 0u;
 					const uint32_t v = lane < nvalid ? ent.y - sk : 0u;
 					uint32_t inc = v;

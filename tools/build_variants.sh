@@ -9,3 +9,4 @@ build rowfill "-DNBODY_LEAF_BULK=0"                               # the cp.async
 build cta3 "-DNBODY_LEAF_MIN_CTAS=3"                              # 3 CTAs of 4 warps per SM at up to 168 registers
 build cta3_rows8 "-DNBODY_LEAF_MIN_CTAS=3 -DNBODY_LEAF_ROWS=8"    # ... with 8 source rows in flight per lane
 build cta5_g8 "-DNBODY_LEAF_MIN_CTAS=5 -DNBODY_LEAF_G=8"          # 5 CTAs per SM, 8 targets per block
+build flat "-DNBODY_LEAF_FLAT=1"                                  # tiles run across the segments of a leaf's source list
