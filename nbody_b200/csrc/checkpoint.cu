@@ -13,6 +13,10 @@
 #include <memory>
 #include <vector>
 
+#include <unistd.h>
+
+#include <cerrno>
+
 #include "common.cuh"
 
 namespace nbody {
@@ -88,10 +92,12 @@ int write_file(const char* path, nbody_checkpoint_header h, const nbody_particle
 	File f(std::fopen(tmp.c_str(), "wb"));
 	if (!f) return fail_io("cannot create", tmp.c_str());
 	const bool ok = std::fwrite(&h, sizeof(h), 1, f.get()) == 1 && std::fwrite(particles, sizeof(nbody_particle), n, f.get()) == n &&
-	                std::fwrite(orig, sizeof(uint32_t), n, f.get()) == n && std::fflush(f.get()) == 0;
+	                std::fwrite(orig, sizeof(uint32_t), n, f.get()) == n && std::fflush(f.get()) == 0 &&
+	                fsync(fileno(f.get())) == 0;  // on disk before the rename makes it the checkpoint
+	const int err = errno;                         // (the cleanup below may overwrite it)
 	f.reset();
-	if (!ok) { std::remove(tmp.c_str()); return fail_io("short write to", tmp.c_str()); }
-	if (std::rename(tmp.c_str(), path) != 0) { std::remove(tmp.c_str()); return fail_io("cannot rename the finished checkpoint to", path); }
+	if (!ok) { std::remove(tmp.c_str()); errno = err; return fail_io("short write to", tmp.c_str()); }
+	if (std::rename(tmp.c_str(), path) != 0) { const int e2 = errno; std::remove(tmp.c_str()); errno = e2; return fail_io("cannot rename the finished checkpoint to", path); }
 	return NBODY_OK;
 }
 
