@@ -81,3 +81,67 @@ def test_generate_slices_tile_the_global_set(kind):
     cuts = [0, 1, 1234, 5003, 5004, 9999, n]
     parts = [workloads.generate(kind, n, a, b - a) for a, b in zip(cuts, cuts[1:])]
     assert np.array_equal(np.concatenate(parts), full)
+
+
+def _lists_worker(rank, world, port, n, cap, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    P = workloads.plummer(n)
+    keys = np.sort(oracle.morton_keys(P[:, 0:3], [1, 1, 1]))
+    split = [0] + [int(keys[n * k // world]) for k in range(1, world)] + [M.KEY_END]
+    lo = [int(np.searchsorted(keys, np.uint64(split[r]), "left")) if split[r] < M.KEY_END else n for r in range(world + 1)]
+    mine = keys[lo[rank]:lo[rank + 1]]
+    cells = M.straddling_cells(split)
+    allc = [None] * world
+    dist.all_gather_object(allc, M.local_straddle_counts(mine, split))
+    glob = np.sum(np.array(allc, dtype=np.int64), axis=0)
+    forced = frozenset((d, p) for (b, d, p), c in zip(cells, glob) if c > cap)
+    local = M.build_tree(mine, cap, M.MAX_DEPTH, forced)
+    trees = [None] * world
+    dist.all_gather_object(trees, local)                                         # X3: every rank's tree (here: the whole dict)
+    ref = M.build_tree(keys, cap, M.MAX_DEPTH)
+
+    def members(cell, a, b):                                                     # global particle indices of keys[a:b) inside `cell`
+        c_lo, c_hi = M.cell_range(*cell)
+        i0 = a + int(np.searchsorted(keys[a:b], np.uint64(c_lo), "left"))
+        i1 = a + (int(np.searchsorted(keys[a:b], np.uint64(c_hi), "left")) if c_hi < (1 << 64) else b - a)
+        return i0, i1
+
+    # the rank's own targets against every rank's tree (own first, then the imported ones: the seeds of k_traverse_init)
+    pairs_p2p, covered = set(), np.zeros(lo[rank + 1] - lo[rank], np.int64)
+    for s in range(world):
+        m2l, p2p = M.traverse(local, trees[s])
+        for (ca, cb), near in [(x, False) for x in m2l] + [(x, True) for x in p2p]:
+            t0, t1 = members(ca, lo[rank], lo[rank + 1])
+            s0, s1 = members(cb, lo[s], lo[s + 1])
+            covered[t0 - lo[rank]:t1 - lo[rank]] += s1 - s0
+            if near:
+                pairs_p2p.update((i, j) for i in range(t0, t1) for j in range(s0, s1))
+    # the single-GPU lists, restricted to this rank's target particles
+    m2l_g, p2p_g = M.traverse(ref, ref)
+    ref_p2p = set()
+    for ca, cb in p2p_g:
+        t0, t1 = members(ca, 0, n)
+        s0, s1 = members(cb, 0, n)
+        t0, t1 = max(t0, lo[rank]), min(t1, lo[rank + 1])
+        if t0 < t1:
+            ref_p2p.update((i, j) for i in range(t0, t1) for j in range(s0, s1))
+    with open(os.path.join(tmp, f"l{rank}.json"), "w") as f:
+        json.dump({"covered_once": bool(np.all(covered == n)), "p2p_equal": pairs_p2p == ref_p2p, "n_p2p": len(pairs_p2p),
+                   "n_local": int(len(mine))}, f)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n,cap,world,port", [(1200, 8, 2, 29551), (900, 4, 3, 29552)])
+def test_own_targets_against_all_ranks_trees_give_the_global_lists(tmp_path, n, cap, world, port):
+    """The second half of the construction: traversing a rank's own targets against (own tree + every other rank's tree) covers every
+    (own target particle, source particle) pair exactly once by an M2L or a P2P interaction, and the P2P particle pairs are exactly those
+    of the single-GPU traversal of the global tree — which is why the P2P evaluation counts of the ranks sum to the single-GPU count."""
+    mp.spawn(_lists_worker, args=(world, port, n, cap, str(tmp_path)), nprocs=world, join=True)
+    total = 0
+    for r in range(world):
+        d = json.load(open(tmp_path / f"l{r}.json"))
+        assert d["covered_once"] and d["p2p_equal"] and d["n_p2p"] > 0, d
+        total += d["n_local"]
+    assert total == n
