@@ -250,11 +250,16 @@ int nbody_cuda_direct_field(int device, const float* src_posq, uint64_t n_src, c
 int nbody_cuda_sort_runs(int device, const uint64_t* keys, uint64_t n, const uint32_t* bound, int nruns, uint64_t* keys_out,
                          uint32_t* index_out);
 
-/* ---- multi-GPU (one process per GPU; Morton-range partition, NCCL) ------- */
+/* ---- multi-GPU (one process per GPU; Morton-range partition; NCCL + NVLink peer memory) ------- */
+/* The reference is single-device (src/open_cl_simulation.cpp:627-632); this part of the ABI has no counterpart there. */
 /* 128-byte NCCL unique id created on rank 0 and sent to the other ranks by the caller. */
 int nbody_cuda_comm_unique_id(uint8_t id[128]);
-/* Same as nbody_cuda_create, but this rank passes only ITS slice of the global
- * particle set; `global_offset` is the index of its first particle. */
+/* Same as nbody_cuda_create, but this rank passes only ITS slice of the global particle set; `global_offset` is the index of its
+ * first particle (the slices need not be sorted in any way). Collective: every rank calls it with the same cfg->flags.
+ * With NBODY_FLAG_PARTITIONED the object then holds ONLY the particles of this rank's Morton-key range: nbody_cuda_num_particles,
+ * get_particles, get_permutation (indices into the GLOBAL input array), get_keys, get_accelerations and get_stats answer for those
+ * particles, in tree order (ranks in rank order = the global tree order), and their number changes from step to step.
+ * Without the flag (round 1's replicated scheme) every rank holds the whole state and the calls answer for all n_global particles. */
 int nbody_cuda_create_distributed(const nbody_cuda_config* cfg, const nbody_particle* local_particles, uint64_t n_local,
                                   uint64_t n_global, uint64_t global_offset, int rank, int world, const uint8_t id[128],
                                   nbody_cuda_sim** out);
@@ -271,7 +276,8 @@ void nbody_cuda_destroy_group(nbody_cuda_sim** sims, int world);
  * (before the first step: the slice passed to nbody_cuda_create_distributed). Single GPU: [0, n). */
 int nbody_cuda_owned_range(nbody_cuda_sim* sim, uint64_t* first, uint64_t* count);
 /* Host <-> device transfer of this rank's OWNED slice only (count particles, tree order): the distributed
- * counterparts of get_particles / set_particles. set_ is collective: every rank must call it. */
+ * counterparts of get_particles / set_particles. Partitioned scheme: purely local (no other rank is involved).
+ * Replicated scheme: set_ is collective, every rank must call it. */
 int nbody_cuda_get_owned_particles(nbody_cuda_sim* sim, nbody_particle* out, uint64_t capacity);
 int nbody_cuda_set_owned_particles(nbody_cuda_sim* sim, const nbody_particle* particles, uint64_t n);
 /* Per-step load rebalancing, the host-side rule on its own (no device needed): from last step's slice boundaries
