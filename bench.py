@@ -538,6 +538,7 @@ def multi_gpu_check(args, rank, world, local_rank, make_sim, partitioned, dist, 
         gperm1 = np.concatenate([p[5] for p in parts])
         same_order = gperm1.shape == rperm1.shape and bool(np.array_equal(gperm1, rperm1))
         p2p_sum = int(sum(p[6] for p in parts))
+        # (bars: |dx| < 1e-5 of a unit box, |dv| < 2e-3 where speeds reach 8 in the core of the Plummer model; measured 8e-7 and 4.7e-4 at 8 ranks)
         # after `steps` steps: the same trajectories by particle identity (the runs differ by FP32 round-off, so a particle that sits
         # 1e-7 from a cell boundary may sort differently: the order itself is only compared on the first step)
         complete = got.shape == r.shape and bool(np.array_equal(np.sort(gperm), np.arange(n2, dtype=np.uint32)))
@@ -549,7 +550,7 @@ def multi_gpu_check(args, rank, world, local_rank, make_sim, partitioned, dist, 
                "all_particles_present": complete, "max_abs_dx": dx, "max_abs_dv": dv,
                "m2l_interactions_sum": int(sum(p[3] for p in parts)), "m2l_interactions_1gpu": int(rst["m2l_interactions"]),
                "device_bytes_per_rank": [int(p[4]) for p in parts], "device_bytes_1gpu": int(rst["device_bytes"])}
-        ok = same_order and complete and dx < 1e-5 and dv < 1e-3 and p2p_sum == rp2p1
+        ok = same_order and complete and dx < 1e-5 and dv < 2e-3 and p2p_sum == rp2p1
         if not partitioned:
             res["state_identical_on_all_ranks"] = all(abs(float(x) - float(hs[0])) <= 1e-9 * abs(float(hs[0])) for x in hs)
             ok = ok and res["state_identical_on_all_ranks"]
