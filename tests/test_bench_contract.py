@@ -24,6 +24,10 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] == 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]
+    # BASELINE config 1 beside it: the unmodified NaiveSimulation on all 4096 particles of the uniform cube, 10 steps (the one
+    # same-configuration ratio; our arm reports the same configuration under the same key)
+    c1 = d["config1"]
+    assert c1["same_config_as_ours_config1"] is True and c1["value"] > 0 and c1["unit"] == "particle-steps/s" and "4096" in c1["workload"]
 
 
 def test_other_ranks_of_the_reference_arm_exit_quietly():
