@@ -3,8 +3,10 @@
 Only tests/, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline /
 ``--impl reference`` leg may import this package (see oracle/oracle.cpp header).
 ``liboracle.so`` is the restatement; ``_ref/libnaive_ref.so`` is the UNMODIFIED
-reference naive path (/root/reference/src/naive_simulation.cpp) compiled by
-oracle/Makefile.
+reference naive path (/root/reference/src/naive_simulation.cpp) and
+``_ref/libclref.so`` the reference's OpenCL C device kernels compiled for the host
+(oracle/ref_cl_harness.cpp), both built by oracle/Makefile from the sources where
+they lie.
 """
 import ctypes as C
 import os
@@ -15,6 +17,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 _REF = None
+_CLREF = None
 
 u8p = np.ctypeslib.ndpointer(np.uint8, flags="C")
 u32p = np.ctypeslib.ndpointer(np.uint32, flags="C")
@@ -209,3 +212,112 @@ def ref_naive_run(particles12, force_constant, dt, steps=1):
     P = np.ascontiguousarray(particles12, np.float32).copy()
     t = R.ref_naive_run(P.shape[0], P, force_constant, dt, steps)
     return P, t
+
+
+# ---- the reference's OpenCL C kernels on the host (oracle/_ref/libclref.so) ----------------------------------------------
+def clref_lib():
+    """The reference's device kernels compiled for the host (oracle/ref_cl_harness.cpp), or None when never built."""
+    global _CLREF
+    if _CLREF is None:
+        path = os.path.join(_HERE, "_ref", "libclref.so")
+        if not os.path.exists(path):
+            if os.path.isdir("/root/reference/src"):
+                build()
+            else:
+                return None
+        R = C.CDLL(path)
+        R.clref_type_sizes.argtypes = [u32p]
+        R.clref_create.argtypes = [C.c_uint32, u32p, u64p, u32p, u32p, u8p, u32p, i32p, u32p, f32p, C.c_uint32, f32p]
+        R.clref_create.restype = C.c_void_p
+        R.clref_free.argtypes = [C.c_void_p]
+        R.clref_node_geometry.argtypes = [C.c_void_p, f32p]
+        R.clref_compute_moments.argtypes = [C.c_void_p, C.c_int]
+        R.clref_compute_moments.restype = C.c_uint32
+        R.clref_get_moments.argtypes = [C.c_void_p, f32p, f32p, f32p, f32p]
+        R.clref_traverse.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        R.clref_get_lists.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        R.clref_forces.argtypes = [C.c_void_p, C.c_int, C.c_uint32, f32p, f32p]
+        R.clref_integrate.argtypes = [C.c_void_p, f32p, f32p, C.c_float, C.c_void_p]
+        R.clref_pair_force.argtypes = [C.c_float, C.c_float, f32p, f32p, f32p, f32p]
+        _CLREF = R
+    return _CLREF
+
+
+# names of the nine sizes verify.cl reports, in its index order (include/nbody/device/types.h:18-27)
+CLREF_TYPE_NAMES = ("leaf_t", "node_t", "leaf_value_t", "node_value_t", "leaf_moment_t", "node_moment_t", "leaf_field_t",
+                    "node_field_t", "interaction_t")
+
+
+def clref_type_sizes():
+    out = np.zeros(9, np.uint32)
+    clref_lib().clref_type_sizes(out)
+    return dict(zip(CLREF_TYPE_NAMES, (int(v) for v in out)))
+
+
+def clref_pair_force(qa, qb, pa, pb):
+    """Force on a and on b from the reference's leaf_moment_field + leaf_field_to_force (src/field.cl:17-32, src/force.cl:4-10)."""
+    fa, fb = np.zeros(3, np.float32), np.zeros(3, np.float32)
+    clref_lib().clref_pair_force(qa, qb, np.asarray(pa, np.float32)[:3].copy(), np.asarray(pb, np.float32)[:3].copy(), fa, fb)
+    return fa, fb
+
+
+class ClRef:
+    """The reference's kernels run on one octree: `tree` is an oracle.Tree, `particles12_sorted` the particle records in
+    tree order. The octree itself is the oracle's (glade is absent); everything computed ON it comes from the reference's
+    own kernel sources."""
+
+    def __init__(self, tree, particles12_sorted, bounds=(1.0, 1.0, 1.0)):
+        R = clref_lib()
+        if R is None:
+            raise RuntimeError("oracle/_ref/libclref.so is not built")
+        self.tree = tree
+        P = np.ascontiguousarray(particles12_sorted, np.float32)
+        self.n = P.shape[0]
+        self._h = R.clref_create(tree.num_nodes, tree.depth, tree.prefix, tree.leaf_index, tree.leaf_count, tree.has_children,
+                                 np.ascontiguousarray(tree.child_off.reshape(-1)), tree.parent_off, tree.sibling,
+                                 np.asarray(bounds, np.float32)[:3].copy(), self.n, P)
+
+    def geometry(self):
+        g = np.empty((self.tree.num_nodes, 4), np.float32)
+        clref_lib().clref_node_geometry(self._h, g)
+        return g
+
+    def traverse(self):
+        """(node interactions = M2L pairs, leaf interactions = P2P pairs, rounds), in the order the reference's host loop
+        appends them (src/open_cl_simulation.cpp:242-266)."""
+        a, b, r = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        clref_lib().clref_traverse(self._h, C.byref(a), C.byref(b), C.byref(r))
+        node = np.empty((a.value, 2), np.uint32)
+        leaf = np.empty((b.value, 2), np.uint32)
+        clref_lib().clref_get_lists(self._h, _ptr(node), _ptr(leaf))
+        return node, leaf, r.value
+
+    def moments(self, repair_d5=True):
+        """compute_moments_from_leafs + the upsweep (src/moment.cl); returns (launches, charge, dipole, cross, trace)."""
+        m = self.tree.num_nodes
+        launches = clref_lib().clref_compute_moments(self._h, 1 if repair_d5 else 0)
+        q = np.empty(m, np.float32)
+        d, c, t = (np.empty((m, 4), np.float32) for _ in range(3))
+        clref_lib().clref_get_moments(self._h, q, d, c, t)
+        return launches, q, d, c, t
+
+    def forces(self, repair_d7=True, node_local_size=None):
+        """(leaf forces, node forces) per particle: the two arrays the reference's integration adds
+        (src/open_cl_simulation.cpp:589-590). Call traverse() and moments() first."""
+        if node_local_size is None:
+            node_local_size = 1 << max(5, int(np.ceil(np.log2(max(self.n, 1)))))  # every leaf of every target node is reached
+        lf, nf = np.empty((self.n, 4), np.float32), np.empty((self.n, 4), np.float32)
+        clref_lib().clref_forces(self._h, 1 if repair_d7 else 0, node_local_size, lf, nf)
+        return lf[:, :3].copy(), nf[:, :3].copy()
+
+    def integrate(self, leaf_forces, node_forces, dt):
+        lf = np.zeros((self.n, 4), np.float32); lf[:, :3] = leaf_forces
+        nf = np.zeros((self.n, 4), np.float32); nf[:, :3] = node_forces
+        out = np.empty((self.n, 12), np.float32)
+        clref_lib().clref_integrate(self._h, lf, nf, dt, _ptr(out))
+        return out
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _CLREF is not None:
+            _CLREF.clref_free(self._h)
+            self._h = None

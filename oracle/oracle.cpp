@@ -17,12 +17,24 @@
 //    restated here is the contract inferred from how the reference CONSUMES
 //    node_t (include/nbody/device/types.h:124-141 and the sites listed at each
 //    function below).
-//  * traversal / MAC   — restates src/interaction.cl:22-99 and the host
-//    partition loop src/open_cl_simulation.cpp:247-266 exactly (FP32, no FMA
-//    contraction); the reference ships no test vectors for it.
+//  * traversal / MAC   — PINNED on a given octree: orc_traverse() restates
+//    src/interaction.cl:22-99 and the host partition loop
+//    src/open_cl_simulation.cpp:247-266 (FP32, no FMA contraction) and is
+//    checked entry for entry, in order, against the reference's own
+//    find_interactions kernel compiled for the host from the file where it lies
+//    (oracle/_ref/libclref.so, oracle/ref_cl_harness.cpp) and against the golden
+//    lists generated from it (tests/test_reference_kernels.py,
+//    tests/golden/clref_golden.npz). One deliberate difference: a childless
+//    root keeps its self pair (see orc_traverse).
+//  * expansions        — orc_fmm_field() at order 1 IS the reference's far field
+//    (monopole at the target cell centre, src/field.cl:35-47,187-210) and at
+//    order 2 carries the reference's leaf moments (src/moment.cl:27-54): both
+//    checked against the reference's kernels to FP32 round-off (same test file).
+//    Orders 2..5 continue that scheme; the reference has nothing to compare.
 //  * accelerations     — FP64 direct sum with the reference's softening
-//    (src/field.cl:22-24) and the naive loop's pair structure
-//    (src/naive_simulation.cpp:7-46, with the x-only delta defect D1 fixed).
+//    (src/field.cl:22-24, pair term checked against leaf_moment_field) and the
+//    naive loop's pair structure (src/naive_simulation.cpp:7-46, with the x-only
+//    delta defect D1 fixed).
 //
 // Build: see oracle/Makefile (g++ -O2 -ffp-contract=off).
 // ============================================================================

@@ -1,7 +1,8 @@
 """Generates tests/golden/fmm_path.npz: keys, permutation, octree, interaction lists and FP64 direct-sum accelerations of
 small seeded particle sets, computed by the ORACLE (oracle/oracle.cpp). These fixtures pin the restatement against drift
-and give the GPU tests a committed answer that does not depend on rebuilding the oracle; they are NOT reference-pinned
-(the reference's FMM path cannot be built or run: no glade, no OpenCL).
+and give the GPU tests a committed answer that does not depend on rebuilding the oracle. The octree in them is the oracle's
+(glade is absent: unpinned); the interaction lists are, entry for entry, the ones the reference's own find_interactions kernel
+produces on that octree (tests/test_reference_kernels.py asserts it against tests/golden/clref_golden.npz).
 Run in the authoring container: python tests/golden/make_fmm_golden.py"""
 import os
 import sys

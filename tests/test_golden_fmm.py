@@ -1,7 +1,8 @@
 """The committed FMM-path fixtures (tests/golden/fmm_path.npz, written by tests/golden/make_fmm_golden.py from the oracle):
 on CPU the oracle must still reproduce them bit for bit (drift guard); on a B200 the CUDA path, called through the C ABI,
 must match them — bit-exact keys, permutation, octree and interaction lists, accelerations within 1e-3 RMS of the stored
-FP64 direct sum. Not reference-pinned: see the generator's header."""
+FP64 direct sum. The lists in the fixture are the reference's own kernel's lists (tests/test_reference_kernels.py); the octree is
+the oracle's (glade absent: unpinned), see the generator's header."""
 import os
 
 import numpy as np
