@@ -200,11 +200,12 @@ float nbody_cuda_next_time_step(const nbody_cuda_config* cfg, float acc_max);
  * accumulator step() returns), step count, the time step the next step() will use, the 48-byte particle records in the
  * order particles() returns them and the permutation nbody_cuda_get_permutation returns. Layout: nbody_checkpoint_header,
  * n * 48 bytes, n * 4 bytes; little-endian; `checksum` = sum over i of (w_i + 0x9E3779B97F4A7C15) * (2 i + 1) mod 2^64, w_i the
- * 64-bit words of the particle array followed by those of the permutation (zero-padded to a whole word). Resuming reproduces the
+ * 64-bit words of the header (19 words, its checksum field taken as zero), then of the particle array, then of the permutation
+ * (zero-padded to a whole word); version 1 files, whose sum covers the two arrays only, are still read. Resuming reproduces the
  * uninterrupted run bit for bit with NBODY_FLAG_DIRECT; the FMM path sums its interaction lists in an order that depends
  * on kernel timing, so there (as between any two runs of it) the states agree to FP32 round-off, not bitwise. */
 #define NBODY_CHECKPOINT_MAGIC 0x31504b435944424eull /* the bytes "NBDYCKP1" */
-#define NBODY_CHECKPOINT_VERSION 1u
+#define NBODY_CHECKPOINT_VERSION 2u
 typedef struct nbody_checkpoint_header {
 	uint64_t magic;
 	uint32_t version;

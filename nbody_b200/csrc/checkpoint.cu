@@ -15,8 +15,6 @@
 
 #include <unistd.h>
 
-#include <cerrno>
-
 #include "common.cuh"
 
 namespace nbody {
@@ -46,9 +44,15 @@ uint64_t word_sum(const void* data, size_t bytes, uint64_t& i0) {
 	return acc;
 }
 
-uint64_t payload_checksum(const nbody_particle* particles, const uint32_t* orig, uint64_t n) {
-	uint64_t i = 0;
-	uint64_t c = word_sum(particles, (size_t) n * sizeof(nbody_particle), i);
+// Version 2 files: the sum starts with the header itself (its checksum field read as zero), so a changed time, step count,
+// next step or configuration is detected like a changed particle; version 1 files (payload only) are still read.
+uint64_t file_checksum(nbody_checkpoint_header h, const nbody_particle* particles, const uint32_t* orig, uint64_t n) {
+	uint64_t i = 0, c = 0;
+	if (h.version >= 2u) {
+		h.checksum = 0;
+		c = word_sum(&h, sizeof(h), i);
+	}
+	c += word_sum(particles, (size_t) n * sizeof(nbody_particle), i);
 	c += word_sum(orig, (size_t) n * sizeof(uint32_t), i);
 	return c;
 }
@@ -61,7 +65,7 @@ int fail_io(const std::string& what, const char* path) {
 int read_header(std::FILE* f, const char* path, nbody_checkpoint_header* h) {
 	if (std::fread(h, sizeof(*h), 1, f) != 1) { set_error(std::string("checkpoint '") + path + "' is shorter than its header"); return NBODY_ERR_INVALID; }
 	if (h->magic != NBODY_CHECKPOINT_MAGIC) { set_error(std::string("'") + path + "' is not an nbody checkpoint (bad magic)"); return NBODY_ERR_INVALID; }
-	if (h->version != NBODY_CHECKPOINT_VERSION || h->header_bytes != sizeof(nbody_checkpoint_header)) {
+	if (h->version < 1u || h->version > NBODY_CHECKPOINT_VERSION || h->header_bytes != sizeof(nbody_checkpoint_header)) {
 		set_error("checkpoint version / header size not understood by this library");
 		return NBODY_ERR_INVALID;
 	}
@@ -86,7 +90,7 @@ int write_file(const char* path, nbody_checkpoint_header h, const nbody_particle
 	h.magic = NBODY_CHECKPOINT_MAGIC;
 	h.version = NBODY_CHECKPOINT_VERSION;
 	h.header_bytes = (uint32_t) sizeof(h);
-	h.checksum = payload_checksum(particles, orig, n);
+	h.checksum = file_checksum(h, particles, orig, n);
 	// write next to the target and rename, so that an interrupted save never leaves a half-written checkpoint behind
 	const std::string tmp = std::string(path) + ".partial";
 	File f(std::fopen(tmp.c_str(), "wb"));
@@ -169,7 +173,7 @@ int nbody_cuda_checkpoint_read(const char* path, nbody_particle* particles, uint
 	if (!orig_index) { otmp.resize(n); orig_index = otmp.data(); }
 	if (std::fread(particles, sizeof(nbody_particle), n, f.get()) != n || std::fread(orig_index, sizeof(uint32_t), n, f.get()) != n)
 		return fail_io("short read from", path);
-	if (payload_checksum(particles, orig_index, n) != h.checksum) { set_error(std::string("checkpoint '") + path + "' is corrupt (checksum mismatch)"); return NBODY_ERR_INVALID; }
+	if (file_checksum(h, particles, orig_index, n) != h.checksum) { set_error(std::string("checkpoint '") + path + "' is corrupt (checksum mismatch)"); return NBODY_ERR_INVALID; }
 	return NBODY_OK;
 }
 

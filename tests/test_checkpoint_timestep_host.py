@@ -54,13 +54,32 @@ def test_checkpoint_file_layout_and_round_trip(tmp_path, n):
     assert hb == 152 and len(raw) == hb + n * 48 + n * 4
     magic, version, header_bytes, n_file, steps = struct.unpack_from("<QIIQQ", raw, 0)
     time_, next_dt, last_dt, last_amax, checksum = struct.unpack_from("<ffffQ", raw, 32)
-    assert raw[:8] == b"NBDYCKP1" and magic == nbody_b200.CHECKPOINT_MAGIC and version == 1 and header_bytes == hb
+    assert raw[:8] == b"NBDYCKP1" and magic == nbody_b200.CHECKPOINT_MAGIC and version == 2 and header_bytes == hb
     assert (n_file, steps, time_) == (n, 17, 0.125) and next_dt == np.float32(7.5e-4) and last_dt == 0 and last_amax == 0
     assert np.array_equal(np.frombuffer(raw, "<f4", n * 12, hb).reshape(n, 12), P)
     assert np.array_equal(np.frombuffer(raw, "<u4", n, hb + n * 48), orig)
-    assert checksum == layout_checksum(raw[hb:]) == hdr.checksum
+    # version 2: the sum runs over the header with its checksum field (bytes 48..55) zeroed, then the payload
+    assert checksum == layout_checksum(raw[:48] + b"\0" * 8 + raw[56:]) == hdr.checksum
     cfg_file = nbody_b200.Config.from_buffer_copy(raw[56:56 + C.sizeof(nbody_b200.Config)])
     assert cfg_file.order == 3 and cfg_file.time_step == np.float32(2e-3)
+
+
+def test_version_1_files_are_still_read(tmp_path):
+    # version 1 (written by this library before the header came under the checksum): the sum covers the two arrays only
+    path = str(tmp_path / "v2.ckp")
+    P = particles(50)
+    nbody_b200.checkpoint_write(path, P, time=0.5, steps_done=3)
+    raw = bytearray(open(path, "rb").read())
+    raw[8:12] = struct.pack("<I", 1)
+    raw[48:56] = struct.pack("<Q", layout_checksum(bytes(raw[152:])))
+    old = str(tmp_path / "v1.ckp")
+    open(old, "wb").write(bytes(raw))
+    hdr, Q, o = nbody_b200.checkpoint_read(old)
+    assert hdr.version == 1 and hdr.time == 0.5 and hdr.steps_done == 3 and np.array_equal(P, Q)
+    raw[152 + 7] ^= 0x20
+    open(old, "wb").write(bytes(raw))
+    with pytest.raises(nbody_b200.NbodyCudaError):
+        nbody_b200.checkpoint_read(old)
 
 
 def test_checkpoint_default_permutation_is_identity(tmp_path):
@@ -89,6 +108,9 @@ def test_checkpoint_rejects_damaged_files(tmp_path):
     expect_error(flipped, "corrupt")
     swapped = bytearray(raw); swapped[152:152 + 48], swapped[152 + 48:152 + 96] = raw[152 + 48:152 + 96], raw[152:152 + 48]
     expect_error(swapped, "corrupt")                                        # the checksum is order-sensitive
+    for at in (32, 36, 24, 56 + 8):                                         # time, next step, steps done, a configuration field
+        flipped = bytearray(raw); flipped[at] ^= 0x01
+        expect_error(flipped, "corrupt")                                    # (version 2: the header is under the checksum too)
     expect_error(raw[:-4], "truncated")
     expect_error(raw + b"\0" * 8, "trailing")
     expect_error(b"XXXXXXXX" + raw[8:], "magic")
