@@ -220,8 +220,10 @@ typedef struct nbody_checkpoint_header {
 	nbody_cuda_config config;
 } nbody_checkpoint_header;
 
-/* Write the state of `sim` to `path` (blocking). Distributed: the state is replicated, every rank may call it (each with
- * its own path); it is a collective only in that every rank must have finished the same step. */
+/* Write the state of `sim` to `path` (blocking). Distributed, replicated scheme: every rank holds the whole state and may call
+ * it (each with its own path); it is a collective only in that every rank must have finished the same step. Partitioned scheme
+ * (NBODY_FLAG_PARTITIONED): NBODY_ERR_STATE — a rank holds only its own particles and the file format is single-rank; save per
+ * rank with nbody_cuda_get_owned_particles + nbody_cuda_get_permutation + nbody_cuda_checkpoint_write. */
 int nbody_cuda_checkpoint_save(nbody_cuda_sim* sim, const char* path);
 /* Host-only (no device needed): read and validate the header of a checkpoint file. */
 int nbody_cuda_checkpoint_info(const char* path, nbody_checkpoint_header* header);

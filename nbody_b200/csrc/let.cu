@@ -21,12 +21,14 @@
 //       (sort.cu: merge path), local counts of the straddling cells
 //   X2  all-gather of the straddling counts (also the barrier after which the sorted arrays [1] may be overwritten)
 //   2b  gather into [1]; octree with forced splits; P2M / M2M
-//   X3  all-gather of the node counts, then the trees themselves: geometry, child/count records, first-particle indices and
-//       multipoles of every rank with grouped ncclBroadcast (an all-gather with unequal counts) over NVLink into the node arrays
-//       behind the own tree (ids [max_nodes, ...)); child pointers are rebased, first-particle indices become "imported leaf" tags
-//   3   traversal (seeds: all roots), then the halo: the P2P lists are scanned for imported leaves, those leaves get slots behind
-//       the own particles (prefix sum) and their particles are fetched from the owners' sorted arrays with NVLink loads (8f rank 4),
-//       the list entries are pointed at the slots; M2L, L2L, P2P + L2P + integrator as on one GPU
+//   X3  all-gather of the node counts, then the trees as the traversal reads them: geometry, child/count records and
+//       first-particle indices of every rank (28 bytes per node) by three ncclAllGather into equal slots behind the own tree
+//       (ids [max_nodes, ...); grouped ncclBroadcast when a rank's arrays are smaller than the largest tree); child pointers are
+//       rebased, first-particle indices become "imported leaf" tags. The multipoles do not travel here.
+//   3   traversal (seeds: all roots; it marks every imported leaf / node its lists name), then the halo: the marked leaves get
+//       slots behind the own particles (prefix sum) and their particles are fetched from the owners' sorted arrays with NVLink
+//       loads (8f rank 4), the list entries are pointed at the slots; the multipoles the M2L lists name are fetched from the
+//       owners' compact exports the same way; M2L, L2L, P2P + L2P + integrator as on one GPU
 //   X4  all-gather of {device time of stage 3, status}; X5 all-gather of the next step's splitter candidates (balance.h rule on the
 //       device: the owner of each wanted boundary position looks up the key there)
 // Host synchronisations per step: after X1 (run lengths), after X3's counts, at the end. NCCL carries control words and the trees;
