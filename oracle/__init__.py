@@ -239,6 +239,7 @@ def clref_lib():
         R.clref_forces.argtypes = [C.c_void_p, C.c_int, C.c_uint32, f32p, f32p]
         R.clref_integrate.argtypes = [C.c_void_p, f32p, f32p, C.c_float, C.c_void_p]
         R.clref_pair_force.argtypes = [C.c_float, C.c_float, f32p, f32p, f32p, f32p]
+        R.clref_can_approx.argtypes = [C.c_uint64, f32p, f32p, f32p, f32p, u8p]
         _CLREF = R
     return _CLREF
 
@@ -259,6 +260,16 @@ def clref_pair_force(qa, qb, pa, pb):
     fa, fb = np.zeros(3, np.float32), np.zeros(3, np.float32)
     clref_lib().clref_pair_force(qa, qb, np.asarray(pa, np.float32)[:3].copy(), np.asarray(pb, np.float32)[:3].copy(), fa, fb)
     return fa, fb
+
+
+def clref_can_approx(pos_a, dim_a, pos_b, dim_b):
+    """find_interactions' can_approx (src/interaction.cl:64-82) for n pairs of cells given by lower corner [n,3] and edge [n]."""
+    n = len(dim_a)
+    pa = np.zeros((n, 4), np.float32); pa[:, :3] = pos_a
+    pb = np.zeros((n, 4), np.float32); pb[:, :3] = pos_b
+    out = np.zeros(n, np.uint8)
+    clref_lib().clref_can_approx(n, pa, np.ascontiguousarray(dim_a, np.float32), pb, np.ascontiguousarray(dim_b, np.float32), out)
+    return out.astype(bool)
 
 
 class ClRef:

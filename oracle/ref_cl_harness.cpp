@@ -314,6 +314,25 @@ void clref_integrate(void* h, const float* leaf_force4, const float* node_force4
 	}
 }
 
+// find_interactions' verdict on arbitrary pairs of cells: pair k = two childless, non-empty nodes with lower corner pos_*4[4k..4k+2]
+// and edge dim_*[k]; one launch over the n interactions (A_k, B_k); out[k] = can_approx (src/interaction.cl:76-82).
+// Lets a test put the product's acceptance test next to the reference's kernel on geometry no octree would produce.
+void clref_can_approx(std::uint64_t n, const float* pos_a4, const float* dim_a, const float* pos_b4, const float* dim_b, std::uint8_t* out) {
+	std::vector<node_t> nodes(2 * n + 1);
+	std::memset(nodes.data(), 0, sizeof(node_t) * nodes.size());
+	std::vector<interaction_t> pending(n), fresh(64 * n, interaction_t{});
+	for (std::uint64_t k = 0; k < n; ++k) {
+		node_t& a = nodes[1 + 2 * k];
+		node_t& b = nodes[2 + 2 * k];
+		a.position = float4(pos_a4[4 * k], pos_a4[4 * k + 1], pos_a4[4 * k + 2], 0.0f); a.dimensions = float4(dim_a[k], dim_a[k], dim_a[k], 0.0f);
+		b.position = float4(pos_b4[4 * k], pos_b4[4 * k + 1], pos_b4[4 * k + 2], 0.0f); b.dimensions = float4(dim_b[k], dim_b[k], dim_b[k], 0.0f);
+		a.leaf_count = b.leaf_count = 1;
+		pending[k] = interaction_t{(index_t) (1 + 2 * k), (index_t) (2 + 2 * k), 0, 0, 0, 0};
+	}
+	launch_8x8(n, [&] { find_interactions((index_t) nodes.size(), nodes.data(), (index_t) n, pending.data(), fresh.data()); });
+	for (std::uint64_t k = 0; k < n; ++k) out[k] = fresh[64 * k].can_approx;
+}
+
 // src/field.cl:17-32 and src/force.cl:4-10 on one pair: the FORCE (charge x field) on a and on b.
 void clref_pair_force(float qa, float qb, const float* pa3, const float* pb3, float* force_a3, float* force_b3) {
 	leaf_moment_t ma{qa}, mb{qb};
