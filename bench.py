@@ -136,6 +136,22 @@ class ClockSampler:
                 "samples": len(sm), "samples_in_timed_region": len(timed), "window": window, "reasons": sorted(reasons)}
 
 
+FLAG_PARTITIONED = 128  # nbody_b200.FLAG_PARTITIONED / NBODY_FLAG_PARTITIONED (include/nbody_cuda.h)
+
+
+def arm_config(args, world):
+    """The benchmark configuration, printed under "config" by BOTH arms: the bench contract has the reference arm run "on your
+    arm's config" (a bounded sample of that workload per step; what the sample was is said in cpu_baseline.sample and
+    reference_sample). Everything here follows from the command line and the rank count alone."""
+    partitioned = world > 1 and args.scheme != "replicated"
+    return {"workload": f"{args.workload} sphere N={args.n}" if args.workload == "plummer" else f"{args.workload} N={args.n}",
+            "order": args.order, "leaf_capacity": args.leaf_capacity, "mac_ratio": 0.5, "softening": 0.01,
+            "integrator": "kick-drift", "l2_policy": "working set (>1 GB of lists and particle state per step) exceeds the 126 MB L2",
+            "partition": ("morton-range, partitioned state + locally essential tree" if partitioned else
+                          "morton-range, replicated state" if world > 1 else "single"),
+            "flags": args.flags | (FLAG_PARTITIONED if partitioned else 0)}
+
+
 def reference_arm(args, rank, emit):
     """--impl reference: the unmodified reference CPU path (naive_simulation.cpp via oracle/_ref;
     the oracle port if the reference was never compiled) on a bounded sample of the same workload."""
@@ -160,7 +176,9 @@ def reference_arm(args, rank, emit):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload} N={args.n} (reference arm: first {ns} particles of it)", "sample_n": ns},
+        "config": arm_config(args, int(os.environ.get("WORLD_SIZE", "1"))),
+        "reference_sample": {"n": ns, "what": f"each step = NaiveSimulation::step() on the first {ns} particles of the workload named in config "
+                                              "(the solver fields of config describe the measured arm; the reference's direct sum has none of them)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "reference" if have_ref else "port",
                          "sample": f"NaiveSimulation::step() x{args.steps} on the first {ns} particles of the workload "
                                    f"(O(N^2), single-threaded by construction; {pairs_per_s:.3e} pair-interactions/s; "
@@ -448,12 +466,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
             "ms_per_step": 1e3 * elapsed / K, "device_ms_per_step": counts.pop("device_ms_per_step", None), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": f"{args.workload} sphere N={n}" if args.workload == "plummer" else f"{args.workload} N={n}",
-                       "order": args.order, "leaf_capacity": args.leaf_capacity, "mac_ratio": 0.5, "softening": 0.01,
-                       "integrator": "kick-drift", "l2_policy": "working set (>1 GB of lists and particle state per step) exceeds the 126 MB L2",
-                       "partition": ("morton-range, partitioned state + locally essential tree" if partitioned else
-                                     "morton-range, replicated state" if world > 1 else "single"), "flags": base_flags,
-                       "library": os.path.basename(nbody_b200.LIB_PATH), "cpu_binding": numa},
+            "config": arm_config(args, world), "library": os.path.basename(nbody_b200.LIB_PATH), "cpu_binding": numa,
             "clocks": clocks, "e2e": e2e, "gpu_launches": K * launches_per_step(sim, world, counts.get("n_levels"), partitioned),
             "roofline": roof,
             "p2p_fp32_tflops": {"tree_p2p_kernel": p2p_tf, "tree_p2p_frac_of_peak": p2p_tf / peak,

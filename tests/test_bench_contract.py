@@ -23,7 +23,15 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert d["steps"] == 2 and d["higher_is_better"] is True and d["vs_baseline"] is None and d["value"] > 0
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] == 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert "workload" in d["config"]
+    # the reference arm runs "on the measured arm's config" (bench contract): the same dictionary both arms print, from the command line alone;
+    # what each step actually executed is said beside it
+    import argparse
+    sys.path.insert(0, ROOT)
+    import bench
+    ours = bench.arm_config(argparse.Namespace(workload="plummer", n=1 << 24, order=4, leaf_capacity=48, scheme="auto", flags=0), 1)
+    assert d["config"] == ours and d["config"]["workload"] == "plummer sphere N=16777216" and d["config"]["partition"] == "single"
+    assert d["reference_sample"]["n"] == 1024 and "first 1024 particles" in d["cpu_baseline"]["sample"]
+    assert bench.arm_config(argparse.Namespace(workload="plummer", n=1 << 24, order=4, leaf_capacity=48, scheme="auto", flags=0), 8)["flags"] == 128
     # BASELINE config 1 beside it: the unmodified NaiveSimulation on all 4096 particles of the uniform cube, 10 steps (the one
     # same-configuration ratio; our arm reports the same configuration under the same key)
     c1 = d["config1"]
