@@ -35,10 +35,12 @@ void exp_chain(int p, const float* src, int ns, const float* cB_child, const flo
 	if (p == 2) run_chain<2>(src, ns, cB_child, cB, cA, cA_child, tgt, nt, eps, field, M_out, L_out);
 	if (p == 3) run_chain<3>(src, ns, cB_child, cB, cA, cA_child, tgt, nt, eps, field, M_out, L_out);
 	if (p == 4) run_chain<4>(src, ns, cB_child, cB, cA, cA_child, tgt, nt, eps, field, M_out, L_out);
+	if (p == 5) run_chain<5>(src, ns, cB_child, cB, cA, cA_child, tgt, nt, eps, field, M_out, L_out);
 }
 void exp_derivatives(int p, float x, float y, float z, float eps2, float* D) {
 	if (p == 2) { float d[ncoef(2)]; Expansion<2>::derivatives(x, y, z, eps2, d); for (int a = 0; a < ncoef(2); ++a) D[a] = d[a]; }
 	if (p == 3) { float d[ncoef(3)]; Expansion<3>::derivatives(x, y, z, eps2, d); for (int a = 0; a < ncoef(3); ++a) D[a] = d[a]; }
 	if (p == 4) { float d[ncoef(4)]; Expansion<4>::derivatives(x, y, z, eps2, d); for (int a = 0; a < ncoef(4); ++a) D[a] = d[a]; }
+	if (p == 5) { float d[ncoef(5)]; Expansion<5>::derivatives(x, y, z, eps2, d); for (int a = 0; a < ncoef(5); ++a) D[a] = d[a]; }
 }
 }

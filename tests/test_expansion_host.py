@@ -30,14 +30,14 @@ def multi_indices(p):
 
 
 def test_index_order_matches_oracle(hostlib):
-    for p in (2, 3, 4):
+    for p in (2, 3, 4, 5):
         mi = multi_indices(p)
         assert hostlib.exp_ncoef(p) == len(mi)
         for a, (i, j, k) in enumerate(mi):
             assert hostlib.exp_index(i, j, k) == a
 
 
-@pytest.mark.parametrize("p", [2, 3, 4])
+@pytest.mark.parametrize("p", [2, 3, 4, 5])
 def test_derivative_tensor_against_finite_differences(hostlib, p):
     x = np.array([0.31, -0.22, 0.47]); eps2 = 1e-4
     D = np.zeros(hostlib.exp_ncoef(p), np.float32)
@@ -57,7 +57,7 @@ def test_derivative_tensor_against_finite_differences(hostlib, p):
         assert abs(D[a] - ref) <= 2e-3 * max(1.0, abs(ref)) * (1 + sum(n)), (n, D[a], ref)
 
 
-@pytest.mark.parametrize("p,tol", [(2, 6e-2), (3, 1.5e-2), (4, 4e-3)])
+@pytest.mark.parametrize("p,tol", [(2, 6e-2), (3, 1.5e-2), (4, 4e-3), (5, 1.5e-3)])
 def test_operator_chain_converges(hostlib, p, tol):
     rng = np.random.default_rng(1)
     s = 0.125
