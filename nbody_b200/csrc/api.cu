@@ -342,6 +342,7 @@ using namespace nbody;
 extern "C" {
 
 void nbody_cuda_default_config(nbody_cuda_config* cfg) {
+	if (!cfg) return;
 	std::memset(cfg, 0, sizeof(*cfg));
 	cfg->abi_version = NBODY_CUDA_ABI_VERSION;
 	cfg->bounds[0] = cfg->bounds[1] = cfg->bounds[2] = 1.0f; cfg->bounds[3] = 0.0f;
@@ -360,6 +361,7 @@ void nbody_cuda_default_config(nbody_cuda_config* cfg) {
 }
 
 void nbody_cuda_tuned_config(nbody_cuda_config* cfg) {
+	if (!cfg) return;
 	nbody_cuda_default_config(cfg);
 	cfg->leaf_capacity = 48;
 }
