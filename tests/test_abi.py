@@ -151,3 +151,43 @@ def test_cpp_wrapper_compiles_and_fails_loudly_without_a_device(tmp_path):
     assert r.returncode == 0 and "failures 3" in r.stdout and "no CPU fallback" in r.stdout, r.stdout + r.stderr
     r = subprocess.run([str(tmp_path / "nbody_main"), "--n", "100", "--steps", "1", "--quiet", "--csv", "none"], capture_output=True, text=True, timeout=60)
     assert r.returncode == 1 and "no CPU fallback" in r.stderr
+
+
+REFERENCE_LAYOUT_CLIENT = r"""
+// the REFERENCE's own headers (include/nbody/simulation.h, include/nbody/device/types.h) next to the C ABI's record
+#include <cstddef>
+#include <vector>
+#include "nbody/device/types.h"
+#include "nbody/simulation.h"
+#include "nbody_cuda.h"
+using RefSim = nbody::Simulation<nbody::device::scalar_t, nbody::device::vector_t>;
+using P = RefSim::Particle;
+static_assert(sizeof(P) == sizeof(nbody_particle) && sizeof(P) == 48, "size");
+static_assert(alignof(P) == 16, "alignment");
+static_assert(offsetof(P, position) == offsetof(nbody_particle, position), "position");
+static_assert(offsetof(P, velocity) == offsetof(nbody_particle, velocity), "velocity");
+static_assert(offsetof(P, mass) == offsetof(nbody_particle, mass), "mass");
+static_assert(offsetof(P, charge) == offsetof(nbody_particle, charge), "charge");
+int main() {
+	// the cast INTEGRATION.md section 2 uses, on values: a reference Particle read through the boundary record
+	std::vector<P> v(3, P({1.0f, 2.0f, 3.0f, 0.0f}, {4.0f, 5.0f, 6.0f, 0.0f}, 7.0f, 8.0f));
+	const nbody_particle* q = reinterpret_cast<const nbody_particle*>(v.data());
+	for (int i = 0; i < 3; ++i)
+		if (q[i].position[0] != 1.0f || q[i].position[2] != 3.0f || q[i].velocity[1] != 5.0f || q[i].mass != 7.0f || q[i].charge != 8.0f) return 1;
+	return 0;
+}
+"""
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/include"), reason="needs the reference's headers (/root/reference)")
+def test_reference_particle_type_is_the_boundary_record(tmp_path):
+    """The reference's Simulation<float, vector_t>::Particle, compiled from the reference's OWN headers (with the 6-typedef
+    CL/cl2.hpp shim of oracle/shim), has the size, alignment and field offsets of nbody_particle: the reinterpret_cast a
+    maintainer's binding uses is layout-exact."""
+    import subprocess
+    src = tmp_path / "layout.cpp"
+    src.write_text(REFERENCE_LAYOUT_CLIENT)
+    exe = str(tmp_path / "layout")
+    subprocess.check_call(["g++", "-std=c++14", "-Wall", "-Wextra", "-Werror", "-Wno-invalid-offsetof", "-I" + os.path.join(ROOT, "oracle", "shim"),
+                           "-I/root/reference/include", "-I" + os.path.join(ROOT, "include"), str(src), "-o", exe])
+    assert subprocess.run([exe]).returncode == 0
