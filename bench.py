@@ -196,6 +196,23 @@ def reference_arm(args, rank, emit):
     dt1 = time.perf_counter() - t0
     line["config1"] = {"workload": "uniform cube N=4096, 10 steps (BASELINE configs[0])", "value": 4096 * 10 / dt1, "unit": UNIT,
                        "ms_per_step": 1e2 * dt1, "cores": 1, "kind": "reference" if have_ref else "port", "same_config_as_ours_config1": True}
+    # For the record, the reference's FMM path itself on the same configuration: its OpenCL kernels compiled for the host
+    # (oracle/_ref/libclref.so), one thread, on the oracle's octree (glade is not in the reference tree). What an OpenCL CPU device
+    # would execute for OpenClSimulation::step(); its direct sum above is the faster of the two at these sizes, hence the headline.
+    try:
+        if oracle.clref_lib() is not None:
+            keys = oracle.morton_keys(P1[:, 0:3], (1.0, 1.0, 1.0))
+            t0 = time.perf_counter()
+            sk, perm = oracle.sort_keys(keys)
+            tree = oracle.Tree(sk, (1.0, 1.0, 1.0), 8, 21)
+            _, pairs = oracle.ClRef(tree, P1[perm]).step(args.dt, repair=True, node_local_size=32)
+            dtf = time.perf_counter() - t0
+            line["config1"]["reference_fmm_kernels_on_host"] = {
+                "value": 4096 / dtf, "unit": UNIT, "ms_per_step": 1e3 * dtf, "steps": 1, "cores": 1, "interaction_pairs": pairs,
+                "what": "src/{moment,interaction,field,force}.cl compiled for the host, host defects D5/D7 repaired, octree by the oracle; "
+                        "2-7 % RMS from direct summation (profiles/r02z_reference_kernels_on_host.md)"}
+    except Exception as exc:  # noqa: BLE001 — informational only
+        line["config1"]["reference_fmm_kernels_on_host"] = {"unavailable": str(exc)[:120]}
     emit(line)
 
 

@@ -240,6 +240,8 @@ def clref_lib():
         R.clref_integrate.argtypes = [C.c_void_p, f32p, f32p, C.c_float, C.c_void_p]
         R.clref_pair_force.argtypes = [C.c_float, C.c_float, f32p, f32p, f32p, f32p]
         R.clref_can_approx.argtypes = [C.c_uint64, f32p, f32p, f32p, f32p, u8p]
+        R.clref_step.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_float, C.c_void_p]
+        R.clref_step.restype = C.c_uint64
         _CLREF = R
     return _CLREF
 
@@ -327,6 +329,12 @@ class ClRef:
         out = np.empty((self.n, 12), np.float32)
         clref_lib().clref_integrate(self._h, lf, nf, dt, _ptr(out))
         return out
+
+    def step(self, dt, repair=True, node_local_size=32):
+        """moments + traversal + fields + forces + integration in one call; returns (particles [n,12] in the same order, interactions)."""
+        out = np.empty((self.n, 12), np.float32)
+        pairs = clref_lib().clref_step(self._h, 1 if repair else 0, node_local_size, dt, _ptr(out))
+        return out, int(pairs)
 
     def __del__(self):
         if getattr(self, "_h", None) and _CLREF is not None:

@@ -314,6 +314,11 @@ void clref_integrate(void* h, const float* leaf_force4, const float* node_force4
 	}
 }
 
+// One force evaluation + integration with the kernels above, in one call (no Python between the stages): what an OpenCL CPU device
+// would execute for OpenClSimulation::step() (src/open_cl_simulation.cpp:70-106) once the octree exists, on ONE host thread.
+// Returns the number of field slots the reference's design allocates (leaf + node), for the record.
+std::uint64_t clref_step(void* h, int repair, std::uint32_t node_local_size, float dt, float* particles12_out);
+
 // find_interactions' verdict on arbitrary pairs of cells: pair k = two childless, non-empty nodes with lower corner pos_*4[4k..4k+2]
 // and edge dim_*[k]; one launch over the n interactions (A_k, B_k); out[k] = can_approx (src/interaction.cl:76-82).
 // Lets a test put the product's acceptance test next to the reference's kernel on geometry no octree would produce.
@@ -341,6 +346,17 @@ void clref_pair_force(float qa, float qb, const float* pa3, const float* pb3, fl
 	const force_t fa = leaf_field_to_force(ma, f.field_a, a), fb = leaf_field_to_force(mb, f.field_b, b);
 	force_a3[0] = fa.force.x; force_a3[1] = fa.force.y; force_a3[2] = fa.force.z;
 	force_b3[0] = fb.force.x; force_b3[1] = fb.force.y; force_b3[2] = fb.force.z;
+}
+
+std::uint64_t clref_step(void* h, int repair, std::uint32_t node_local_size, float dt, float* particles12_out) {
+	State& s = *(State*) h;
+	clref_compute_moments(h, repair);
+	std::uint64_t a, b, r;
+	clref_traverse(h, &a, &b, &r);
+	std::vector<float> lf(4 * s.leafs.size()), nf(4 * s.leafs.size());
+	clref_forces(h, repair, node_local_size, lf.data(), nf.data());
+	clref_integrate(h, lf.data(), nf.data(), dt, particles12_out);
+	return a + b;
 }
 
 }  // extern "C"

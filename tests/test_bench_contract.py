@@ -36,6 +36,9 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     # same-configuration ratio; our arm reports the same configuration under the same key)
     c1 = d["config1"]
     assert c1["same_config_as_ours_config1"] is True and c1["value"] > 0 and c1["unit"] == "particle-steps/s" and "4096" in c1["workload"]
+    # ... and the reference's FMM kernels themselves, compiled for the host, on that configuration (informational)
+    f = c1["reference_fmm_kernels_on_host"]
+    assert ("unavailable" in f) or (f["value"] > 0 and f["cores"] == 1 and f["interaction_pairs"] == 327049)
 
 
 def test_other_ranks_of_the_reference_arm_exit_quietly():
