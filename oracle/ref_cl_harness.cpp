@@ -4,7 +4,7 @@
 // The reference's OpenCL C device kernels, compiled for the HOST from the files where they lie
 // under /root/reference/src (oracle/Makefile, target `clref`, output oracle/_ref/libclref.so):
 //   interaction.cl, field.cl, verify.cl   — byte for byte as they are;
-//   moment.cl, force.cl                   — a generated copy under oracle/_ref/gen/ in which the OpenCL vector
+//   moment.cl, force.cl                   — a transient copy under oracle/_ref/gen/ (deleted after the link) in which the OpenCL vector
 //                                           literal "(vector_t) (" reads "make_vector_t(" (a C++ compiler parses
 //                                           the literal as a cast of a comma expression); nothing else changes.
 // oracle/shim_cl/opencl_c_host.h supplies float4, dot, sqrt, min, the work-item functions and the

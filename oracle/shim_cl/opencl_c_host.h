@@ -39,7 +39,7 @@ inline float4& operator+=(float4& a, float4 b) { a = a + b; return a; }
 inline float dot(float4 a, float4 b) { return ((a.x * b.x + a.y * b.y) + a.z * b.z) + a.w * b.w; }
 // (vector_t)(a, b, c, d) literals (src/moment.cl:43-54, src/force.cl:35,66) are the one construct a C++ compiler reads
 // differently (a cast of a comma expression): interaction.cl, field.cl and verify.cl have none and compile as they are;
-// for moment.cl and force.cl the Makefile writes a copy into oracle/_ref/gen/ with exactly the token sequence
+// for moment.cl and force.cl the Makefile writes a transient copy into oracle/_ref/gen/ (removed after the link) with exactly the token sequence
 // "(vector_t) (" replaced by "make_vector_t(" and nothing else changed.
 inline float4 make_vector_t(float a, float b, float c, float d) { return float4(a, b, c, d); }
 
