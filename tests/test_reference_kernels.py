@@ -171,6 +171,7 @@ def test_kernels_reproduce_the_golden_file():
     ("uniform", 3000, 8, (1.0, 0.5, 0.25), 21),         # not a cube: the MAC reads dimensions.x only
     ("uniform", 3000, 8, (1.5, 1.5, 1.5), 21),          # not a power of two: cell corners as index * size in both
     ("uniform", 9, 8, (1.0, 1.0, 1.0), 21),             # the smallest tree that splits
+    ("two_galaxies", 131072, 8, (1.0, 1.0, 1.0), 21),   # 26 million pairs (BASELINE config 2, uniform 2^20, 182 million pairs: the report under profiles/)
 ])
 def test_traversal_beyond_the_golden_cases(kind, n, cap, bounds, max_depth):
     P = workloads.GENERATORS[kind](n)
