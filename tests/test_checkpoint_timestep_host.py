@@ -219,3 +219,24 @@ def test_denormal_softening_is_rejected():
     with pytest.raises(nbody_b200.NbodyCudaError) as e:
         nbody_b200.CudaSimulation([1, 1, 1], workloads.uniform_cube(8), 1e-3, softening=1e-30)
     assert "denormal" in str(e.value)
+
+
+@pytest.mark.parametrize("field,value,needle", [
+    ("order", 1, "order must be"), ("order", 6, "order must be"), ("max_depth", 0, "max_depth"), ("max_depth", 22, "max_depth"),
+    ("leaf_capacity", 0, "leaf_capacity"), ("softening", -1.0, "softening"), ("mac_ratio", 0.0, "mac_ratio"), ("integrator", 2, "integrator"),
+    ("low_order_tau", -0.1, "low_order_tau"), ("time_step_eta", -1.0, "time_step_eta"), ("abi_version", 99, "abi_version"),
+])
+def test_configuration_errors_are_reported_before_any_device_is_touched(field, value, needle):
+    """nbody_cuda_create validates its configuration first (api.cu: validate), so every argument error reaches the caller as
+    NBODY_ERR_INVALID with its message even on a box without a GPU — where every VALID configuration fails with "no CUDA device"."""
+    with pytest.raises(nbody_b200.NbodyCudaError) as e:
+        nbody_b200.CudaSimulation([1, 1, 1], workloads.uniform_cube(8), 1e-3, **{field: value})
+    assert needle in str(e.value) and "no CUDA device" not in str(e.value), str(e.value)
+
+
+def test_bounds_and_time_step_rules():
+    for bounds, dt, kw, needle in (([1.0, 0.0, 1.0], 1e-3, {}, "bounds"), ([1, 1, 1], 1e-3, dict(time_step_min=2e-3, time_step_max=1e-3), "min <= max"),
+                                   ([1, 1, 1], 0.0, dict(time_step_eta=0.1), "time_step > 0")):
+        with pytest.raises(nbody_b200.NbodyCudaError) as e:
+            nbody_b200.CudaSimulation(bounds, workloads.uniform_cube(8), dt, **kw)
+        assert needle in str(e.value), str(e.value)
