@@ -191,3 +191,50 @@ def test_reference_particle_type_is_the_boundary_record(tmp_path):
     subprocess.check_call(["g++", "-std=c++14", "-Wall", "-Wextra", "-Werror", "-Wno-invalid-offsetof", "-I" + os.path.join(ROOT, "oracle", "shim"),
                            "-I/root/reference/include", "-I" + os.path.join(ROOT, "include"), str(src), "-o", exe])
     assert subprocess.run([exe]).returncode == 0
+
+
+def test_every_entry_point_rejects_null_arguments():
+    """A binding written in another language passes NULL sooner or later: every entry point answers with an error code (or does nothing)
+    instead of crashing. None of these paths touches a device."""
+    L = nbody_b200.load_library()
+    N = None
+    f32 = C.c_float
+    calls = {
+        "get_particles": lambda: L.nbody_cuda_get_particles(N, N, 0),
+        "get_permutation": lambda: L.nbody_cuda_get_permutation(N, N, 0),
+        "get_accelerations": lambda: L.nbody_cuda_get_accelerations(N, N, 0),
+        "get_keys": lambda: L.nbody_cuda_get_keys(N, N, 0),
+        "get_tree": lambda: L.nbody_cuda_get_tree(N, N, 0, N, N, N, N, N, N, N, N, N),
+        "get_lists": lambda: L.nbody_cuda_get_lists(N, N, N, N, N),
+        "get_expansions": lambda: L.nbody_cuda_get_expansions(N, N, N, 0),
+        "get_stats": lambda: L.nbody_cuda_get_stats(N, N),
+        "set_time_step": lambda: L.nbody_cuda_set_time_step(N, f32(1e-3)),
+        "get_time_step": lambda: L.nbody_cuda_get_time_step(N, N, N, N),
+        "get_time": lambda: L.nbody_cuda_get_time(N, N, N),
+        "checkpoint_save": lambda: L.nbody_cuda_checkpoint_save(N, b"/tmp/never_written.ckp"),
+        "checkpoint_load": lambda: L.nbody_cuda_checkpoint_load(N, N, N),
+        "checkpoint_info": lambda: L.nbody_cuda_checkpoint_info(N, N),
+        "checkpoint_read": lambda: L.nbody_cuda_checkpoint_read(N, N, N, 0),
+        "checkpoint_write": lambda: L.nbody_cuda_checkpoint_write(N, N, N, N),
+        "owned_range": lambda: L.nbody_cuda_owned_range(N, N, N),
+        "get_owned_particles": lambda: L.nbody_cuda_get_owned_particles(N, N, 0),
+        "set_owned_particles": lambda: L.nbody_cuda_set_owned_particles(N, N, 0),
+        "set_particles": lambda: L.nbody_cuda_set_particles(N, N, 0),
+        "step": lambda: L.nbody_cuda_step(N, N),
+        "group_step": lambda: L.nbody_cuda_group_step(N, 2, N),
+        "create_group": lambda: L.nbody_cuda_create_group(N, N, 0, 2, N),
+        "create_distributed": lambda: L.nbody_cuda_create_distributed(N, N, 0, 0, 0, 0, 1, N, N),
+        "comm_unique_id": lambda: L.nbody_cuda_comm_unique_id(N),
+        "sort_runs": lambda: L.nbody_cuda_sort_runs(0, N, 0, N, 1, N, N),
+        "direct_field": lambda: L.nbody_cuda_direct_field(0, N, 0, N, 0, f32(0.01), N, N, 1),
+        "rebalance": lambda: L.nbody_cuda_rebalance(2, N, N, f32(0.5), N),
+        "create": lambda: L.nbody_cuda_create(N, N, 0, N),
+    }
+    for name, call in calls.items():
+        assert call() != 0, name
+        assert len(L.nbody_cuda_last_error()) > 0, name
+    # the void ones, and the rule that returns a value
+    L.nbody_cuda_destroy(N); L.nbody_cuda_destroy_group(N, 2); L.nbody_cuda_default_config(N); L.nbody_cuda_tuned_config(N)
+    assert L.nbody_cuda_num_particles(N) == 0 and L.nbody_cuda_next_time_step(N, f32(1.0)) == 0.0
+    exercised = set(calls) | {"destroy", "destroy_group", "default_config", "tuned_config", "num_particles", "next_time_step", "last_error"}
+    assert {s.replace("nbody_cuda_", "") for s in nbody_b200.EXPORTED_SYMBOLS} == exercised
