@@ -240,3 +240,37 @@ def test_bounds_and_time_step_rules():
         with pytest.raises(nbody_b200.NbodyCudaError) as e:
             nbody_b200.CudaSimulation(bounds, workloads.uniform_cube(8), dt, **kw)
         assert needle in str(e.value), str(e.value)
+
+
+def test_checkpoint_reader_survives_mutated_files(tmp_path):
+    """1500 random mutations of a valid file (bit flips, truncation, trailing bytes, random words in the header, zeroed runs): the
+    reader never crashes, and accepts a file only if it is byte-identical to the original (the header is under the checksum too)."""
+    rng = np.random.default_rng(5)
+    path = str(tmp_path / "a.ckp")
+    nbody_b200.checkpoint_write(path, particles(37), rng.permutation(37).astype(np.uint32), time=0.5, steps_done=3)
+    raw = open(path, "rb").read()
+    bad = str(tmp_path / "m.ckp")
+    rejected = 0
+    for _ in range(1500):
+        b = bytearray(raw)
+        kind = rng.integers(0, 5)
+        if kind == 0:
+            for _ in range(rng.integers(1, 4)):
+                b[rng.integers(0, len(b))] ^= 1 << rng.integers(0, 8)
+        elif kind == 1:
+            b = b[:rng.integers(0, len(b))]
+        elif kind == 2:
+            b += bytes(rng.integers(0, 256, rng.integers(1, 64)).astype(np.uint8))
+        elif kind == 3:
+            at = rng.integers(0, 152 - 8)
+            b[at:at + 8] = bytes(rng.integers(0, 256, 8).astype(np.uint8))
+        else:
+            at = rng.integers(0, len(b) - 16)
+            b[at:at + 16] = bytes(16)
+        open(bad, "wb").write(bytes(b))
+        try:
+            nbody_b200.checkpoint_read(bad)
+            assert bytes(b) == raw
+        except nbody_b200.NbodyCudaError:
+            rejected += 1
+    assert rejected > 1400
