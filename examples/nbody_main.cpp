@@ -117,7 +117,16 @@ int main(int argc, char** argv) {
 		else if (a == "--restart") restart = next();
 		else if (a == "--distribution") distribution = next();
 		else if (a == "--capacity") capacity = (unsigned) std::strtoul(next(), nullptr, 10);
-		else { std::cerr << "unknown option " << a << "\n"; return 2; }
+		else if (a == "--help" || a == "-h") {
+			std::cout << "usage: nbody_main [--n N] [--steps K] [--dt DT] [--seed S] [--distribution uniform|plummer|two-galaxies] [--capacity C]\n"
+			             "                  [--eta ETA] [--csv FILE|none] [--csv-max ROWS] [--checkpoint FILE] [--restart FILE] [--quiet]\n";
+			return 0;
+		}
+		else { std::cerr << "unknown option " << a << " (--help lists them)\n"; return 2; }
+	}
+	if (restart.empty() && (n == 0 || n > 0xfffffff0ull)) {
+		std::cerr << "--n must be a particle count in [1, 2^32-16)\n";
+		return 2;
 	}
 	if (distribution != "uniform" && distribution != "plummer" && distribution != "two-galaxies") {
 		std::cerr << "unknown distribution " << distribution << " (uniform, plummer, two-galaxies)\n";
