@@ -50,7 +50,7 @@ def measured_peaks():
 
 def measured_traffic(kernel, args):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full
-    capture of exactly this workload (profiles/r01k_traffic.json); None for any other workload."""
+    capture of exactly this workload (profiles/r02_traffic.json); None for any other workload."""
     p = os.path.join(ROOT, "profiles", "r02_traffic.json")
     try:
         with open(p) as f:
