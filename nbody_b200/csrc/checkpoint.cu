@@ -8,6 +8,7 @@
 // and needs no device; only save (device -> file) and load (file -> new simulation) touch CUDA.
 #include <cerrno>
 #include <cmath>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <memory>
@@ -46,11 +47,15 @@ uint64_t word_sum(const void* data, size_t bytes, uint64_t& i0) {
 
 // Version 2 files: the sum starts with the header itself (its checksum field read as zero), so a changed time, step count,
 // next step or configuration is detected like a changed particle; version 1 files (payload only) are still read.
-uint64_t file_checksum(nbody_checkpoint_header h, const nbody_particle* particles, const uint32_t* orig, uint64_t n) {
+// (Works on the bytes of the very object that is written to / was read from the file, tail padding included: a by-value copy of
+// the struct need not preserve padding bytes.)
+uint64_t file_checksum(const nbody_checkpoint_header& h, const nbody_particle* particles, const uint32_t* orig, uint64_t n) {
 	uint64_t i = 0, c = 0;
 	if (h.version >= 2u) {
-		h.checksum = 0;
-		c = word_sum(&h, sizeof(h), i);
+		unsigned char raw[sizeof(nbody_checkpoint_header)];
+		std::memcpy(raw, &h, sizeof(raw));
+		std::memset(raw + offsetof(nbody_checkpoint_header, checksum), 0, sizeof(uint64_t));
+		c = word_sum(raw, sizeof(raw), i);
 	}
 	c += word_sum(particles, (size_t) n * sizeof(nbody_particle), i);
 	c += word_sum(orig, (size_t) n * sizeof(uint32_t), i);
@@ -90,6 +95,10 @@ int write_file(const char* path, nbody_checkpoint_header h, const nbody_particle
 	h.magic = NBODY_CHECKPOINT_MAGIC;
 	h.version = NBODY_CHECKPOINT_VERSION;
 	h.header_bytes = (uint32_t) sizeof(h);
+	{  // the padding behind the last field is written as zeros, whatever the caller's struct held there
+		constexpr size_t used = offsetof(nbody_checkpoint_header, config) + sizeof(nbody_cuda_config);
+		std::memset(reinterpret_cast<unsigned char*>(&h) + used, 0, sizeof(h) - used);
+	}
 	h.checksum = file_checksum(h, particles, orig, n);
 	// write next to the target and rename, so that an interrupted save never leaves a half-written checkpoint behind
 	const std::string tmp = std::string(path) + ".partial";
